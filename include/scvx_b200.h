@@ -1,0 +1,126 @@
+/* scvx_b200.h — C ABI of the B200-native linearise-and-discretise path.
+ *
+ * The reference (BenChung/SuccessiveConvexification) has no FFI for this path: the boundary is
+ * the pair of Julia functions
+ *     Dynamics.linearize_dynamics(states, tf_guess, base_dt, cache)   reference dynamics.jl:321-334
+ *     Dynamics.predict_state(x, uk, up, sigma, dt, pinfo, cache)       reference dynamics.jl:315-317
+ * (+ simulate_zygote / sensitivity_zygote, dynamics.jl:308-313).  The entry points below are what a
+ * Julia `ccall` shim (julia/SCvxB200.jl) binds to replace them.
+ *
+ * Conventions
+ *   - Everything is FP64.  Arrays are column-major with Julia's index order, i.e. a Julia
+ *     Array{Float64,3} of size (14, n_nodes, B) is passed as-is.
+ *   - State x(14) = [m, r(3), v(3), q(4, scalar first), w(3)]  (dynamics.jl:13-19); control u(3).
+ *   - One unit of work = one interval (trajectory b, nodes i and i+1):
+ *       inp = [x_i ; u_i ; u_{i+1} ; sigma_b]   (21)            dynamics.jl:318-320, 136-139
+ *   - Output block per interval: 14 x 23 column-major  [ endpoint | A(14) | B-(3) | B+(3) | Sigma | z ]
+ *     (accumulator layout of old_dynamics.jl:84-98; rocketland.jl:22-23 acc_width = 23).
+ *     Columns 1..21 are LinRes.derivative (master.jl:90-93), column 0 is LinRes.endpoint,
+ *     z = endpoint - D*inp (old_dynamics.jl:139, 150-153).
+ *   - Pointers may be host or device memory (detected with cudaPointerGetAttributes); device
+ *     pointers must live on the context's first device.  Host pointers stay caller-owned and must
+ *     remain valid until the call returns (calls are synchronous for host pointers).  For device
+ *     pointers the work is enqueued on the context stream (scvx_set_stream) and the call returns
+ *     without synchronising.
+ *   - Return value: 0 on success, negative error code otherwise; message via scvx_last_error()
+ *     (thread-local).  No C++ exception crosses the ABI.  There is no CPU fallback.
+ */
+#ifndef SCVX_B200_H
+#define SCVX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scvx_ctx scvx_ctx;
+
+enum { SCVX_OK = 0, SCVX_ERR_ARG = -1, SCVX_ERR_CUDA = -2, SCVX_ERR_STATE = -3, SCVX_ERR_NOMEM = -4 };
+
+/* aero_kind: ExoatmosphericData (master.jl:8) vs AtmosphericData (master.jl:10-16) */
+enum { SCVX_AERO_EXO = 0, SCVX_AERO_TABLE = 1 };
+/* RK4 stage rule: LITERAL reproduces dynamics.jl:126-128 (stage increments not scaled by the
+ * sub-step); TEXTBOOK scales them (classical RK4).  SURVEY.md §0.4 */
+enum { SCVX_MODE_LITERAL = 0, SCVX_MODE_TEXTBOOK = 1 };
+/* tables of AtmosphericData (drag_itrp, lift_itrp, trq_itrp; aerodynamics.jl:19-21) */
+enum { SCVX_TABLE_DRAG = 0, SCVX_TABLE_LIFT = 1, SCVX_TABLE_TORQUE = 2 };
+/* kernel selection: AUTO picks the fastest validated path */
+enum { SCVX_KERNEL_AUTO = 0, SCVX_KERNEL_DUALWARP = 1, SCVX_KERNEL_STAGED = 2 };
+
+/* Mirror of ProbInfo (master.jl:73-83) + AtmosphericData scalars (master.jl:14-15) + Tmin
+ * (master.jl:21, used by the thrust-lower-bound rows rocketland.jl:199-200).  3x3 column-major. */
+typedef struct scvx_probinfo {
+    double a, g0, sos;
+    double jB[9], jBi[9];
+    double rTB[3], rFB[3];
+    double force_scalar, length_scalar;
+    double Tmin;
+    int32_t aero_kind;
+    int32_t _pad;
+} scvx_probinfo;
+
+/* Number of visible CUDA devices (0 if none / no driver). */
+int scvx_device_count(void);
+/* Thread-local message of the last failing call on this thread. */
+const char* scvx_last_error(void);
+/* Library / ABI version (major*1000 + minor). */
+int scvx_version(void);
+/* sizeof(scvx_probinfo) the library was built with (binding sanity check). */
+int scvx_sizeof_probinfo(void);
+
+/* Opaque context: owns device memory, streams and the staged tables of every listed device.
+ * Stands in for the reference's IntegratorCache (master.jl:113-120; ctor dynamics.jl:258-286).
+ * n_dev > 1 shards the trajectories of host-pointer calls over the devices in contiguous blocks. */
+int scvx_create(scvx_ctx** out, const int* device_ids, int n_dev);
+void scvx_destroy(scvx_ctx* ctx);
+
+/* n == 1: parameters shared by all trajectories; n == B: one record per trajectory
+ * (mass / thrust-bound sweeps).  `p` is a host pointer. */
+int scvx_set_params(scvx_ctx* ctx, const scvx_probinfo* p, int n);
+
+/* Upload one aero table.  `samples` (host): n_cos x n_mach column-major exactly as the reshape at
+ * aerodynamics.jl:19-21; axes are the StepRangeLen's cos0:dcos:.. and mach0:dmach:..
+ * (aerodynamics.jl:17-18).  prefiltered == 0: the library runs the cubic-B-spline prefilter
+ * (Interpolations.jl BSpline(Cubic(Line(OnGrid())))) on the device; prefiltered != 0: `samples`
+ * already holds the (n_cos+2) x (n_mach+2) coefficients. */
+int scvx_set_aero_table(scvx_ctx* ctx, int which, const double* samples, int n_cos, int n_mach,
+                        double cos0, double dcos, double mach0, double dmach, int prefiltered);
+/* Read back the staged coefficients ((n_cos+2) x (n_mach+2) doubles, host pointer). */
+int scvx_get_aero_coefficients(scvx_ctx* ctx, int which, double* out);
+
+/* linearize_dynamics for B trajectories of n_nodes nodes each (dynamics.jl:321-334 with the
+ * rk4 + forward-Jacobian body of dynamics.jl:112-134, 311-313).
+ *   X          14 x n_nodes x B       U  3 x n_nodes x B       sigma  B
+ *   out_blocks 14 x 23 x (n_nodes-1) x B                          (required)
+ *   out_lin_err 14 x (n_nodes-1) x B   endpoint_n - x_{n+1}       (optional, may be NULL; rocketland.jl:130, 256)
+ *   out_tlb     4 x n_nodes x B        [-u/|u| ; Tmin - |u|]      (optional, may be NULL; rocketland.jl:199-200, 261-263)
+ * B == 1 reproduces one call of the reference function. */
+int scvx_linearize_batch(scvx_ctx* ctx, const double* X, const double* U, const double* sigma,
+                         double base_dt, int npts, int mode, int n_nodes, int B,
+                         double* out_blocks, double* out_lin_err, double* out_tlb);
+
+/* predict_state / simulate_zygote for every interval (value only): out 14 x (n_nodes-1) x B. */
+int scvx_predict_batch(scvx_ctx* ctx, const double* X, const double* U, const double* sigma,
+                       double base_dt, int npts, int mode, int n_nodes, int B, double* out_endpoints);
+
+/* Stream used for device-pointer calls on the first device (a cudaStream_t; NULL = library stream). */
+int scvx_set_stream(scvx_ctx* ctx, void* cuda_stream);
+/* Kernel selection (SCVX_KERNEL_*). */
+int scvx_set_kernel(scvx_ctx* ctx, int which);
+/* Wait for everything enqueued by this context. */
+int scvx_synchronize(scvx_ctx* ctx);
+/* Number of kernels the library launched since the context was created (all devices). */
+int64_t scvx_launch_count(scvx_ctx* ctx);
+/* Device-event duration (ms) of the kernels of the last device-pointer linearize/predict call on the
+ * first device; synchronises the stream. */
+int scvx_last_kernel_ms(scvx_ctx* ctx, double* ms);
+
+/* Dependent-chain-free FP64 FMA microbenchmark on the first device: writes the sustained DFMA rate
+ * in TFLOP/s (2 flop per FMA).  Roofline denominator of the FP64-pipe-bound kernels. */
+int scvx_measure_fp64_peak(scvx_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCVX_B200_H */

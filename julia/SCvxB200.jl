@@ -1,0 +1,166 @@
+# SCvxB200.jl — Julia `ccall` shim over libscvx_b200.so (C ABI: include/scvx_b200.h).
+#
+# Drop-in for the linearise-and-discretise path of BenChung/SuccessiveConvexification.  Include it
+# AFTER the reference's master.jl; it adds methods to the reference's own entry points
+#     Dynamics.linearize_dynamics(states, tf_guess, base_dt, cache)     (reference dynamics.jl:321-334)
+#     Dynamics.predict_state(x, uk, up, sigma, dt, pinfo, cache)         (reference dynamics.jl:315-317)
+# that dispatch on a cache whose `sim_prob` field (typed `Any`, master.jl:113-120) holds a
+# `SCvxB200.Context`.  Everything else of the reference (SOCP assembly, Mosek solve, initial guess,
+# trust-region logic) is untouched.
+#
+# Written without a Julia toolchain in the build container (see INTEGRATION.md); it is mirrored 1:1 by
+# the ctypes binding successiveconvexification_b200/_lib.py, which the test-suite exercises.
+module SCvxB200
+
+using ..RocketlandDefns
+import ..Dynamics
+
+const LIB = get(ENV, "SCVX_B200_LIB", joinpath(@__DIR__, "..", "successiveconvexification_b200", "libscvx_b200.so"))
+
+const MODE_LITERAL = Cint(0)    # reproduces dynamics.jl:126-128
+const MODE_TEXTBOOK = Cint(1)
+const AERO_EXO = Cint(0)
+const AERO_TABLE = Cint(1)
+
+# mirror of scvx_probinfo
+struct CProbInfo
+    a::Cdouble; g0::Cdouble; sos::Cdouble
+    jB::NTuple{9,Cdouble}; jBi::NTuple{9,Cdouble}
+    rTB::NTuple{3,Cdouble}; rFB::NTuple{3,Cdouble}
+    force_scalar::Cdouble; length_scalar::Cdouble
+    Tmin::Cdouble
+    aero_kind::Int32; _pad::Int32
+end
+
+function CProbInfo(info::ProbInfo, Tmin::Float64)
+    atm = info.aero isa AtmosphericData
+    CProbInfo(info.a, info.g0, info.sos, Tuple(info.jB), Tuple(info.jBi), Tuple(info.rTB), Tuple(info.rFB),
+              atm ? info.aero.force_scalar : 0.0, atm ? info.aero.length_scalar : 0.0, Tmin,
+              atm ? AERO_TABLE : AERO_EXO, Int32(0))
+end
+
+last_error() = unsafe_string(ccall((:scvx_last_error, LIB), Cstring, ()))
+check(rc::Integer) = rc == 0 ? nothing : error("scvx_b200 error $rc: $(last_error())")   # reference style: rocketland.jl:275
+
+device_count() = Int(ccall((:scvx_device_count, LIB), Cint, ()))
+version() = Int(ccall((:scvx_version, LIB), Cint, ()))
+
+mutable struct Context
+    handle::Ptr{Cvoid}
+    npts::Int
+    mode::Cint
+    function Context(device_ids::Vector{Int}=[0]; npts::Int=10, mode::Cint=MODE_LITERAL)
+        @assert ccall((:scvx_sizeof_probinfo, LIB), Cint, ()) == sizeof(CProbInfo)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        ids = Cint.(device_ids)
+        check(ccall((:scvx_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cint}, Cint), h, ids, length(ids)))
+        ctx = new(h[], npts, mode)
+        finalizer(c -> (c.handle != C_NULL && ccall((:scvx_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.handle); c.handle = C_NULL), ctx)
+        return ctx
+    end
+end
+
+function set_params!(ctx::Context, recs::Vector{CProbInfo})
+    check(ccall((:scvx_set_params, LIB), Cint, (Ptr{Cvoid}, Ptr{CProbInfo}, Cint), ctx.handle, recs, length(recs)))
+end
+
+# `samples`: the n_cos x n_mach matrix handed to `interpolate(...)` at aerodynamics.jl:19-21
+function set_aero_table!(ctx::Context, which::Integer, samples::Matrix{Float64}, aoa::AbstractRange, mach::AbstractRange;
+                         prefiltered::Bool=false)
+    check(ccall((:scvx_set_aero_table, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Cint, Cdouble, Cdouble, Cdouble, Cdouble, Cint),
+                ctx.handle, which, samples, length(aoa), length(mach), first(aoa), step(aoa), first(mach), step(mach),
+                prefiltered ? 1 : 0))
+end
+
+function aero_coefficients(ctx::Context, which::Integer, n_cos::Integer, n_mach::Integer)
+    out = Matrix{Float64}(undef, n_cos + 2, n_mach + 2)
+    check(ccall((:scvx_get_aero_coefficients, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}), ctx.handle, which, out))
+    return out
+end
+
+set_kernel!(ctx::Context, which::Integer) = check(ccall((:scvx_set_kernel, LIB), Cint, (Ptr{Cvoid}, Cint), ctx.handle, which))
+set_stream!(ctx::Context, stream::Ptr{Cvoid}) = check(ccall((:scvx_set_stream, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.handle, stream))
+synchronize(ctx::Context) = check(ccall((:scvx_synchronize, LIB), Cint, (Ptr{Cvoid},), ctx.handle))
+launch_count(ctx::Context) = ccall((:scvx_launch_count, LIB), Int64, (Ptr{Cvoid},), ctx.handle)
+
+function last_kernel_ms(ctx::Context)
+    ms = Ref{Cdouble}(0.0)
+    check(ccall((:scvx_last_kernel_ms, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}), ctx.handle, ms))
+    return ms[]
+end
+
+function measure_fp64_peak(ctx::Context)
+    tf = Ref{Cdouble}(0.0)
+    check(ccall((:scvx_measure_fp64_peak, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}), ctx.handle, tf))
+    return tf[]
+end
+
+# Batched entry points.  X: 14 x n_nodes x B, U: 3 x n_nodes x B, sigma: B  (plain Julia arrays, column-major).
+function linearize_batch(ctx::Context, X::Array{Float64,3}, U::Array{Float64,3}, sigma::Vector{Float64}, base_dt::Float64;
+                         lin_err::Bool=true, tlb::Bool=true)
+    n_nodes, B = size(X, 2), size(X, 3)
+    blocks = Array{Float64,4}(undef, 14, 23, n_nodes - 1, B)
+    err = lin_err ? Array{Float64,3}(undef, 14, n_nodes - 1, B) : Array{Float64,3}(undef, 0, 0, 0)
+    tl = tlb ? Array{Float64,3}(undef, 4, n_nodes, B) : Array{Float64,3}(undef, 0, 0, 0)
+    GC.@preserve X U sigma blocks err tl begin
+        check(ccall((:scvx_linearize_batch, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Cint, Cint, Cint,
+                     Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                    ctx.handle, X, U, sigma, base_dt, ctx.npts, ctx.mode, n_nodes, B,
+                    blocks, lin_err ? pointer(err) : Ptr{Cdouble}(C_NULL), tlb ? pointer(tl) : Ptr{Cdouble}(C_NULL)))
+    end
+    return blocks, err, tl
+end
+
+function predict_batch(ctx::Context, X::Array{Float64,3}, U::Array{Float64,3}, sigma::Vector{Float64}, base_dt::Float64)
+    n_nodes, B = size(X, 2), size(X, 3)
+    out = Array{Float64,3}(undef, 14, n_nodes - 1, B)
+    GC.@preserve X U sigma out begin
+        check(ccall((:scvx_predict_batch, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Cint, Cint, Cint, Ptr{Cdouble}),
+                    ctx.handle, X, U, sigma, base_dt, ctx.npts, ctx.mode, n_nodes, B, out))
+    end
+    return out
+end
+
+# IntegratorCache(prob, info) replacement (reference dynamics.jl:258-260): context + parameters + tables.
+# `aero_samples = (drag, lift, torque, aoa_range, mach_range)` are the matrices / ranges of aerodynamics.jl:17-21.
+function make_cache(prob::DescentProblem, info::ProbInfo; device_ids::Vector{Int}=[0], aero_samples=nothing)
+    ctx = Context(device_ids)
+    set_params!(ctx, [CProbInfo(info, prob.Tmin)])
+    if info.aero isa AtmosphericData
+        aero_samples === nothing && error("AtmosphericData needs aero_samples = (drag, lift, torque, aoa, mach)")
+        drag, lift, trq, aoa, mach = aero_samples
+        set_aero_table!(ctx, 0, drag, aoa, mach); set_aero_table!(ctx, 1, lift, aoa, mach); set_aero_table!(ctx, 2, trq, aoa, mach)
+    end
+    return IntegratorCache(ctx, nothing, nothing, nothing, Any[1.0, info], info)
+end
+
+end # module
+
+# ---- methods added to the reference's own entry points -------------------------------------------------
+function _scvx_ctx(cache::IntegratorCache)
+    cache.sim_prob isa SCvxB200.Context || error("cache does not hold a SCvxB200.Context")
+    return cache.sim_prob::SCvxB200.Context
+end
+
+# Replaces the method of dynamics.jl:321-334 (same signature); the cache must hold a device context.
+function Dynamics.linearize_dynamics(states::Array{LinPoint,1}, tf_guess::Float64, base_dt::Float64, cache::IntegratorCache)
+    ctx = _scvx_ctx(cache)
+    n = length(states)
+    X = Array{Float64,3}(undef, 14, n, 1); U = Array{Float64,3}(undef, 3, n, 1)
+    for i = 1:n
+        X[:, i, 1] .= states[i].state; U[:, i, 1] .= states[i].control
+    end
+    blocks, _, _ = SCvxB200.linearize_batch(ctx, X, U, [tf_guess], base_dt; lin_err=false, tlb=false)
+    return [LinRes(blocks[:, 1, i, 1], blocks[:, 2:22, i, 1]) for i = 1:n-1]
+end
+
+# Replaces dynamics.jl:315-317.
+function Dynamics.predict_state(initial_state, uk, up, sigma, dt, pinfo, cache::IntegratorCache)
+    ctx = _scvx_ctx(cache)
+    X = zeros(14, 2, 1); U = zeros(3, 2, 1)
+    X[:, 1, 1] .= initial_state; U[:, 1, 1] .= uk; U[:, 2, 1] .= up
+    return SCvxB200.predict_batch(ctx, X, U, [Float64(sigma)], Float64(dt))[:, 1, 1]
+end

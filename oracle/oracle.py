@@ -79,6 +79,12 @@ def _tb(tables):
 def _params(infos):
     """infos: ProbInfo-like object(s) with .to_c() -> ctypes array + count."""
     from successiveconvexification_b200.defns import CProbInfo
+    assert lib().oracle_sizeof_probinfo() == ctypes.sizeof(CProbInfo)
+    if isinstance(infos, np.ndarray):       # structured PROBINFO_DTYPE array (workloads.probinfo_array)
+        arr = np.ascontiguousarray(infos)
+        assert arr.dtype.itemsize == ctypes.sizeof(CProbInfo)
+        keep = (CProbInfo * arr.shape[0]).from_buffer_copy(arr.tobytes())
+        return keep, arr.shape[0]
     if not isinstance(infos, (list, tuple)):
         infos = [infos]
     arr = (CProbInfo * len(infos))(*[i.to_c() for i in infos])

@@ -1,0 +1,428 @@
+// scvx_api.cu — context management and the C ABI declared in include/scvx_b200.h.
+//
+// A context owns, per device: the staged spline tables, the parameter records, two pipeline slots of
+// staging buffers + streams (host-pointer calls are cut into trajectory chunks so that the H2D copy of
+// chunk c+1, the kernels of chunk c and the D2H copy of chunk c-1 overlap), and launch bookkeeping.
+// Trajectories are independent (reference dynamics.jl:324-332 reads only nodes i, i+1), so multi-device
+// contexts shard them in contiguous blocks with no exchange step.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "scvx_kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(SCVX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    double *dX = nullptr, *dU = nullptr, *dS = nullptr, *dOut = nullptr, *dErr = nullptr, *dTlb = nullptr, *dEnd = nullptr;
+    size_t capX = 0, capU = 0, capS = 0, capOut = 0, capErr = 0, capTlb = 0, capEnd = 0;
+};
+
+struct Dev {
+    int id = 0;
+    Slot slot[2];
+    double* coef[3] = { nullptr, nullptr, nullptr };
+    int n1 = 0, n2 = 0;
+    double x0 = 0, dx = 1, y0 = 0, dy = 1;
+    scvx_probinfo* dP = nullptr;
+    int nP = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void* scratch = nullptr;           // STAGED kernel scratch (stage records)
+    size_t scratch_cap = 0;
+};
+
+}  // namespace
+
+struct scvx_ctx {
+    std::vector<Dev> devs;
+    cudaStream_t user_stream = nullptr;
+    bool have_user_stream = false;
+    int kernel = SCVX_KERNEL_AUTO;
+    int64_t launches = 0;
+    bool timed = false;
+    std::vector<scvx_probinfo> hP;
+};
+
+namespace {
+
+int grow(double** p, size_t* cap, size_t need_doubles) {
+    if (need_doubles <= *cap) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc((void**)p, need_doubles * sizeof(double));
+    if (e != cudaSuccess) return fail(SCVX_ERR_NOMEM, "cudaMalloc(%zu B) failed: %s", need_doubles * sizeof(double), cudaGetErrorString(e));
+    *cap = need_doubles;
+    return 0;
+}
+
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+ScvxTables tables_of(const Dev& d) {
+    ScvxTables t;
+    t.drag = d.coef[SCVX_TABLE_DRAG]; t.lift = d.coef[SCVX_TABLE_LIFT];
+    t.n1 = d.n1; t.n2 = d.n2; t.x0 = d.x0; t.inv_dx = 1.0 / d.dx; t.y0 = d.y0; t.inv_dy = 1.0 / d.dy;
+    return t;
+}
+
+int check_ready(scvx_ctx* c, int B) {
+    if (c->hP.empty()) return fail(SCVX_ERR_STATE, "scvx_set_params has not been called");
+    if ((int)c->hP.size() != 1 && (int)c->hP.size() != B)
+        return fail(SCVX_ERR_ARG, "parameter count %d must be 1 or B=%d", (int)c->hP.size(), B);
+    bool need_tables = false;
+    for (const auto& p : c->hP) if (p.aero_kind == SCVX_AERO_TABLE) { need_tables = true; break; }
+    if (need_tables) {
+        const Dev& d = c->devs[0];
+        if (!d.coef[SCVX_TABLE_DRAG] || !d.coef[SCVX_TABLE_LIFT])
+            return fail(SCVX_ERR_STATE, "aero_kind=TABLE needs the drag and lift tables (scvx_set_aero_table)");
+    }
+    return 0;
+}
+
+// Launch the linearisation kernels for `bt` on device `d`, stream `s`.
+int launch_linearize(scvx_ctx* c, Dev& d, const ScvxBatch& bt, cudaStream_t s) {
+    const ScvxTables tb = tables_of(d);
+    int k = c->kernel;
+    if (k == SCVX_KERNEL_AUTO) k = SCVX_KERNEL_DUALWARP;
+    (void)k;
+    CK(scvx_launch_dualwarp(bt, tb, s));
+    c->launches += 1;
+    return 0;
+}
+
+int launch_predict(scvx_ctx* c, Dev& d, const ScvxBatch& bt, cudaStream_t s) {
+    CK(scvx_launch_predict(bt, tables_of(d), s));
+    c->launches += 1;
+    return 0;
+}
+
+// Run one call. predict=false: linearize. Handles host pointers (chunked, all devices) and device pointers.
+int run(scvx_ctx* c, bool predict, const double* X, const double* U, const double* sigma, double dt, int npts,
+        int mode, int n_nodes, int B, double* out_blocks, double* out_lin_err, double* out_tlb, double* out_end) {
+    if (!c) return fail(SCVX_ERR_ARG, "null context");
+    if (!X || !U || !sigma) return fail(SCVX_ERR_ARG, "X, U and sigma must be non-null");
+    if (predict ? !out_end : !out_blocks) return fail(SCVX_ERR_ARG, "output pointer is null");
+    if (n_nodes < 2) return fail(SCVX_ERR_ARG, "n_nodes=%d: at least two nodes (one interval) are required", n_nodes);
+    if (B < 0) return fail(SCVX_ERR_ARG, "B=%d is negative", B);
+    if (npts < 1) return fail(SCVX_ERR_ARG, "npts=%d must be >= 1", npts);
+    if (mode != SCVX_MODE_LITERAL && mode != SCVX_MODE_TEXTBOOK) return fail(SCVX_ERR_ARG, "unknown mode %d", mode);
+    if (!(dt > 0.0)) return fail(SCVX_ERR_ARG, "base_dt must be positive");
+    if (B == 0) return 0;
+    if (int rc = check_ready(c, B)) return rc;
+    const int ni = n_nodes - 1;
+    const int nP = (int)c->hP.size();
+
+    const bool dev_in = is_device_ptr(X);
+    if (dev_in != is_device_ptr(U) || dev_in != is_device_ptr(sigma) ||
+        dev_in != is_device_ptr(predict ? out_end : out_blocks) ||
+        (out_lin_err && dev_in != is_device_ptr(out_lin_err)) || (out_tlb && dev_in != is_device_ptr(out_tlb)))
+        return fail(SCVX_ERR_ARG, "all array arguments must be either host or device pointers, not a mix");
+
+    if (dev_in) {
+        Dev& d = c->devs[0];
+        CK(cudaSetDevice(d.id));
+        cudaStream_t s = c->have_user_stream ? c->user_stream : d.slot[0].stream;
+        ScvxBatch bt;
+        bt.X = X; bt.U = U; bt.sigma = sigma; bt.P = d.dP; bt.n_params = nP; bt.n_nodes = n_nodes; bt.B = B;
+        bt.dt = dt; bt.npts = npts; bt.mode = mode;
+        bt.out_blocks = out_blocks; bt.out_lin_err = out_lin_err; bt.out_tlb = out_tlb; bt.out_endpoints = out_end;
+        CK(cudaEventRecord(d.ev0, s));
+        if (int rc = predict ? launch_predict(c, d, bt, s) : launch_linearize(c, d, bt, s)) return rc;
+        CK(cudaEventRecord(d.ev1, s));
+        c->timed = true;
+        return 0;
+    }
+
+    // Host pointers: contiguous trajectory blocks per device, chunked + double-buffered inside a device.
+    const int nd = (int)c->devs.size();
+    const size_t per_traj_out = predict ? (size_t)ni * 14 : (size_t)ni * SCVX_BLOCK_DOUBLES;
+    long chunk = (long)((size_t)(64u << 20) / (per_traj_out * sizeof(double)));   // ~64 MiB of output per chunk
+    chunk = std::max(1L, chunk);
+    for (int di = 0; di < nd; ++di) {
+        Dev& d = c->devs[di];
+        const long b0 = (long)B * di / nd, b1 = (long)B * (di + 1) / nd;
+        if (b1 <= b0) continue;
+        CK(cudaSetDevice(d.id));
+        int ci = 0;
+        for (long cb = b0; cb < b1; cb += chunk, ++ci) {
+            const int nb = (int)std::min(chunk, b1 - cb);
+            Slot& sl = d.slot[ci & 1];
+            CK(cudaStreamSynchronize(sl.stream));       // previous user of this slot has drained its D2H
+            if (grow(&sl.dX, &sl.capX, (size_t)nb * n_nodes * 14) || grow(&sl.dU, &sl.capU, (size_t)nb * n_nodes * 3) ||
+                grow(&sl.dS, &sl.capS, (size_t)nb))
+                return SCVX_ERR_NOMEM;
+            CK(cudaMemcpyAsync(sl.dX, X + (size_t)cb * n_nodes * 14, (size_t)nb * n_nodes * 14 * 8, cudaMemcpyHostToDevice, sl.stream));
+            CK(cudaMemcpyAsync(sl.dU, U + (size_t)cb * n_nodes * 3, (size_t)nb * n_nodes * 3 * 8, cudaMemcpyHostToDevice, sl.stream));
+            CK(cudaMemcpyAsync(sl.dS, sigma + cb, (size_t)nb * 8, cudaMemcpyHostToDevice, sl.stream));
+            ScvxBatch bt;
+            bt.X = sl.dX; bt.U = sl.dU; bt.sigma = sl.dS; bt.P = (nP == 1) ? d.dP : d.dP + cb; bt.n_params = (nP == 1) ? 1 : nb;
+            bt.n_nodes = n_nodes; bt.B = nb; bt.dt = dt; bt.npts = npts; bt.mode = mode;
+            bt.out_blocks = nullptr; bt.out_lin_err = nullptr; bt.out_tlb = nullptr; bt.out_endpoints = nullptr;
+            if (predict) {
+                if (grow(&sl.dEnd, &sl.capEnd, (size_t)nb * ni * 14)) return SCVX_ERR_NOMEM;
+                bt.out_endpoints = sl.dEnd;
+                if (int rc = launch_predict(c, d, bt, sl.stream)) return rc;
+                CK(cudaMemcpyAsync(out_end + (size_t)cb * ni * 14, sl.dEnd, (size_t)nb * ni * 14 * 8, cudaMemcpyDeviceToHost, sl.stream));
+            } else {
+                if (grow(&sl.dOut, &sl.capOut, (size_t)nb * ni * SCVX_BLOCK_DOUBLES)) return SCVX_ERR_NOMEM;
+                bt.out_blocks = sl.dOut;
+                if (out_lin_err) { if (grow(&sl.dErr, &sl.capErr, (size_t)nb * ni * 14)) return SCVX_ERR_NOMEM; bt.out_lin_err = sl.dErr; }
+                if (out_tlb) { if (grow(&sl.dTlb, &sl.capTlb, (size_t)nb * n_nodes * 4)) return SCVX_ERR_NOMEM; bt.out_tlb = sl.dTlb; }
+                if (int rc = launch_linearize(c, d, bt, sl.stream)) return rc;
+                CK(cudaMemcpyAsync(out_blocks + (size_t)cb * ni * SCVX_BLOCK_DOUBLES, sl.dOut,
+                                   (size_t)nb * ni * SCVX_BLOCK_DOUBLES * 8, cudaMemcpyDeviceToHost, sl.stream));
+                if (out_lin_err)
+                    CK(cudaMemcpyAsync(out_lin_err + (size_t)cb * ni * 14, sl.dErr, (size_t)nb * ni * 14 * 8, cudaMemcpyDeviceToHost, sl.stream));
+                if (out_tlb)
+                    CK(cudaMemcpyAsync(out_tlb + (size_t)cb * n_nodes * 4, sl.dTlb, (size_t)nb * n_nodes * 4 * 8, cudaMemcpyDeviceToHost, sl.stream));
+            }
+        }
+    }
+    for (int di = 0; di < nd; ++di) {
+        Dev& d = c->devs[di];
+        CK(cudaSetDevice(d.id));
+        CK(cudaStreamSynchronize(d.slot[0].stream));
+        CK(cudaStreamSynchronize(d.slot[1].stream));
+    }
+    c->timed = false;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int scvx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* scvx_last_error(void) { return g_err.c_str(); }
+int scvx_version(void) { return 1000; }
+int scvx_sizeof_probinfo(void) { return (int)sizeof(scvx_probinfo); }
+
+int scvx_create(scvx_ctx** out, const int* device_ids, int n_dev) {
+    if (!out) return fail(SCVX_ERR_ARG, "out is null");
+    *out = nullptr;
+    int have = scvx_device_count();
+    if (have <= 0) return fail(SCVX_ERR_CUDA, "no CUDA device is visible: this library has no CPU fallback");
+    std::vector<int> ids;
+    if (!device_ids || n_dev <= 0) ids.push_back(0);
+    else ids.assign(device_ids, device_ids + n_dev);
+    for (int id : ids) if (id < 0 || id >= have) return fail(SCVX_ERR_ARG, "device id %d out of range (have %d)", id, have);
+    scvx_ctx* c = new (std::nothrow) scvx_ctx();
+    if (!c) return fail(SCVX_ERR_NOMEM, "out of host memory");
+    c->devs.resize(ids.size());
+    for (size_t i = 0; i < ids.size(); ++i) {
+        Dev& d = c->devs[i];
+        d.id = ids[i];
+        cudaError_t e = cudaSetDevice(d.id);
+        for (int s = 0; s < 2 && e == cudaSuccess; ++s) e = cudaStreamCreateWithFlags(&d.slot[s].stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreate(&d.ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&d.ev1);
+        if (e != cudaSuccess) { scvx_destroy(c); return fail(SCVX_ERR_CUDA, "context setup on device %d failed: %s", d.id, cudaGetErrorString(e)); }
+    }
+    *out = c;
+    return 0;
+}
+
+void scvx_destroy(scvx_ctx* c) {
+    if (!c) return;
+    for (Dev& d : c->devs) {
+        cudaSetDevice(d.id);
+        for (int s = 0; s < 2; ++s) {
+            Slot& sl = d.slot[s];
+            if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+            double* bufs[] = { sl.dX, sl.dU, sl.dS, sl.dOut, sl.dErr, sl.dTlb, sl.dEnd };
+            for (double* b : bufs) if (b) cudaFree(b);
+        }
+        for (int t = 0; t < 3; ++t) if (d.coef[t]) cudaFree(d.coef[t]);
+        if (d.dP) cudaFree(d.dP);
+        if (d.scratch) cudaFree(d.scratch);
+        if (d.ev0) cudaEventDestroy(d.ev0);
+        if (d.ev1) cudaEventDestroy(d.ev1);
+    }
+    delete c;
+}
+
+int scvx_set_params(scvx_ctx* c, const scvx_probinfo* p, int n) {
+    if (!c || !p || n < 1) return fail(SCVX_ERR_ARG, "scvx_set_params: bad arguments");
+    for (int i = 0; i < n; ++i)
+        if (p[i].aero_kind != SCVX_AERO_EXO && p[i].aero_kind != SCVX_AERO_TABLE)
+            return fail(SCVX_ERR_ARG, "record %d: unknown aero_kind %d", i, p[i].aero_kind);
+    c->hP.assign(p, p + n);
+    for (Dev& d : c->devs) {
+        CK(cudaSetDevice(d.id));
+        CK(cudaStreamSynchronize(d.slot[0].stream));
+        CK(cudaStreamSynchronize(d.slot[1].stream));
+        if (d.nP < n) {
+            if (d.dP) cudaFree(d.dP);
+            d.dP = nullptr; d.nP = 0;
+            CK(cudaMalloc((void**)&d.dP, (size_t)n * sizeof(scvx_probinfo)));
+            d.nP = n;
+        }
+        CK(cudaMemcpy(d.dP, p, (size_t)n * sizeof(scvx_probinfo), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int scvx_set_aero_table(scvx_ctx* c, int which, const double* samples, int n_cos, int n_mach, double cos0,
+                        double dcos, double mach0, double dmach, int prefiltered) {
+    if (!c || !samples) return fail(SCVX_ERR_ARG, "scvx_set_aero_table: null argument");
+    if (which < 0 || which > 2) return fail(SCVX_ERR_ARG, "unknown table id %d", which);
+    if (n_cos < 2 || n_mach < 2) return fail(SCVX_ERR_ARG, "table needs at least 2 samples per axis");
+    if (!(dcos > 0.0) || !(dmach > 0.0)) return fail(SCVX_ERR_ARG, "axis steps must be positive");
+    const size_t ncoef = (size_t)(n_cos + 2) * (n_mach + 2);
+    const int nmax = std::max(n_cos, n_mach);
+    std::vector<double> cp(nmax);
+    cp[0] = 0.25;
+    for (int m = 1; m < nmax; ++m) cp[m] = 1.0 / (4.0 - cp[m - 1]);
+    for (Dev& d : c->devs) {
+        CK(cudaSetDevice(d.id));
+        if (d.n1 && (d.n1 != n_cos || d.n2 != n_mach || d.x0 != cos0 || d.dx != dcos || d.y0 != mach0 || d.dy != dmach)) {
+            // a new geometry invalidates tables uploaded with the old one
+            for (int t = 0; t < 3; ++t) if (t != which && d.coef[t]) { cudaFree(d.coef[t]); d.coef[t] = nullptr; }
+        }
+        if (d.coef[which]) { cudaFree(d.coef[which]); d.coef[which] = nullptr; }
+        CK(cudaMalloc((void**)&d.coef[which], ncoef * sizeof(double)));
+        cudaStream_t s = d.slot[0].stream;
+        if (prefiltered) {
+            CK(cudaMemcpyAsync(d.coef[which], samples, ncoef * sizeof(double), cudaMemcpyHostToDevice, s));
+        } else {
+            double *ds = nullptr, *dt = nullptr, *dcp = nullptr;
+            CK(cudaMalloc((void**)&ds, (size_t)n_cos * n_mach * 8));
+            CK(cudaMalloc((void**)&dt, (size_t)(n_cos + 2) * n_mach * 8));
+            CK(cudaMalloc((void**)&dcp, (size_t)nmax * 8));
+            CK(cudaMemcpyAsync(ds, samples, (size_t)n_cos * n_mach * 8, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(dcp, cp.data(), (size_t)nmax * 8, cudaMemcpyHostToDevice, s));
+            CK(scvx_launch_prefilter(ds, n_cos, n_mach, dt, d.coef[which], dcp, s));
+            c->launches += 2;
+            CK(cudaStreamSynchronize(s));
+            cudaFree(ds); cudaFree(dt); cudaFree(dcp);
+        }
+        CK(cudaStreamSynchronize(s));
+        d.n1 = n_cos; d.n2 = n_mach; d.x0 = cos0; d.dx = dcos; d.y0 = mach0; d.dy = dmach;
+    }
+    return 0;
+}
+
+int scvx_get_aero_coefficients(scvx_ctx* c, int which, double* out) {
+    if (!c || !out || which < 0 || which > 2) return fail(SCVX_ERR_ARG, "scvx_get_aero_coefficients: bad arguments");
+    Dev& d = c->devs[0];
+    if (!d.coef[which]) return fail(SCVX_ERR_STATE, "table %d has not been uploaded", which);
+    CK(cudaSetDevice(d.id));
+    CK(cudaMemcpy(out, d.coef[which], (size_t)(d.n1 + 2) * (d.n2 + 2) * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int scvx_linearize_batch(scvx_ctx* c, const double* X, const double* U, const double* sigma, double base_dt,
+                         int npts, int mode, int n_nodes, int B, double* out_blocks, double* out_lin_err,
+                         double* out_tlb) {
+    try {
+        return run(c, false, X, U, sigma, base_dt, npts, mode, n_nodes, B, out_blocks, out_lin_err, out_tlb, nullptr);
+    } catch (...) { return fail(SCVX_ERR_STATE, "unexpected C++ exception"); }
+}
+
+int scvx_predict_batch(scvx_ctx* c, const double* X, const double* U, const double* sigma, double base_dt,
+                       int npts, int mode, int n_nodes, int B, double* out_endpoints) {
+    try {
+        return run(c, true, X, U, sigma, base_dt, npts, mode, n_nodes, B, nullptr, nullptr, nullptr, out_endpoints);
+    } catch (...) { return fail(SCVX_ERR_STATE, "unexpected C++ exception"); }
+}
+
+int scvx_set_stream(scvx_ctx* c, void* stream) {
+    if (!c) return fail(SCVX_ERR_ARG, "null context");
+    c->user_stream = (cudaStream_t)stream;
+    c->have_user_stream = true;
+    return 0;
+}
+
+int scvx_set_kernel(scvx_ctx* c, int which) {
+    if (!c) return fail(SCVX_ERR_ARG, "null context");
+    if (which < SCVX_KERNEL_AUTO || which > SCVX_KERNEL_STAGED) return fail(SCVX_ERR_ARG, "unknown kernel id %d", which);
+    c->kernel = which;
+    return 0;
+}
+
+int scvx_synchronize(scvx_ctx* c) {
+    if (!c) return fail(SCVX_ERR_ARG, "null context");
+    for (Dev& d : c->devs) {
+        CK(cudaSetDevice(d.id));
+        CK(cudaStreamSynchronize(d.slot[0].stream));
+        CK(cudaStreamSynchronize(d.slot[1].stream));
+    }
+    if (c->have_user_stream) { CK(cudaSetDevice(c->devs[0].id)); CK(cudaStreamSynchronize(c->user_stream)); }
+    return 0;
+}
+
+int64_t scvx_launch_count(scvx_ctx* c) { return c ? c->launches : 0; }
+
+int scvx_last_kernel_ms(scvx_ctx* c, double* ms) {
+    if (!c || !ms) return fail(SCVX_ERR_ARG, "null argument");
+    if (!c->timed) return fail(SCVX_ERR_STATE, "no device-pointer call has been made yet");
+    Dev& d = c->devs[0];
+    CK(cudaSetDevice(d.id));
+    CK(cudaEventSynchronize(d.ev1));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, d.ev0, d.ev1));
+    *ms = (double)f;
+    return 0;
+}
+
+int scvx_measure_fp64_peak(scvx_ctx* c, double* tflops) {
+    if (!c || !tflops) return fail(SCVX_ERR_ARG, "null argument");
+    Dev& d = c->devs[0];
+    CK(cudaSetDevice(d.id));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, d.id));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    double* buf = nullptr;
+    CK(cudaMalloc((void**)&buf, (size_t)blocks * 256 * 8));
+    cudaStream_t s = d.slot[0].stream;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(d.ev0, s));
+        CK(scvx_launch_fp64_peak(buf, blocks, iters, s));
+        CK(cudaEventRecord(d.ev1, s));
+        CK(cudaEventSynchronize(d.ev1));
+        c->launches += 1;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        const double fl = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;   // 8 chains x 8 unroll FMAs per iteration
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) * 1e-12);
+    }
+    cudaFree(buf);
+    c->timed = false;
+    *tflops = best;
+    return 0;
+}
+
+}  // extern "C"

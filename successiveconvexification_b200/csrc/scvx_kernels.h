@@ -1,0 +1,10 @@
+// scvx_kernels.h — host-side launchers of the CUDA kernels (internal to the shared library).
+#pragma once
+#include <cuda_runtime.h>
+#include "scvx_common.cuh"
+
+cudaError_t scvx_launch_dualwarp(const ScvxBatch& bt, const ScvxTables& tb, cudaStream_t s);
+cudaError_t scvx_launch_predict(const ScvxBatch& bt, const ScvxTables& tb, cudaStream_t s);
+cudaError_t scvx_launch_prefilter(const double* d_samples, int n1, int n2, double* d_tmp, double* d_coef,
+                                  const double* d_cp, cudaStream_t s);
+cudaError_t scvx_launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t s);

@@ -1,0 +1,189 @@
+// scvx_kernels_basic.cu — first-generation kernels of the linearise-and-discretise path (sm_100a, FP64):
+//   * linearize_dualwarp_kernel : one warp per (trajectory, interval); lane L < 21 carries the tangent
+//                                 d/d inp[L] as a one-partial dual number through the whole rk4
+//                                 (= Zygote.forward_jacobian of rk4, reference dynamics.jl:311-313).
+//                                 Exact forward mode of the executed arithmetic by construction; kept as
+//                                 the on-device cross-check of the faster STAGED kernel.
+//   * predict_kernel            : one thread per interval, value only (predict_state / simulate_zygote,
+//                                 dynamics.jl:308-310, 315-317).
+//   * prefilter kernels         : Interpolations.jl cubic-B-spline prefilter, one thread per grid line.
+//   * fp64_peak_kernel          : DFMA throughput microbenchmark (roofline denominator).
+#include "scvx_common.cuh"
+#include "scvx_kernels.h"
+
+// ---------------------------------------------------------------------------------------------
+// thrust-lower-bound rows of one node (rocketland.jl:199-200, 261-263):  H = -u/|u| (3), h = Tmin - |u|
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void write_tlb(const ScvxBatch& bt, int b, int node) {
+    const double* u = bt.U + ((size_t)b * bt.n_nodes + node) * 3;
+    const double u0 = u[0], u1 = u[1], u2 = u[2];
+    const double nu = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
+    double* o = bt.out_tlb + ((size_t)b * bt.n_nodes + node) * 4;
+    o[0] = -(u0 / nu); o[1] = -(u1 / nu); o[2] = -(u2 / nu);
+    o[3] = bt.P[bt.n_params == 1 ? 0 : b].Tmin - nu;
+}
+
+__global__ void __launch_bounds__(128)
+linearize_dualwarp_kernel(ScvxBatch bt, ScvxTables tb) {
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int ni = bt.n_nodes - 1;
+    const long total = (long)ni * bt.B;
+    if (warp >= total) return;
+    const int b = (int)(warp / ni), i = (int)(warp % ni);
+    const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
+    const double* xin = bt.X + ((size_t)b * bt.n_nodes + i) * 14;
+    const double* uin = bt.U + ((size_t)b * bt.n_nodes + i) * 3;
+
+    D1 st[14], um[3], up[3];
+#pragma unroll
+    for (int r = 0; r < 14; ++r) st[r] = D1(xin[r], lane == r ? 1.0 : 0.0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        um[c] = D1(uin[c], lane == 14 + c ? 1.0 : 0.0);
+        up[c] = D1(uin[3 + c], lane == 17 + c ? 1.0 : 0.0);
+    }
+    const D1 sg(bt.sigma[b], lane == 20 ? 1.0 : 0.0);
+    // this lane's own input value (for z = endpoint - D*inp)
+    double my_inp = 0.0;
+    if (lane < 14) my_inp = xin[lane];
+    else if (lane < 20) my_inp = uin[lane - 14];
+    else if (lane == 20) my_inp = bt.sigma[b];
+
+    rk4_t<D1>(P, tb, st, um, up, sg, bt.dt, bt.npts, bt.mode);
+
+    double* blk = bt.out_blocks + (size_t)warp * SCVX_BLOCK_DOUBLES;
+#pragma unroll
+    for (int r = 0; r < 14; ++r) {
+        if (lane < 21) blk[14 * (1 + lane) + r] = st[r].d;
+        double t = st[r].d * my_inp;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) {
+            blk[r] = st[r].v;
+            blk[14 * 22 + r] = st[r].v - t;
+            if (bt.out_lin_err) bt.out_lin_err[(size_t)warp * 14 + r] = st[r].v - xin[14 + r];
+        }
+    }
+    if (bt.out_tlb) {
+        if (lane == 31) write_tlb(bt, b, i);
+        if (lane == 30 && i == ni - 1) write_tlb(bt, b, i + 1);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+predict_kernel(ScvxBatch bt, ScvxTables tb) {
+    const long w = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ni = bt.n_nodes - 1;
+    const long total = (long)ni * bt.B;
+    if (w >= total) return;
+    const int b = (int)(w / ni), i = (int)(w % ni);
+    const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
+    const double* xin = bt.X + ((size_t)b * bt.n_nodes + i) * 14;
+    const double* uin = bt.U + ((size_t)b * bt.n_nodes + i) * 3;
+    double st[14], um[3], up[3];
+#pragma unroll
+    for (int r = 0; r < 14; ++r) st[r] = xin[r];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { um[c] = uin[c]; up[c] = uin[3 + c]; }
+    rk4_t<double>(P, tb, st, um, up, bt.sigma[b], bt.dt, bt.npts, bt.mode);
+    double* o = bt.out_endpoints + (size_t)w * 14;
+#pragma unroll
+    for (int r = 0; r < 14; ++r) o[r] = st[r];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cubic B-spline prefilter, BSpline(Cubic(Line(OnGrid()))) (Interpolations.jl; call sites
+// aerodynamics.jl:19-21).  Per line of n samples d_1..d_n solve for c_0..c_{n+1}:
+//     c_{k-1}/6 + 2 c_k/3 + c_{k+1}/6 = d_k  (k=1..n),   c_0 - 2c_1 + c_2 = 0,   c_{n-1} - 2c_n + c_{n+1} = 0.
+// Subtracting the boundary rows from rows 1 and n gives c_1 = d_1 and c_n = d_n exactly; the interior
+// unknowns c_2..c_{n-1} then satisfy the diagonally dominant tridiagonal system [1 4 1] c = 6 d, solved
+// by the Thomas algorithm (its elimination factors `cp` are data independent and precomputed once).
+// ---------------------------------------------------------------------------------------------
+__device__ void prefilter_line(const double* __restrict__ in, int n, size_t sin, double* __restrict__ out,
+                               size_t sout, const double* __restrict__ cp) {
+    // out index g = 0..n+1 ; in index k-1 for grid point k
+    const double d1 = in[0], dn = in[(size_t)(n - 1) * sin];
+    out[1 * sout] = d1;
+    out[(size_t)n * sout] = dn;
+    if (n >= 3) {
+        // forward sweep over k = 2..n-1 (m = k-2 = 0..n-3); modified rhs stored in place
+        double prev = 0.0;
+        for (int k = 2; k <= n - 1; ++k) {
+            double rhs = 6.0 * in[(size_t)(k - 1) * sin];
+            if (k == 2) rhs -= d1;
+            if (k == n - 1) rhs -= dn;
+            const double denom_inv = cp[k - 2];                 // 1 / (4 - cp'[m-1]) precomputed
+            prev = (rhs - prev) * denom_inv;
+            out[(size_t)k * sout] = prev;
+        }
+        // back substitution: c_k = d'_k - cp[m] * c_{k+1}
+        double next = 0.0;
+        for (int k = n - 1; k >= 2; --k) {
+            double v = out[(size_t)k * sout];
+            if (k < n - 1) v -= cp[k - 2] * next;
+            out[(size_t)k * sout] = v;
+            next = v;
+        }
+    }
+    out[0] = 2.0 * out[1 * sout] - out[2 * sout];
+    out[(size_t)(n + 1) * sout] = 2.0 * out[(size_t)n * sout] - out[(size_t)(n - 1) * sout];
+}
+
+// pass 1: along axis 0 (length n1) for each of n2 columns: samples (n1 x n2) -> tmp ((n1+2) x n2)
+__global__ void prefilter_axis0_kernel(const double* samples, int n1, int n2, double* tmp, const double* cp) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n2) return;
+    prefilter_line(samples + (size_t)j * n1, n1, 1, tmp + (size_t)j * (n1 + 2), 1, cp);
+}
+// pass 2: along axis 1 (length n2) for each of n1+2 rows: tmp ((n1+2) x n2) -> coef ((n1+2) x (n2+2))
+__global__ void prefilter_axis1_kernel(const double* tmp, int n1, int n2, double* coef, const double* cp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1 + 2) return;
+    prefilter_line(tmp + i, n2, (size_t)(n1 + 2), coef + i, (size_t)(n1 + 2), cp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 FMA throughput microbenchmark: 8 independent chains per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+            r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+cudaError_t scvx_launch_dualwarp(const ScvxBatch& bt, const ScvxTables& tb, cudaStream_t s) {
+    const long total = (long)(bt.n_nodes - 1) * bt.B;
+    if (total <= 0) return cudaSuccess;
+    const long blocks = (total + 3) / 4;
+    linearize_dualwarp_kernel<<<(unsigned)blocks, 128, 0, s>>>(bt, tb);
+    return cudaGetLastError();
+}
+
+cudaError_t scvx_launch_predict(const ScvxBatch& bt, const ScvxTables& tb, cudaStream_t s) {
+    const long total = (long)(bt.n_nodes - 1) * bt.B;
+    if (total <= 0) return cudaSuccess;
+    predict_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(bt, tb);
+    return cudaGetLastError();
+}
+
+cudaError_t scvx_launch_prefilter(const double* d_samples, int n1, int n2, double* d_tmp, double* d_coef,
+                                  const double* d_cp, cudaStream_t s) {
+    prefilter_axis0_kernel<<<(n2 + 63) / 64, 64, 0, s>>>(d_samples, n1, n2, d_tmp, d_cp);
+    prefilter_axis1_kernel<<<(n1 + 2 + 63) / 64, 64, 0, s>>>(d_tmp, n1, n2, d_coef, d_cp);
+    return cudaGetLastError();
+}
+
+cudaError_t scvx_launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t s) {
+    fp64_peak_kernel<<<blocks, 256, 0, s>>>(d_out, iters, 0.999999, 1e-9);
+    return cudaGetLastError();
+}

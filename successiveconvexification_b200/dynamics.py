@@ -1,0 +1,244 @@
+"""Device-backed mirror of module `Dynamics` (reference dynamics.jl) — the drop-in boundary.
+
+Same names, argument meaning and error behaviour as the reference entry points:
+    linearize_dynamics(states, tf_guess, base_dt, cache)   dynamics.jl:321-334
+    predict_state(x, uk, up, sigma, dt, pinfo, cache)       dynamics.jl:315-317
+    simulate_zygote / sensitivity_zygote(inp, dt, cache)    dynamics.jl:308-313
+    simulate / sensitivity(inp, dt, cache)                  dynamics.jl:288-305 (deviation form)
+    make_state(a, b, sig)                                   dynamics.jl:318-320
+    IntegratorCache(prob, info, lin_mod)                    dynamics.jl:258-260
+plus additive batched entry points (`linearize_batch`, `predict_batch`) for Monte-Carlo batches.
+All numerics run in the CUDA library behind include/scvx_b200.h; nothing here computes dynamics.
+
+Variant note: the device implements the deterministic rk4 + exact forward Jacobian
+(`sensitivity_zygote`, "V2").  `simulate`/`sensitivity` return the same quantities in the live code's
+deviation form so that `linearize_dynamics`' post-processing (dynamics.jl:327-330) is unchanged.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .defns import (AERO_TABLE, ACC_WIDTH, AtmosphericData, CProbInfo, DescentProblem, INP_DIM, IntegratorCache,
+                    LinPoint, LinRes, ProbInfo, STATE_DIM)
+
+MODE_LITERAL = 0      # reproduces dynamics.jl:126-128 (stage increments not scaled by the sub-step)
+MODE_TEXTBOOK = 1     # classical RK4
+KERNEL_AUTO, KERNEL_DUALWARP, KERNEL_STAGED = 0, 1, 2
+TABLE_DRAG, TABLE_LIFT, TABLE_TORQUE = 0, 1, 2
+
+state_idx = slice(0, 14)          # dynamics.jl:136  stateC = 1:14
+uk_idx = slice(14, 17)            # dynamics.jl:137  ukC
+up_idx = slice(17, 20)            # dynamics.jl:138  upC
+sigma_idx = 20                    # dynamics.jl:139  sigmaC
+
+
+class DeviceContext:
+    """Owns one `scvx_ctx` (opaque C handle).  Stored in `IntegratorCache.sim_prob`."""
+
+    def __init__(self, device_ids: Optional[Sequence[int]] = None):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        if device_ids is None:
+            rc = self._lib.scvx_create(ctypes.byref(self._h), None, 0)
+        else:
+            ids = (ctypes.c_int * len(device_ids))(*device_ids)
+            rc = self._lib.scvx_create(ctypes.byref(self._h), ids, len(device_ids))
+        _lib.check(rc)
+        self.n_params = 0
+        self.mode = MODE_LITERAL
+        self.npts = 10
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.scvx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setup
+    def set_params(self, infos):
+        if isinstance(infos, ProbInfo):
+            infos = [infos]
+        arr = (CProbInfo * len(infos))(*[i.to_c() if isinstance(i, ProbInfo) else i for i in infos])
+        _lib.check(self._lib.scvx_set_params(self._h, arr, len(infos)))
+        self.n_params = len(infos)
+
+    def set_params_raw(self, arr, n):
+        _lib.check(self._lib.scvx_set_params(self._h, arr, n))
+        self.n_params = n
+
+    def set_aero(self, aero: AtmosphericData):
+        for which, t in ((TABLE_DRAG, aero.drag_itrp), (TABLE_LIFT, aero.lift_itrp), (TABLE_TORQUE, aero.trq_itrp)):
+            s = np.asfortranarray(t.samples, dtype=np.float64)
+            _lib.check(self._lib.scvx_set_aero_table(self._h, which, s.ctypes.data, s.shape[0], s.shape[1],
+                                                     t.cos0, t.dcos, t.mach0, t.dmach, 0))
+
+    def aero_coefficients(self, which: int, n_cos: int, n_mach: int) -> np.ndarray:
+        out = np.zeros((n_cos + 2, n_mach + 2), order="F")
+        _lib.check(self._lib.scvx_get_aero_coefficients(self._h, which, out.ctypes.data))
+        return out
+
+    def set_kernel(self, which: int):
+        _lib.check(self._lib.scvx_set_kernel(self._h, which))
+
+    def set_stream(self, cuda_stream: int):
+        _lib.check(self._lib.scvx_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        _lib.check(self._lib.scvx_synchronize(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._lib.scvx_launch_count(self._h))
+
+    def last_kernel_ms(self) -> float:
+        ms = ctypes.c_double()
+        _lib.check(self._lib.scvx_last_kernel_ms(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def measure_fp64_peak(self) -> float:
+        tf = ctypes.c_double()
+        _lib.check(self._lib.scvx_measure_fp64_peak(self._h, ctypes.byref(tf)))
+        return tf.value
+
+    # ---- raw pointer calls (host or device addresses)
+    def linearize_ptr(self, X, U, sigma, base_dt, npts, mode, n_nodes, B, out_blocks, out_lin_err=0, out_tlb=0):
+        _lib.check(self._lib.scvx_linearize_batch(self._h, X, U, sigma, base_dt, npts, mode, n_nodes, B,
+                                                  out_blocks, out_lin_err or None, out_tlb or None))
+
+    def predict_ptr(self, X, U, sigma, base_dt, npts, mode, n_nodes, B, out):
+        _lib.check(self._lib.scvx_predict_batch(self._h, X, U, sigma, base_dt, npts, mode, n_nodes, B, out))
+
+
+def make_dynamics_module(info: ProbInfo):
+    """dynamics.jl:141-215 generates the V1 `Linearizer` module by symbolic codegen.  The device path
+    needs no generated code; a descriptor is returned so the documented bring-up sequence
+    (rocketland.jl:26-31) keeps its shape."""
+    return {"name": "Linearizer", "info": info, "backend": "scvx_b200"}
+
+
+def make_cache(prob: DescentProblem, info: Optional[ProbInfo] = None, lin_mod=None,
+               device_ids: Optional[Sequence[int]] = None) -> IntegratorCache:
+    """`IntegratorCache(prob, info, lin_mod)` (dynamics.jl:258-260): builds the device context,
+    uploads the parameters and (for AtmosphericData) the spline tables."""
+    info = info if info is not None else ProbInfo(prob)
+    ctx = DeviceContext(device_ids)
+    ctx.set_params(info)
+    if isinstance(info.aero, AtmosphericData):
+        ctx.set_aero(info.aero)
+    return IntegratorCache(sim_prob=ctx, sense_prob=None, sim_int=None, sense_int=None,
+                           params=[1.0, info], info=info)
+
+
+def _ctx(cache: IntegratorCache) -> DeviceContext:
+    ctx = cache.sim_prob
+    if not isinstance(ctx, DeviceContext):
+        raise TypeError("cache does not hold a device context; build it with make_cache(prob, info)")
+    return ctx
+
+
+def make_state(a: LinPoint, b: LinPoint, sig: float) -> np.ndarray:
+    """dynamics.jl:318-320."""
+    return np.concatenate([a.state, a.control, b.control, [sig]])
+
+
+# -------------------------------------------------------------------------------------------
+# batched entry points (numpy, host memory).  Shapes are C-order views of the Julia arrays:
+#   X (B, n_nodes, 14) == Julia (14, n_nodes, B);  blocks (B, n_int, 23, 14) == Julia (14, 23, n_int, B)
+# -------------------------------------------------------------------------------------------
+def linearize_batch(cache: IntegratorCache, X, U, sigma, base_dt: float, npts: int = 10, mode: int = MODE_LITERAL,
+                    lin_err: bool = True, tlb: bool = True):
+    ctx = _ctx(cache)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64).reshape(-1)
+    if X.ndim != 3 or X.shape[2] != 14 or U.shape != (X.shape[0], X.shape[1], 3) or sigma.shape[0] != X.shape[0]:
+        raise ValueError("expected X (B, n_nodes, 14), U (B, n_nodes, 3), sigma (B,)")
+    B, n_nodes, _ = X.shape
+    ni = max(n_nodes - 1, 0)
+    blocks = np.empty((B, ni, ACC_WIDTH, STATE_DIM))
+    err = np.empty((B, ni, STATE_DIM)) if lin_err else None
+    tl = np.empty((B, n_nodes, 4)) if tlb else None
+    ctx.linearize_ptr(X.ctypes.data, U.ctypes.data, sigma.ctypes.data, float(base_dt), int(npts), int(mode),
+                      n_nodes, B, blocks.ctypes.data, err.ctypes.data if lin_err else 0, tl.ctypes.data if tlb else 0)
+    return blocks, err, tl
+
+
+def predict_batch(cache: IntegratorCache, X, U, sigma, base_dt: float, npts: int = 10, mode: int = MODE_LITERAL):
+    ctx = _ctx(cache)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64).reshape(-1)
+    B, n_nodes, _ = X.shape
+    out = np.empty((B, n_nodes - 1, STATE_DIM))
+    ctx.predict_ptr(X.ctypes.data, U.ctypes.data, sigma.ctypes.data, float(base_dt), int(npts), int(mode),
+                    n_nodes, B, out.ctypes.data)
+    return out
+
+
+def blocks_to_linres(blocks_one_traj: np.ndarray):
+    """(n_int, 23, 14) C-order -> [LinRes]; derivative is the 14x21 column-major matrix (a Fortran view)."""
+    return [LinRes(endpoint=blk[0].copy(), derivative=np.asfortranarray(blk[1:22].T)) for blk in blocks_one_traj]
+
+
+# -------------------------------------------------------------------------------------------
+# the reference entry points
+# -------------------------------------------------------------------------------------------
+def linearize_dynamics(states: Sequence[LinPoint], tf_guess: float, base_dt: float, cache: IntegratorCache):
+    """dynamics.jl:321-334: one LinRes per adjacent pair of nodes."""
+    ctx = _ctx(cache)
+    X = np.stack([p.state for p in states])[None]
+    U = np.stack([p.control for p in states])[None]
+    blocks, _, _ = linearize_batch(cache, X, U, [float(tf_guess)], base_dt, ctx.npts, ctx.mode, lin_err=False, tlb=False)
+    return blocks_to_linres(blocks[0])
+
+
+def simulate_zygote(inp, dt: float, cache: IntegratorCache, npts: int = 10) -> np.ndarray:
+    """dynamics.jl:308-310: rk4(inp, dt, info) -> absolute end state (14)."""
+    inp = np.asarray(inp, dtype=np.float64)
+    if inp.shape != (INP_DIM,):
+        raise ValueError("inp must have 21 entries [x; uk; up; sigma]")
+    X = np.zeros((1, 2, 14)); U = np.zeros((1, 2, 3))
+    X[0, 0] = inp[state_idx]; U[0, 0] = inp[uk_idx]; U[0, 1] = inp[up_idx]
+    return predict_batch(cache, X, U, [inp[sigma_idx]], dt, npts, _ctx(cache).mode)[0, 0]
+
+
+def sensitivity_zygote(inp, dt: float, cache: IntegratorCache):
+    """dynamics.jl:311-313: (y(14), J^T (21x14)) as Zygote.forward_jacobian returns them."""
+    inp = np.asarray(inp, dtype=np.float64)
+    if inp.shape != (INP_DIM,):
+        raise ValueError("inp must have 21 entries [x; uk; up; sigma]")
+    ctx = _ctx(cache)
+    X = np.zeros((1, 2, 14)); U = np.zeros((1, 2, 3))
+    X[0, 0] = inp[state_idx]; U[0, 0] = inp[uk_idx]; U[0, 1] = inp[up_idx]
+    blocks, _, _ = linearize_batch(cache, X, U, [inp[sigma_idx]], dt, ctx.npts, ctx.mode, lin_err=False, tlb=False)
+    blk = blocks[0, 0]
+    return blk[0].copy(), blk[1:22].copy()          # rows of blk[1:22] are the columns of D, i.e. J^T
+
+
+def simulate(inp, dt: float, cache: IntegratorCache) -> np.ndarray:
+    """dynamics.jl:288-296: absolute end state (the reference returns `(u .+ inp)[1:14]`)."""
+    return simulate_zygote(inp, dt, cache, _ctx(cache).npts)
+
+
+def sensitivity(inp, dt: float, cache: IntegratorCache):
+    """dynamics.jl:298-305 in the live code's DEVIATION form: val(21) = x(dt) - x(0) (zero-padded),
+    mat(21x21) with mat[0:14, :] = D - [I 0]; `linearize_dynamics` adds x and I back (327-330)."""
+    inp = np.asarray(inp, dtype=np.float64)
+    y, JT = sensitivity_zygote(inp, dt, cache)
+    val = np.zeros(INP_DIM); val[:14] = y - inp[:14]
+    mat = np.zeros((INP_DIM, INP_DIM), order="F"); mat[:14, :] = JT.T
+    mat[np.arange(14), np.arange(14)] -= 1.0
+    return val, mat
+
+
+def predict_state(initial_state, uk, up, sigma, dt, pinfo, cache: IntegratorCache) -> np.ndarray:
+    """dynamics.jl:315-317."""
+    return simulate(np.concatenate([initial_state, uk, up, [sigma]]), dt, cache)

@@ -1,0 +1,214 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle and the committed
+golden vectors.  Tolerance: 1e-10 relative per matrix entry (BASELINE.json north_star), metric in
+conftest.parity_report.  Nothing here reads /root/reference."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, PARITY_TOL, assert_parity, parity_report
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [1, 2]          # SCVX_KERNEL_DUALWARP, SCVX_KERNEL_STAGED
+
+
+@pytest.fixture(scope="module")
+def dyn():
+    from successiveconvexification_b200 import dynamics
+    return dynamics
+
+
+@pytest.fixture(scope="module")
+def cache_aero(dyn, prob_aero):
+    return dyn.make_cache(prob_aero)
+
+
+@pytest.fixture(scope="module")
+def cache_exo(dyn, prob_exo):
+    return dyn.make_cache(prob_exo)
+
+
+def _oracle():
+    from oracle import oracle
+    return oracle
+
+
+def test_device_present():
+    from successiveconvexification_b200 import _lib
+    assert _lib.load().scvx_device_count() >= 1
+
+
+def test_prefilter_on_device_matches_oracle(dyn, cache_aero, prob_aero, oracle_tables):
+    ctx = cache_aero.sim_prob
+    for which, ref in ((0, oracle_tables.drag), (1, oracle_tables.lift)):
+        got = ctx.aero_coefficients(which, 181, 61)
+        assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("aero", ["aero", "exo"])
+def test_c2_sample_trajectory_vs_golden_and_oracle(dyn, cache_aero, cache_exo, prob_aero, prob_exo, oracle_tables,
+                                                   kernel, mode, aero):
+    """BASELINE config 2: 1 trajectory, intervals 1..50 (reference convention) which contain 1..49 (paper)."""
+    from successiveconvexification_b200 import workloads
+    from successiveconvexification_b200.defns import ProbInfo
+    cache, prob, tb = (cache_aero, prob_aero, oracle_tables) if aero == "aero" else (cache_exo, prob_exo, None)
+    cache.sim_prob.set_kernel(kernel)
+    X, U, sigma, dt = workloads.sample_trajectory(prob)
+    blocks, err, tlb = dyn.linearize_batch(cache, X, U, sigma, dt, 10, mode)
+    gold = np.load(os.path.join(GOLDEN, "golden_c2.npz"))[f"{aero}_{'literal' if mode == 0 else 'textbook'}"]
+    assert_parity(blocks[0], gold)
+    ref, rerr, rtlb, _ = _oracle().linearize_batch(ProbInfo(prob), tb, X, U, sigma, dt, 10, mode)
+    assert_parity(blocks, ref)
+    assert np.abs(err - rerr).max() <= 1e-13
+    assert np.abs(tlb - rtlb).max() <= 1e-15
+    # structural zeros: nothing depends on position
+    expect = np.zeros((3, 14)); expect[[0, 1, 2], [1, 2, 3]] = 1.0
+    assert np.array_equal(blocks[0, :, 2:5, :], np.broadcast_to(expect, (50, 3, 14)))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_reference_entry_points(dyn, cache_aero, prob_aero, oracle_tables, kernel):
+    """linearize_dynamics / predict_state / sensitivity_zygote / simulate keep the reference's shapes and values."""
+    from successiveconvexification_b200.defns import ProbInfo
+    from successiveconvexification_b200.first_round import linear_points
+    cache_aero.sim_prob.set_kernel(kernel)
+    pts = linear_points(prob_aero)
+    res = dyn.linearize_dynamics(pts, prob_aero.tf_guess, 1 / (prob_aero.K + 1), cache_aero)
+    assert len(res) == prob_aero.K and res[0].derivative.shape == (14, 21) and res[0].endpoint.shape == (14,)
+    assert res[0].derivative.flags.f_contiguous
+    info = ProbInfo(prob_aero)
+    inp = dyn.make_state(pts[0], pts[1], 1.0)
+    blk = _oracle().linearize_interval(info, oracle_tables, inp, 1 / 51)
+    assert np.abs(res[0].endpoint - blk[:, 0]).max() <= 1e-14
+    assert np.abs(res[0].derivative - blk[:, 1:22]).max() <= 1e-12
+    y, JT = dyn.sensitivity_zygote(inp, 1 / 51, cache_aero)
+    assert JT.shape == (21, 14) and np.abs(JT.T - blk[:, 1:22]).max() <= 1e-12
+    val, mat = dyn.sensitivity(inp, 1 / 51, cache_aero)
+    assert val.shape == (21,) and mat.shape == (21, 21)
+    assert np.abs(val[:14] + inp[:14] - blk[:, 0]).max() <= 1e-14
+    ps = dyn.predict_state(pts[0].state, pts[0].control, pts[1].control, 1.0, 1 / 51, info, cache_aero)
+    assert np.abs(ps - blk[:, 0]).max() <= 1e-14
+    assert np.abs(dyn.simulate(inp, 1 / 51, cache_aero) - blk[:, 0]).max() <= 1e-14
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_monte_carlo_sweep_vs_golden(dyn, prob_aero, oracle_tables, kernel):
+    """Per-trajectory parameters (C4-style sweep), LITERAL, against the committed golden vectors."""
+    from successiveconvexification_b200 import workloads
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, 5, 6, 4242, sweep=True, sigma_range=(0.8, 1.5))
+    cache = dyn.make_cache(prob_aero)
+    ptr, n, keep = workloads.as_c_params(P)
+    cache.sim_prob.set_params_raw(ptr, n)
+    cache.sim_prob.set_kernel(kernel)
+    blocks, err, tlb = dyn.linearize_batch(cache, X, U, sigma, 1 / 6)
+    g = np.load(os.path.join(GOLDEN, "golden_mc.npz"))
+    assert_parity(blocks, g["blocks"])
+    assert np.abs(err - g["lin_err"]).max() <= 1e-12 * max(1.0, np.abs(g["lin_err"]).max())
+    assert np.abs(tlb - g["tlb"]).max() <= 1e-15
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("mode,srange", [(1, (1.0, 15.0)), (0, (0.8, 1.5))])
+def test_c3_style_batch_vs_oracle(dyn, cache_aero, prob_aero, oracle_tables, kernel, mode, srange):
+    """Aero-table Monte-Carlo batch (both sides of the |dp| >= 0.95 branch), K=100 like C3, B reduced so the
+    oracle finishes in seconds."""
+    from successiveconvexification_b200 import workloads
+    cache_aero.sim_prob.set_kernel(kernel)
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, 100, 24, 1001, sigma_range=srange)
+    blocks, err, tlb = dyn.linearize_batch(cache_aero, X, U, sigma, 1 / 101, 10, mode)
+    ref, rerr, rtlb, _ = _oracle().linearize_batch(P, oracle_tables, X, U, sigma, 1 / 101, 10, mode)
+    assert_parity(blocks, ref)
+    end = dyn.predict_batch(cache_aero, X, U, sigma, 1 / 101, 10, mode)
+    assert np.abs(end - ref[:, :, 0, :]).max() <= 1e-12 * np.abs(ref[:, :, 0, :]).max()
+
+
+def test_staged_kernel_agrees_with_dualwarp_at_scale(dyn, cache_aero, prob_aero):
+    """Full-width property: the two independent device kernels agree on a batch far beyond what the CPU
+    oracle can check in seconds (4096 trajectories x 50 intervals)."""
+    from successiveconvexification_b200 import workloads
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, 50, 4096, 1003)
+    ctx = cache_aero.sim_prob
+    ctx.set_kernel(1)
+    a, _, _ = dyn.linearize_batch(cache_aero, X, U, sigma, 1 / 51, 10, 1, lin_err=False, tlb=False)
+    ctx.set_kernel(2)
+    b, _, _ = dyn.linearize_batch(cache_aero, X, U, sigma, 1 / 51, 10, 1, lin_err=False, tlb=False)
+    assert np.isfinite(b).all()
+    assert_parity(b, a)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_full_size_properties_and_sampled_oracle(dyn, cache_aero, prob_aero, oracle_tables, kernel):
+    """C5 shard at reduced width through the chunked host path (several pipeline chunks): affine-model closure
+    z = endpoint - D*inp, exact structural zeros, endpoint == predict, and a random sample vs the oracle."""
+    from successiveconvexification_b200 import workloads
+    cache_aero.sim_prob.set_kernel(kernel)
+    B, K = 2048, 50
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, K, B, 1003)
+    blocks, err, tlb = dyn.linearize_batch(cache_aero, X, U, sigma, 1 / (K + 1), 10, 1)
+    assert np.isfinite(blocks).all()
+    D = blocks[:, :, 1:22, :]
+    inp = np.concatenate([X[:, :-1], U[:, :-1], U[:, 1:], np.broadcast_to(sigma[:, None, None], (B, K, 1))], axis=-1)
+    z = blocks[:, :, 0, :] - np.einsum("bicr,bic->bir", D, inp)
+    assert np.abs(z - blocks[:, :, 22, :]).max() <= 1e-12 * np.abs(D).max()
+    expect = np.zeros((3, 14)); expect[[0, 1, 2], [1, 2, 3]] = 1.0
+    assert np.array_equal(D[:, :, 1:4, :], np.broadcast_to(expect, (B, K, 3, 14)))
+    assert np.abs(err - (blocks[:, :, 0, :] - X[:, 1:])).max() <= 1e-15
+    end = dyn.predict_batch(cache_aero, X, U, sigma, 1 / (K + 1), 10, 1)
+    assert np.abs(end - blocks[:, :, 0, :]).max() <= 1e-13
+    rng = np.random.default_rng(5)
+    pick = rng.choice(B, 16, replace=False)
+    ref, _, _, _ = _oracle().linearize_batch(P, oracle_tables, X[pick], U[pick], sigma[pick], 1 / (K + 1), 10, 1,
+                                            False, False)
+    assert_parity(blocks[pick], ref)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_device_pointer_path_torch(dyn, cache_aero, prob_aero, oracle_tables, kernel):
+    """Device-resident inputs/outputs on torch's current stream (the path bench.py times)."""
+    import torch
+    from successiveconvexification_b200 import workloads
+    ctx = cache_aero.sim_prob
+    ctx.set_kernel(kernel)
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, 20, 64, 31, sigma_range=(0.8, 1.5))
+    dX, dU, dS = (torch.from_numpy(a).cuda() for a in (X, U, sigma))
+    out = torch.empty((64, 20, 23, 14), dtype=torch.float64, device="cuda")
+    err = torch.empty((64, 20, 14), dtype=torch.float64, device="cuda")
+    tlb = torch.empty((64, 21, 4), dtype=torch.float64, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    n0 = ctx.launch_count()
+    ctx.linearize_ptr(dX.data_ptr(), dU.data_ptr(), dS.data_ptr(), 1 / 21, 10, 0, 21, 64, out.data_ptr(),
+                      err.data_ptr(), tlb.data_ptr())
+    torch.cuda.synchronize()
+    assert ctx.launch_count() > n0 and ctx.last_kernel_ms() > 0.0
+    ref, rerr, rtlb, _ = _oracle().linearize_batch(P, oracle_tables, X, U, sigma, 1 / 21)
+    assert_parity(out.cpu().numpy(), ref)
+    assert np.abs(tlb.cpu().numpy() - rtlb).max() <= 1e-15
+
+
+def test_edge_cases_and_errors(dyn, cache_aero, prob_aero):
+    from successiveconvexification_b200 import _lib, workloads
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, 1, 3, 8, sigma_range=(0.8, 1.5))     # n_nodes = 2
+    blocks, err, tlb = dyn.linearize_batch(cache_aero, X, U, sigma, 0.5)
+    assert blocks.shape == (3, 1, 23, 14) and np.isfinite(blocks).all()
+    b0, _, _ = dyn.linearize_batch(cache_aero, X[:0], U[:0], sigma[:0], 0.5)                      # empty batch
+    assert b0.shape == (0, 1, 23, 14)
+    with pytest.raises(_lib.ScvxError):
+        dyn.linearize_batch(cache_aero, X[:, :1], U[:, :1], sigma, 0.5)                           # a single node
+    with pytest.raises(_lib.ScvxError):
+        dyn.linearize_batch(cache_aero, X, U, sigma, 0.5, npts=0)
+    with pytest.raises(_lib.ScvxError):
+        dyn.linearize_batch(cache_aero, X, U, sigma, 0.5, mode=7)
+    with pytest.raises(_lib.ScvxError):
+        dyn.linearize_batch(cache_aero, X, U, sigma, -1.0)
+    fresh = dyn.DeviceContext()
+    from successiveconvexification_b200.defns import IntegratorCache
+    with pytest.raises(_lib.ScvxError, match="set_params"):
+        dyn.linearize_batch(IntegratorCache(sim_prob=fresh), X, U, sigma, 0.5)
+
+
+def test_fp64_peak_microbenchmark(cache_aero):
+    tf = cache_aero.sim_prob.measure_fp64_peak()
+    assert 5.0 < tf < 80.0
