@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py — FOH interval discretisations / second (FP64, K=50) on N B200s, beside the CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[4] = SURVEY.md §8d C5, the configuration the metric is quoted on): Monte-Carlo
+dispersion of the aero-table sample problem, K=50 (51 nodes, 50 intervals per trajectory), 32768 trajectories PER
+GPU (262144 on 8 GPUs -> weak scaling), per-iteration discretisation + SOCP-assembly extras (lin_err, thrust-LB).
+One "step" = one pass of the hot path over that batch.  No data-path collective: trajectories are sharded.
+
+  value  : intervals/s, inputs and outputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e    : same metric through the C-ABI call with pinned HOST buffers (H2D + kernels + D2H inside the timed region)
+  roofline : binding resource is the FP64 FMA pipe; `peak` is measured in this run by the library's
+             DFMA microbenchmark (MEASURED_PEAKS.json holds no FP64 figure); the HBM view is given beside it
+  cpu_baseline : the CPU oracle (C++ restatement of the reference's Julia path; Julia is not installed) on the
+             box's host cores, bounded sample.  A reported baseline, not the target.
+`--impl reference` times that CPU implementation alone (rank 0 only) and prints the same JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+AERO_NPZ = os.path.join(ROOT, "tests", "golden", "aero_lift_drag.npz")
+K_NODES = 50                    # problem.K -> 51 nodes, 50 intervals (reference convention, initial_solve.jl:115-116)
+TRAJ_PER_GPU = 32768            # C5: 262144 trajectories over 8 GPUs
+SEED = 1003
+NPTS = 10
+METRIC = "FOH interval discretisations/sec (FP64, K=50)"
+UNIT = "intervals/s"
+# algorithmic work per interval (SURVEY.md §8d / BASELINE.md §3), aero-table variant, npts = 10
+FLOP_PER_INTERVAL_AERO = 10 * (4 * (300 + 600 + 2 * 21 * 60 + 2 * 6 * 21 + 28) + 4620)     # 194 200
+BYTES_PER_INTERVAL = 8 * (21 + 14 * 23) + 8 * (14 + 4)                                        # 2 888 incl. lin_err + tlb
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+def cpu_reference_run(prob, steps, warmup, traj_per_thread):
+    """The reference's CPU implementation of the path (oracle port), all host threads, bounded sample per step."""
+    from oracle import oracle
+    from successiveconvexification_b200 import workloads
+    tb = oracle.OracleTables.from_aero(prob.aero)
+    threads = oracle.max_threads()
+    n_traj = max(8, traj_per_thread * threads)
+    X, U, sigma, P = workloads.monte_carlo_batch(prob, K_NODES, n_traj, SEED)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        oracle.linearize_batch(P, tb, X, U, sigma, 1.0 / (K_NODES + 1), NPTS, 0, True, True, nthreads=threads)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = n_traj * K_NODES * len(times) / total
+    sample = (f"{n_traj} trajectories x {K_NODES} intervals of the C5 batch per step, {len(times)} timed steps "
+              f"({total:.1f} s), OpenMP over intervals")
+    return value, threads, sample, total / len(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--traj-per-gpu", type=int, default=TRAJ_PER_GPU)
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 dualwarp, 2 staged")
+    ap.add_argument("--mode", type=int, default=0, help="0 LITERAL (parity contract), 1 TEXTBOOK")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    from successiveconvexification_b200 import sample_problems as sp, workloads
+    prob = sp.base_prob_aero_scaled(AERO_NPZ)
+    config = {"workload": f"C5 Monte-Carlo dispersion, aero-table 6-DoF sample problem, K={K_NODES} "
+                          f"({K_NODES + 1} nodes, {K_NODES} intervals/trajectory), {args.traj_per_gpu} trajectories per GPU, "
+                          f"discretise [A|B-|B+|Sigma|z] + lin_err + thrust-LB rows, npts={NPTS}, "
+                          f"mode={'LITERAL' if args.mode == 0 else 'TEXTBOOK'}",
+              "trajectories_per_gpu": args.traj_per_gpu, "intervals_per_trajectory": K_NODES, "seed": SEED,
+              "sharding": f"trajectory shards, {world} rank(s), no data-path collective",
+              "l2": "inputs (227 MB/GPU) and outputs (4.7 GB/GPU) exceed the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        value, threads, sample, step_s = cpu_reference_run(prob, args.steps, args.warmup, traj_per_thread=120)
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                                 "sample": sample + "; C++ restatement of the reference Julia path (Julia unavailable)"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from successiveconvexification_b200 import dynamics, sharding
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- this rank's shard (independent reproducible stream per shard; C5 = contiguous shards of 32768)
+    B = args.traj_per_gpu
+    X, U, sigma, P = workloads.monte_carlo_batch(prob, K_NODES, B, SEED, shard=rank)
+    n_nodes, ni = K_NODES + 1, K_NODES
+    dt = 1.0 / (K_NODES + 1)
+    cache = dynamics.make_cache(prob, device_ids=[local_rank])
+    ctx = cache.sim_prob
+    ctx.set_kernel(args.kernel)
+    fp64_peak = ctx.measure_fp64_peak()
+
+    dX, dU, dS = (torch.from_numpy(a).to(dev) for a in (X, U, sigma))
+    dOut = torch.empty((B, ni, 23, 14), dtype=torch.float64, device=dev)
+    dErr = torch.empty((B, ni, 14), dtype=torch.float64, device=dev)
+    dTlb = torch.empty((B, n_nodes, 4), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    def step_device():
+        ctx.linearize_ptr(dX.data_ptr(), dU.data_ptr(), dS.data_ptr(), dt, NPTS, args.mode, n_nodes, B,
+                          dOut.data_ptr(), dErr.data_ptr(), dTlb.data_ptr())
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    with ClockSampler(local_rank) as clk:
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        e1.record(stream)
+        barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    # per-launch kernel time of the dominant kernel, measured live (events inside the library, same stream)
+    for _ in range(3):
+        step_device()
+        torch.cuda.synchronize()
+        kern_ms.append(ctx.last_kernel_ms())
+    kern_ms = float(np.median(kern_ms))
+    finite = bool(torch.isfinite(dOut[:: max(1, B // 64)]).all().item())
+    checksum = float(dOut[:: max(1, B // 64), :, 0, :].sum().item())
+
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ok, _ = sharding.reduce_status(finite, checksum, dev)      # NCCL is used only for status / result gathering
+    else:
+        ok = finite
+    elapsed_ms = float(t.item())
+    total_intervals = B * ni * world
+    value = total_intervals * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        hX, hU, hS = (torch.from_numpy(a).pin_memory() for a in (X, U, sigma))
+        hOut = torch.empty((B, ni, 23, 14), dtype=torch.float64).pin_memory()
+        hErr = torch.empty((B, ni, 14), dtype=torch.float64).pin_memory()
+        hTlb = torch.empty((B, n_nodes, 4), dtype=torch.float64).pin_memory()
+
+        def step_host():
+            ctx.linearize_ptr(hX.data_ptr(), hU.data_ptr(), hS.data_ptr(), dt, NPTS, args.mode, n_nodes, B,
+                              hOut.data_ptr(), hErr.data_ptr(), hTlb.data_ptr())
+        for _ in range(2):
+            step_host()
+        barrier()
+        e2e_steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_host()
+        barrier()
+        el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        dev_sample = dOut[:4].cpu()
+        assert torch.equal(hOut[:4], dev_sample), "host-pointer path and device-pointer path disagree"
+        e2e = {"value": total_intervals * e2e_steps / float(el.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(hX.nbytes + hU.nbytes + hS.nbytes),
+               "d2h_bytes_per_step": int(hOut.nbytes + hErr.nbytes + hTlb.nbytes), "steps": e2e_steps,
+               "note": "pinned host buffers through scvx_linearize_batch; chunked H2D/kernel/D2H pipeline; PCIe-bound"}
+        del hOut, hErr, hTlb
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    achieved_tf = FLOP_PER_INTERVAL_AERO * (B * ni) / (kern_ms * 1e-3) * 1e-12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved_gbs = BYTES_PER_INTERVAL * (B * ni) / (kern_ms * 1e-3) * 1e-9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved_tf / fp64_peak, "traffic": traffic,
+                "flop_per_interval": FLOP_PER_INTERVAL_AERO, "kernel_ms": kern_ms,
+                "peak_source": "in-run DFMA microbenchmark (scvx_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+                "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved_gbs / hbm_peak, "bytes_per_interval": BYTES_PER_INTERVAL,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+
+    cpu = None
+    if not args.no_cpu:
+        v, threads, sample, _ = cpu_reference_run(prob, steps=1, warmup=1, traj_per_thread=400)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": sample + "; C++ restatement of the reference Julia path (Julia unavailable)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "results_finite": ok, "kernel": args.kernel}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

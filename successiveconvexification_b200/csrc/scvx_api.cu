@@ -51,6 +51,9 @@ struct Dev {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void* scratch = nullptr;           // STAGED kernel scratch (stage records)
     size_t scratch_cap = 0;
+    int sm_count = 0;
+    cudaStream_t scratch_user = nullptr;   // stream that last used the scratch
+    cudaEvent_t ev_scratch = nullptr;
 };
 
 }  // namespace
@@ -110,10 +113,34 @@ int check_ready(scvx_ctx* c, int B) {
 int launch_linearize(scvx_ctx* c, Dev& d, const ScvxBatch& bt, cudaStream_t s) {
     const ScvxTables tb = tables_of(d);
     int k = c->kernel;
-    if (k == SCVX_KERNEL_AUTO) k = SCVX_KERNEL_DUALWARP;
-    (void)k;
-    CK(scvx_launch_dualwarp(bt, tb, s));
-    c->launches += 1;
+    if (k == SCVX_KERNEL_AUTO) k = SCVX_KERNEL_STAGED;
+    if (k == SCVX_KERNEL_DUALWARP) {
+        CK(scvx_launch_dualwarp(bt, tb, s));
+        c->launches += 1;
+        return 0;
+    }
+    // STAGED: the stage-record scratch is shared by everything enqueued on this device, so work on the other
+    // pipeline stream must have consumed it before it is overwritten.
+    const long total = (long)(bt.n_nodes - 1) * bt.B;
+    int chunk = scvx_staged_chunk_intervals(d.sm_count);
+    if (total < chunk) chunk = (int)((total + 31) / 32 * 32);
+    const size_t need = scvx_staged_scratch_bytes(bt.npts, chunk);
+    if (need > d.scratch_cap) {
+        CK(cudaDeviceSynchronize());
+        if (d.scratch) cudaFree(d.scratch);
+        d.scratch = nullptr; d.scratch_cap = 0;
+        cudaError_t e = cudaMalloc(&d.scratch, need);
+        if (e != cudaSuccess) return fail(SCVX_ERR_NOMEM, "cudaMalloc(%zu B) for the stage-record scratch failed: %s", need, cudaGetErrorString(e));
+        d.scratch_cap = need;
+    }
+    if (d.scratch_user && d.scratch_user != s) {
+        CK(cudaEventRecord(d.ev_scratch, d.scratch_user));
+        CK(cudaStreamWaitEvent(s, d.ev_scratch, 0));
+    }
+    d.scratch_user = s;
+    int n = 0;
+    CK(scvx_launch_staged(bt, tb, d.scratch, chunk, d.sm_count, s, &n));
+    c->launches += n;
     return 0;
 }
 
@@ -248,6 +275,8 @@ int scvx_create(scvx_ctx** out, const int* device_ids, int n_dev) {
         for (int s = 0; s < 2 && e == cudaSuccess; ++s) e = cudaStreamCreateWithFlags(&d.slot[s].stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreate(&d.ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&d.ev1);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_scratch, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.id);
         if (e != cudaSuccess) { scvx_destroy(c); return fail(SCVX_ERR_CUDA, "context setup on device %d failed: %s", d.id, cudaGetErrorString(e)); }
     }
     *out = c;
@@ -269,6 +298,7 @@ void scvx_destroy(scvx_ctx* c) {
         if (d.scratch) cudaFree(d.scratch);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.ev_scratch) cudaEventDestroy(d.ev_scratch);
     }
     delete c;
 }

@@ -8,3 +8,9 @@ cudaError_t scvx_launch_predict(const ScvxBatch& bt, const ScvxTables& tb, cudaS
 cudaError_t scvx_launch_prefilter(const double* d_samples, int n1, int n2, double* d_tmp, double* d_coef,
                                   const double* d_cp, cudaStream_t s);
 cudaError_t scvx_launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t s);
+
+// STAGED path (scvx_kernels_staged.cu): value kernel + persistent tangent kernel, chunked over a scratch buffer.
+size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals);
+int scvx_staged_chunk_intervals(int sm_count);
+cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, void* scratch, int chunk_intervals,
+                               int sm_count, cudaStream_t s, int* launches);

@@ -1,0 +1,707 @@
+// scvx_kernels_staged.cu — the STAGED linearise-and-discretise path (sm_100a, FP64).
+//
+// The exact forward-mode Jacobian of the reference's rk4 (dynamics.jl:112-134, 311-313) is the tangent
+// recursion  K_s = J_x(Y_s) * Yt_s + J_u(Y_s) * U_s + e_sigma f(Y_s)  over the 4*npts stages.
+// The value trajectory does not depend on the tangents, so the work is split in two kernels:
+//
+//  A  stage_value_kernel : one THREAD per interval.  Integrates the 14-state value with rk4, writes the
+//     endpoint (block column 0), lin_err, the thrust-lower-bound rows, and a 25-double "stage record"
+//     (stage state m,v,q,w; stage control u; unscaled rhs f) per stage, laid out
+//     [group of 32 intervals][stage][entry][32 lanes] so that one stage of one group is one contiguous
+//     6400-byte slab.
+//
+//  B  tangent_kernel : persistent, one 256-thread CTA per SM, 32 intervals in flight per CTA.
+//     * Tangent propagation ("consumer" role): 8 lanes per interval, every lane owns two full tangent
+//       columns (rows m,v,q,w + the r rows as pure quadrature) and one light column (inputs m, v), all in
+//       registers.  Structure used: nothing depends on r; m, q, w rows of the m/v columns vanish.
+//     * Jacobian production ("producer" role): the 8 warps take turns (stage T -> warp T mod 8); the producing
+//       warp works with lane = interval (no redundancy), pulls its stage record with one TMA bulk copy
+//       (cp.async.bulk -> mbarrier), forms the sigma-scaled Jacobian blocks (78 doubles per interval) and
+//       stores them into a shared-memory ring; consumers read them back as broadcast 128-bit loads.
+//     * Ring slots are handed over with mbarriers (full/empty), so a warp that is busy producing does not
+//       stall the others until they are a whole ring ahead.
+//     Outputs [A|B-|B+|Sigma|z] go straight from registers to the 14x23 block with 16-byte stores.
+#include "scvx_common.cuh"
+#include "scvx_kernels.h"
+
+namespace {
+
+constexpr int REC = 25;          // stage record entries: m, v(3), q(4), w(3), u(3), f_m, f_v(3), f_q(4), f_w(3)
+constexpr int NJ = 78;           // Jacobian record entries per interval per stage (2 x odd: conflict-free STS.128)
+constexpr int RING = 6;          // ring slots
+constexpr int LOOKAHEAD = 4;     // producer runs this many stages ahead of the consumers (< RING)
+constexpr int GROUP = 32;        // intervals per CTA pass
+constexpr int NWARP = 8;
+
+// Jacobian record layout (doubles)
+constexpr int J_WW = 0;          // 9  sigma * d(wdot)/dw, row-major
+constexpr int J_HW = 9;          // 3  sigma*w/2
+constexpr int J_HQ = 12;         // 4  sigma*q/2
+constexpr int J_VM = 16;         // 3  sigma * d(vdot)/dm
+constexpr int J_VV = 19;         // 9  sigma * d(vdot)/dv (aero), row-major
+constexpr int J_VQ = 28;         // 12 sigma * d(vdot)/dq, row-major 3x4
+constexpr int J_G = 40;          // 4 columns (u0,u1,u2,f) x 7 rows (m, v0..2, w0..2)
+constexpr int J_FRQ = 68;        // 7  f_r (= v) and f_q of the unscaled rhs (sigma column only)
+constexpr int J_SIG = 75;        // 1  sigma
+
+struct StagedArgs {
+    ScvxBatch bt;
+    ScvxTables tb;
+    double* rec;                 // stage records of this chunk
+    long first;                  // first interval (global index) of this chunk
+    int count;                   // intervals in this chunk
+    int n_groups;                // ceil(count / 32)
+};
+
+// ------------------------------------------------------------------------------------------------
+// Kernel A: value trajectory + stage records.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rhs_value(const scvx_probinfo& P, const ScvxTables& tb, const double x[14],
+                                          const double u[3], double f[14]) {
+    // unscaled f(x,u) (dx_static without the `.* mult`, dynamics.jl:54-77)
+    rhs_t<double>(P, tb, x, u, 1.0, f);
+}
+
+__global__ void __launch_bounds__(128) stage_value_kernel(StagedArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_groups * GROUP) return;
+    const ScvxBatch& bt = a.bt;
+    const int ni = bt.n_nodes - 1;
+    const bool live = t < a.count;
+    const long w = a.first + (live ? t : a.count - 1);         // padded lanes recompute the last interval
+    const int b = (int)(w / ni), i = (int)(w % ni);
+    const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
+    const double* xin = bt.X + ((size_t)b * bt.n_nodes + i) * 14;
+    const double* uin = bt.U + ((size_t)b * bt.n_nodes + i) * 3;
+    const double sigma = bt.sigma[b];
+    double x[14], um[3], up[3];
+#pragma unroll
+    for (int r = 0; r < 14; ++r) x[r] = xin[r];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { um[c] = uin[c]; up[c] = uin[3 + c]; }
+
+    const int nst = 4 * bt.npts;
+    double* rec = a.rec + ((size_t)(t >> 5) * nst) * (REC * GROUP) + (t & 31);
+    const double h = bt.dt / (double)bt.npts;
+    const double pcs = 1.0 / (double)bt.npts;
+    const double s = (bt.mode == SCVX_MODE_LITERAL) ? 1.0 : h;
+    double pca = 0.0;
+    for (int it = 0; it < bt.npts; ++it) {
+        double acc[14], y[14];
+#pragma unroll
+        for (int r = 0; r < 14; ++r) { y[r] = x[r]; acc[r] = 0.0; }
+#pragma unroll 1
+        for (int st = 0; st < 4; ++st) {
+            const double pc = (st == 0) ? pca : (st == 3 ? pca + pcs : pca + 0.5 * pcs);
+            double uc[3], f[14];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) uc[c] = (1.0 - pc) * um[c] + pc * up[c];
+            rhs_value(P, a.tb, y, uc, f);
+            // record: m, v, q, w, u, f_m, f_v, f_q, f_w
+            double* rp = rec + (size_t)(it * 4 + st) * (REC * GROUP);
+            rp[0 * GROUP] = y[0];
+#pragma unroll
+            for (int r = 0; r < 10; ++r) rp[(1 + r) * GROUP] = y[4 + r];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) rp[(11 + c) * GROUP] = uc[c];
+            rp[14 * GROUP] = f[0];
+#pragma unroll
+            for (int r = 0; r < 10; ++r) rp[(15 + r) * GROUP] = f[4 + r];
+            const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+            const double cy = (st == 2) ? s : 0.5 * s;
+#pragma unroll
+            for (int r = 0; r < 14; ++r) {
+                const double k = f[r] * sigma;
+                acc[r] = fma(wgt, k, acc[r]);
+                y[r] = fma(cy, k, x[r]);
+            }
+        }
+        pca += pcs;
+#pragma unroll
+        for (int r = 0; r < 14; ++r) x[r] = fma(h * (1.0 / 6.0), acc[r], x[r]);
+    }
+    if (!live) return;
+    double* blk = bt.out_blocks + (size_t)w * SCVX_BLOCK_DOUBLES;
+#pragma unroll
+    for (int r = 0; r < 14; r += 2) *reinterpret_cast<double2*>(blk + r) = make_double2(x[r], x[r + 1]);
+    if (bt.out_lin_err) {
+        double* e = bt.out_lin_err + (size_t)w * 14;
+#pragma unroll
+        for (int r = 0; r < 14; r += 2) *reinterpret_cast<double2*>(e + r) = make_double2(x[r] - xin[14 + r], x[r + 1] - xin[15 + r]);
+    }
+    if (bt.out_tlb) {
+        const int last = (i == ni - 1) ? 2 : 1;
+        for (int k = 0; k < last; ++k) {
+            const double* u = uin + 3 * k;
+            const double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+            double* o = bt.out_tlb + ((size_t)b * bt.n_nodes + i + k) * 4;
+            *reinterpret_cast<double2*>(o) = make_double2(-(u[0] / nu), -(u[1] / nu));
+            *reinterpret_cast<double2*>(o + 2) = make_double2(-(u[2] / nu), P.Tmin - nu);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy helpers (PTX)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n }" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n }" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra WAIT_DONE;\n"
+        " bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// Producer role: Jacobian blocks of one stage for 32 intervals (lane = interval).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
+// spline value + gradient w.r.t. the physical coordinates (0 when strictly outside: Flat extrapolation)
+__device__ __forceinline__ void spline_grad(const double* __restrict__ coef, const ScvxTables& t, double x, double y,
+                                            double& gx, double& gy) {
+    const int L1 = t.n1 + 2;
+    double xi = (x - t.x0) * t.inv_dx + 1.0, yi = (y - t.y0) * t.inv_dy + 1.0;
+    double sx = t.inv_dx, sy = t.inv_dy;
+    if (xi > (double)t.n1) { xi = (double)t.n1; sx = 0.0; } else if (xi < 1.0) { xi = 1.0; sx = 0.0; }
+    if (yi > (double)t.n2) { yi = (double)t.n2; sy = 0.0; } else if (yi < 1.0) { yi = 1.0; sy = 0.0; }
+    int i = (int)floor(xi); i = max(min(i, t.n1 - 1), 1);
+    int j = (int)floor(yi); j = max(min(j, t.n2 - 1), 1);
+    const double dx = xi - (double)i, dy = yi - (double)j, ox = 1.0 - dx, oy = 1.0 - dy;
+    const double wx[4] = { ox * ox * ox * (1.0 / 6.0), (2.0 / 3.0) - dx * dx + 0.5 * dx * dx * dx,
+                           (2.0 / 3.0) - ox * ox + 0.5 * ox * ox * ox, dx * dx * dx * (1.0 / 6.0) };
+    const double gxw[4] = { -0.5 * ox * ox, -2.0 * dx + 1.5 * dx * dx, 2.0 * ox - 1.5 * ox * ox, 0.5 * dx * dx };
+    const double wy[4] = { oy * oy * oy * (1.0 / 6.0), (2.0 / 3.0) - dy * dy + 0.5 * dy * dy * dy,
+                           (2.0 / 3.0) - oy * oy + 0.5 * oy * oy * oy, dy * dy * dy * (1.0 / 6.0) };
+    const double gyw[4] = { -0.5 * oy * oy, -2.0 * dy + 1.5 * dy * dy, 2.0 * oy - 1.5 * oy * oy, 0.5 * dy * dy };
+    const double* base = coef + (i - 1) + (size_t)(j - 1) * L1;
+    double ax = 0.0, ay = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const double* p = base + (size_t)b * L1;
+        const double c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2), c3 = __ldg(p + 3);
+        const double rv = wx[0] * c0 + wx[1] * c1 + wx[2] * c2 + wx[3] * c3;
+        const double rg = gxw[0] * c0 + gxw[1] * c1 + gxw[2] * c2 + gxw[3] * c3;
+        ax = fma(wy[b], rg, ax);
+        ay = fma(gyw[b], rv, ay);
+    }
+    gx = ax * sx; gy = ay * sy;
+}
+
+// spline value only
+__device__ __forceinline__ double spline_val(const double* __restrict__ coef, const ScvxTables& t, double x, double y) {
+    return spline_eval<double>(coef, t, x, y);
+}
+
+// Jacobian of the aerodynamic force F(b, v) (aerodynamics.jl:38-58) w.r.t. v and b = C(q) e1: exact derivative
+// of the executed branch (|dp| >= 0.95 drag only; clamp active only strictly outside [-1,1]).
+__device__ __forceinline__ void aero_jac(const scvx_probinfo& P, const ScvxTables& tb, const double b[3],
+                                         const double v[3], double Fv[3][3], double Fb[3][3]) {
+    const double vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const double nv = sqrt(vv), inv = 1.0 / nv;
+    const double vh[3] = { v[0] * inv, v[1] * inv, v[2] * inv };
+    const double bvdot = b[0] * v[0] + b[1] * v[1] + b[2] * v[2];
+    const double dp = bvdot * inv;
+    const double nb = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]), inb = 1.0 / nb;
+    const double car = dp * inb;
+    double ca = car, mc = 1.0;
+    if (car > 1.0) { ca = 1.0; mc = 0.0; } else if (car < -1.0) { ca = -1.0; mc = 0.0; }
+    const double mach = nv * (1.0 / P.sos);
+    // d(ca)/dv, d(ca)/db ; d(mach)/dv
+    double cav[3], cab[3], mv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        cav[k] = mc * (b[k] - dp * vh[k]) * inv * inb;
+        cab[k] = mc * (vh[k] - car * b[k] * inb) * inb;
+        mv[k] = vh[k] * (1.0 / P.sos);
+    }
+    const double fs = P.force_scalar;
+    const double drag = spline_val(tb.drag, tb, ca, mach) * fs;
+    double gx, gy;
+    spline_grad(tb.drag, tb, ca, mach, gx, gy);
+    gx *= fs; gy *= fs;
+    double dv[3], db[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { dv[k] = gx * cav[k] + gy * mv[k]; db[k] = gx * cab[k]; }
+    const double dn = drag * inv;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Fv[r][c] = vh[r] * dv[c] + dn * ((r == c ? 1.0 : 0.0) - vh[r] * vh[c]);
+            Fb[r][c] = vh[r] * db[c];
+        }
+    if (fabs(dp) >= 0.95) return;
+    const double lift = spline_val(tb.lift, tb, ca, mach) * fs;
+    spline_grad(tb.lift, tb, ca, mach, gx, gy);
+    gx *= fs; gy *= fs;
+    double lv[3], lb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lv[k] = gx * cav[k] + gy * mv[k]; lb[k] = gx * cab[k]; }
+    // l = (-(v x b)) x v = v (v.b) - b (v.v)
+    const double l[3] = { v[0] * bvdot - b[0] * vv, v[1] * bvdot - b[1] * vv, v[2] * bvdot - b[2] * vv };
+    const double nl = sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]), inl = 1.0 / nl;
+    const double lh[3] = { l[0] * inl, l[1] * inl, l[2] * inl };
+    // dl/dv = (v.b) I + v b^T - 2 b v^T ;  dl/db = v v^T - (v.v) I
+    double Lv[3][3], Lb[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Lv[r][c] = (r == c ? bvdot : 0.0) + v[r] * b[c] - 2.0 * b[r] * v[c];
+            Lb[r][c] = v[r] * v[c] - (r == c ? vv : 0.0);
+        }
+    const double ln = lift * inl;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        // (I - lh lh^T) * L[:,c]
+        const double pv = lh[0] * Lv[0][c] + lh[1] * Lv[1][c] + lh[2] * Lv[2][c];
+        const double pb = lh[0] * Lb[0][c] + lh[1] * Lb[1][c] + lh[2] * Lb[2][c];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            Fv[r][c] += lh[r] * lv[c] + ln * (Lv[r][c] - lh[r] * pv);
+            Fb[r][c] += lh[r] * lb[c] + ln * (Lb[r][c] - lh[r] * pb);
+        }
+    }
+}
+
+// rec: this lane's stage record (stride GROUP doubles between entries, in shared memory);
+// out: this lane's NJ-double Jacobian record in the ring.
+__device__ __forceinline__ void produce_stage(const scvx_probinfo& P, const ScvxTables& tb, double sigma,
+                                              const double* __restrict__ rec, double* __restrict__ out) {
+    const double m = rec[0];
+    const double v[3] = { rec[1 * GROUP], rec[2 * GROUP], rec[3 * GROUP] };
+    const double q0 = rec[4 * GROUP], q1 = rec[5 * GROUP], q2 = rec[6 * GROUP], q3 = rec[7 * GROUP];
+    const double w0 = rec[8 * GROUP], w1 = rec[9 * GROUP], w2 = rec[10 * GROUP];
+    const double u0 = rec[11 * GROUP], u1 = rec[12 * GROUP], u2 = rec[13 * GROUP];
+    const double fm = rec[14 * GROUP];
+    const double fv[3] = { rec[15 * GROUP], rec[16 * GROUP], rec[17 * GROUP] };
+    const double fq[4] = { rec[18 * GROUP], rec[19 * GROUP], rec[20 * GROUP], rec[21 * GROUP] };
+    const double fw[3] = { rec[22 * GROUP], rec[23 * GROUP], rec[24 * GROUP] };
+    const double sm = sigma / m;
+
+    // ---- rotational block: Jww = -sigma * jBi * ([w]x jB - [jB w]x)
+    {
+        const double* jB = P.jB; const double* jBi = P.jBi;
+        const double L0 = jB[0] * w0 + jB[3] * w1 + jB[6] * w2;
+        const double L1 = jB[1] * w0 + jB[4] * w1 + jB[7] * w2;
+        const double L2 = jB[2] * w0 + jB[5] * w1 + jB[8] * w2;
+        double M[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {          // column c of [w]x jB = w x jB[:,c]
+            const double a0 = jB[3 * c], a1 = jB[3 * c + 1], a2 = jB[3 * c + 2];
+            M[0][c] = w1 * a2 - w2 * a1; M[1][c] = w2 * a0 - w0 * a2; M[2][c] = w0 * a1 - w1 * a0;
+        }
+        // minus [L]x = [[0,-L2,L1],[L2,0,-L0],[-L1,L0,0]]
+        M[0][1] += L2; M[0][2] -= L1; M[1][0] -= L2; M[1][2] += L0; M[2][0] += L1; M[2][1] -= L0;
+        double Jw[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                Jw[3 * r + c] = -sigma * (jBi[r] * M[0][c] + jBi[r + 3] * M[1][c] + jBi[r + 6] * M[2][c]);
+        const double hs = 0.5 * sigma;
+        st2(out + J_WW + 0, Jw[0], Jw[1]); st2(out + J_WW + 2, Jw[2], Jw[3]); st2(out + J_WW + 4, Jw[4], Jw[5]);
+        st2(out + J_WW + 6, Jw[6], Jw[7]); st2(out + J_WW + 8, Jw[8], hs * w0);
+        st2(out + J_HW + 1, hs * w1, hs * w2);
+        st2(out + J_HQ + 0, hs * q0, hs * q1); st2(out + J_HQ + 2, hs * q2, hs * q3);
+    }
+    // ---- translational block
+    const double c00 = 1.0 - 2.0 * (q2 * q2 + q3 * q3), c01 = 2.0 * (q1 * q2 - q0 * q3), c02 = 2.0 * (q1 * q3 + q0 * q2);
+    const double c10 = 2.0 * (q1 * q2 + q0 * q3), c11 = 1.0 - 2.0 * (q1 * q1 + q3 * q3), c12 = 2.0 * (q2 * q3 - q0 * q1);
+    const double c20 = 2.0 * (q1 * q3 - q0 * q2), c21 = 2.0 * (q2 * q3 + q0 * q1), c22 = 1.0 - 2.0 * (q1 * q1 + q2 * q2);
+    // d(C u)/dq, row-major 3x4
+    double Jq[12];
+    Jq[0] = 2.0 * (q2 * u2 - q3 * u1);             Jq[1] = 2.0 * (q2 * u1 + q3 * u2);
+    Jq[2] = 2.0 * (q1 * u1 + q0 * u2) - 4.0 * q2 * u0; Jq[3] = 2.0 * (q1 * u2 - q0 * u1) - 4.0 * q3 * u0;
+    Jq[4] = 2.0 * (q3 * u0 - q1 * u2);             Jq[5] = 2.0 * (q2 * u0 - q0 * u2) - 4.0 * q1 * u1;
+    Jq[6] = 2.0 * (q1 * u0 + q3 * u2);             Jq[7] = 2.0 * (q0 * u0 + q2 * u2) - 4.0 * q3 * u1;
+    Jq[8] = 2.0 * (q1 * u1 - q2 * u0);             Jq[9] = 2.0 * (q3 * u0 + q0 * u1) - 4.0 * q1 * u2;
+    Jq[10] = 2.0 * (q3 * u1 - q0 * u0) - 4.0 * q2 * u2; Jq[11] = 2.0 * (q1 * u0 + q2 * u1);
+    double Jvv[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    if (P.aero_kind == SCVX_AERO_TABLE) {
+        const double bvec[3] = { c00, c10, c20 };
+        double Fv[3][3], Fb[3][3];
+        aero_jac(P, tb, bvec, v, Fv, Fb);
+        // db/dq
+        const double B[3][4] = { { 0.0, 0.0, -4.0 * q2, -4.0 * q3 },
+                                 { 2.0 * q3, 2.0 * q2, 2.0 * q1, 2.0 * q0 },
+                                 { -2.0 * q2, 2.0 * q3, -2.0 * q0, 2.0 * q1 } };
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) Jq[4 * r + c] += Fb[r][0] * B[0][c] + Fb[r][1] * B[1][c] + Fb[r][2] * B[2][c];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Jvv[3 * r + c] = sm * Fv[r][c];
+        }
+    }
+    // Jvm = -sigma * ((C u + F)/m) / m = -(sigma/m) * (f_v + g0 e1)
+    st2(out + J_VM + 0, -sm * (fv[0] + P.g0), -sm * fv[1]);
+    st2(out + J_VM + 2, -sm * fv[2], Jvv[0]);
+    st2(out + J_VV + 1, Jvv[1], Jvv[2]); st2(out + J_VV + 3, Jvv[3], Jvv[4]);
+    st2(out + J_VV + 5, Jvv[5], Jvv[6]); st2(out + J_VV + 7, Jvv[7], Jvv[8]);
+#pragma unroll
+    for (int k = 0; k < 12; k += 2) st2(out + J_VQ + k, sm * Jq[k], sm * Jq[k + 1]);
+    // ---- direct (control / sigma) columns: G[col][row], rows m, v0..2, w0..2
+    const double nu = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
+    const double gm = -sigma * P.a / nu;
+    const double* jBi = P.jBi; const double* rT = P.rTB;
+    // jBi * (rTB x e_j): rTB x e0 = (0, r2, -r1); x e1 = (-r2, 0, r0); x e2 = (r1, -r0, 0)
+    double G[28];
+    G[0] = gm * u0; G[1] = sm * c00; G[2] = sm * c10; G[3] = sm * c20;
+    G[4] = sigma * (jBi[3] * rT[2] - jBi[6] * rT[1]); G[5] = sigma * (jBi[4] * rT[2] - jBi[7] * rT[1]); G[6] = sigma * (jBi[5] * rT[2] - jBi[8] * rT[1]);
+    G[7] = gm * u1; G[8] = sm * c01; G[9] = sm * c11; G[10] = sm * c21;
+    G[11] = sigma * (jBi[6] * rT[0] - jBi[0] * rT[2]); G[12] = sigma * (jBi[7] * rT[0] - jBi[1] * rT[2]); G[13] = sigma * (jBi[8] * rT[0] - jBi[2] * rT[2]);
+    G[14] = gm * u2; G[15] = sm * c02; G[16] = sm * c12; G[17] = sm * c22;
+    G[18] = sigma * (jBi[0] * rT[1] - jBi[3] * rT[0]); G[19] = sigma * (jBi[1] * rT[1] - jBi[4] * rT[0]); G[20] = sigma * (jBi[2] * rT[1] - jBi[5] * rT[0]);
+    G[21] = fm; G[22] = fv[0]; G[23] = fv[1]; G[24] = fv[2]; G[25] = fw[0]; G[26] = fw[1]; G[27] = fw[2];
+#pragma unroll
+    for (int k = 0; k < 28; k += 2) st2(out + J_G + k, G[k], G[k + 1]);
+    st2(out + J_FRQ + 0, v[0], v[1]); st2(out + J_FRQ + 2, v[2], fq[0]);
+    st2(out + J_FRQ + 4, fq[1], fq[2]); st2(out + J_FRQ + 6, fq[3], sigma);
+    st2(out + J_FRQ + 8, 0.0, 0.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel B
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) TangentSmem {
+    double ring[RING][GROUP][NJ];            // Jacobian records
+    double recbuf[NWARP][REC * GROUP];       // per-warp stage-record staging (TMA destination)
+    uint64_t full[RING];
+    uint64_t empty[RING];
+    uint64_t recfull[NWARP];
+};
+
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// one full tangent column: rows m, v(3), q(4), w(3) carried as (S, acc, Y); r rows as a pure quadrature
+struct FullCol {
+    double S[11], A[11], Y[11], Sr[3];
+};
+struct LightCol {
+    double S[3], A[3], Y[3], Sr[3];
+};
+
+__global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TangentSmem& sm = *reinterpret_cast<TangentSmem*>(smem_raw);
+    const ScvxBatch& bt = a.bt;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int l8 = lane & 7;                   // column-group lane within the interval
+    const int sub = lane >> 3;                 // interval within the warp (0..3)
+    const int ni = bt.n_nodes - 1;
+    const int nst = 4 * bt.npts;
+    const double h = bt.dt / (double)bt.npts;
+    const double pcs = 1.0 / (double)bt.npts;
+    const double sstep = (bt.mode == SCVX_MODE_LITERAL) ? 1.0 : h;
+    const double h6 = h * (1.0 / 6.0);
+
+    if (tid == 0) {
+        for (int r = 0; r < RING; ++r) { mbar_init(&sm.full[r], 32); mbar_init(&sm.empty[r], NWARP); }
+        for (int wq = 0; wq < NWARP; ++wq) mbar_init(&sm.recfull[wq], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // groups handled by this CTA: g = blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int my_groups = (a.n_groups > (int)blockIdx.x) ? (a.n_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const long total_stages = (long)my_groups * nst;       // global stage counter T = it * nst + s
+
+    // ---- static per-lane column configuration
+    // full slots: lanes 0..2: (u-_j, u+_j); lane 3: (sigma, -); lane 4: (w0,w1); 5: (w2,q0); 6: (q1,q2); 7: (q3,-)
+    int colA, colB, colL, gcol;
+    double a0A, a1A, a0B, a1B, dsA, betaL;
+    {
+        colA = -1; colB = -1; colL = -1; gcol = 3;
+        a0A = a1A = a0B = a1B = dsA = betaL = 0.0;
+        if (l8 < 3) { colA = 14 + l8; colB = 17 + l8; gcol = l8; a0A = 1.0; a1A = -1.0; a0B = 0.0; a1B = 1.0; }
+        else if (l8 == 3) { colA = 20; a0A = 1.0; dsA = 1.0; }
+        else if (l8 == 4) { colA = 11; colB = 12; }
+        else if (l8 == 5) { colA = 13; colB = 7; }
+        else if (l8 == 6) { colA = 8; colB = 9; }
+        else { colA = 10; }
+        if (l8 == 0) { colL = 0; betaL = 1.0; }
+        else if (l8 < 4) colL = 3 + l8;            // v0..v2 -> inp columns 4,5,6
+    }
+
+    // producer bookkeeping: this warp produces global stages T with T % NWARP == warp
+    long nextP = warp;                               // next stage this warp has to produce
+    uint32_t rec_phase = 0;
+    auto issue_record = [&](long T) {                // lane 0 only: TMA the stage record of global stage T
+        const int it = (int)(T / nst), s = (int)(T % nst);
+        const int g = blockIdx.x + it * gridDim.x;
+        const double* src = a.rec + ((size_t)g * nst + s) * (REC * GROUP);
+        mbar_expect_tx(&sm.recfull[warp], REC * GROUP * 8);
+        bulk_g2s(sm.recbuf[warp], src, REC * GROUP * 8, &sm.recfull[warp]);
+    };
+    if (lane == 0 && nextP < total_stages) issue_record(nextP);
+
+    auto produce = [&](long T) {
+        const int it = (int)(T / nst);
+        const int g = blockIdx.x + it * gridDim.x;
+        int t = g * GROUP + lane; if (t >= a.count) t = a.count - 1;
+        const long wi = a.first + t;
+        const int b = (int)(wi / ni);
+        const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
+        const double sigma = bt.sigma[b];
+        const int slot = (int)(T % RING);
+        const long use = T / RING;
+        mbar_wait(&sm.recfull[warp], rec_phase); rec_phase ^= 1;
+        if (use > 0) mbar_wait(&sm.empty[slot], (uint32_t)((use - 1) & 1));
+        produce_stage(P, a.tb, sigma, sm.recbuf[warp] + lane, &sm.ring[slot][lane][0]);
+        mbar_arrive(&sm.full[slot]);
+        __syncwarp();
+        if (lane == 0 && T + NWARP < total_stages) { fence_proxy_async(); issue_record(T + NWARP); }
+    };
+
+    // prologue: stages 0..LOOKAHEAD-1
+    for (int k = 0; k < LOOKAHEAD; ++k)
+        if (nextP == k && nextP < total_stages) { produce(nextP); nextP += NWARP; }
+
+    FullCol FA, FB;
+    LightCol FL;
+    long T = 0;
+    for (int it = 0; it < my_groups; ++it) {
+        const int g = blockIdx.x + it * gridDim.x;
+        // ---- initial tangent: S = [I | 0]
+#pragma unroll
+        for (int r = 0; r < 11; ++r) {
+            // local row order of a full column: 0 m, 1..3 v, 4..7 q, 8..10 w  (inp column of local row r >= 4 is r + 3)
+            FA.S[r] = (r >= 4 && colA == r + 3) ? 1.0 : 0.0;
+            FB.S[r] = (r >= 4 && colB == r + 3) ? 1.0 : 0.0;
+            FA.A[r] = 0.0; FB.A[r] = 0.0;
+            FA.Y[r] = FA.S[r]; FB.Y[r] = FB.S[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            FA.Sr[r] = FB.Sr[r] = FL.Sr[r] = 0.0;
+            FL.S[r] = (colL == r + 4) ? 1.0 : 0.0;
+            FL.A[r] = 0.0; FL.Y[r] = FL.S[r];
+        }
+
+        double pca = 0.0;
+        for (int s = 0; s < nst; ++s, ++T) {
+            // producer duty for stage T + LOOKAHEAD
+            if (nextP == T + LOOKAHEAD && nextP < total_stages) { produce(nextP); nextP += NWARP; }
+
+            const int st = s & 3;
+            const double pc = (st == 0) ? pca : (st == 3 ? pca + pcs : pca + 0.5 * pcs);
+            const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+            const double cy = (st == 2) ? sstep : 0.5 * sstep;
+            const double cr = h6 * wgt;
+            const double alA = fma(a1A, pc, a0A), alB = fma(a1B, pc, a0B);
+            const int slot = (int)(T % RING);
+            mbar_wait(&sm.full[slot], (uint32_t)((T / RING) & 1));
+            const double* J = &sm.ring[slot][warp * 4 + sub][0];
+            const double* Gc = J + J_G + 7 * gcol;
+            double KA[11], KB[11], KL[3];
+
+            // ---- w rows: K_w = Jww * Y_w + alpha * G_w
+            {
+                const double2 j01 = ld2(J + J_WW), j23 = ld2(J + J_WW + 2), j45 = ld2(J + J_WW + 4), j67 = ld2(J + J_WW + 6);
+                const double j8 = J[J_WW + 8];
+                const double g0 = Gc[4], g1 = Gc[5], g2 = Gc[6];
+                KA[8] = fma(j01.x, FA.Y[8], fma(j01.y, FA.Y[9], fma(j23.x, FA.Y[10], alA * g0)));
+                KA[9] = fma(j23.y, FA.Y[8], fma(j45.x, FA.Y[9], fma(j45.y, FA.Y[10], alA * g1)));
+                KA[10] = fma(j67.x, FA.Y[8], fma(j67.y, FA.Y[9], fma(j8, FA.Y[10], alA * g2)));
+                KB[8] = fma(j01.x, FB.Y[8], fma(j01.y, FB.Y[9], fma(j23.x, FB.Y[10], alB * g0)));
+                KB[9] = fma(j23.y, FB.Y[8], fma(j45.x, FB.Y[9], fma(j45.y, FB.Y[10], alB * g1)));
+                KB[10] = fma(j67.x, FB.Y[8], fma(j67.y, FB.Y[9], fma(j8, FB.Y[10], alB * g2)));
+            }
+            // ---- q rows: K_q = Omega(hw) Y_q + Omega(Y_w) hq + dsigma * f_q
+            {
+                const double hw0 = J[J_HW], hw1 = J[J_HW + 1], hw2 = J[J_HW + 2];
+                const double2 hq01 = ld2(J + J_HQ), hq23 = ld2(J + J_HQ + 2);
+                const double hq0 = hq01.x, hq1 = hq01.y, hq2 = hq23.x, hq3 = hq23.y;
+                const double fq0 = J[J_FRQ + 3];
+                const double2 fq12 = ld2(J + J_FRQ + 4);
+                const double fq3 = J[J_FRQ + 6];
+#define QROWS(F, K, ds)                                                                                                   \
+                K[4] = fma(-hw0, F.Y[5], fma(-hw1, F.Y[6], fma(-hw2, F.Y[7], fma(-hq1, F.Y[8], fma(-hq2, F.Y[9], fma(-hq3, F.Y[10], ds * fq0)))))); \
+                K[5] = fma(hw0, F.Y[4], fma(hw2, F.Y[6], fma(-hw1, F.Y[7], fma(hq0, F.Y[8], fma(hq2, F.Y[10], fma(-hq3, F.Y[9], ds * fq12.x)))))); \
+                K[6] = fma(hw1, F.Y[4], fma(-hw2, F.Y[5], fma(hw0, F.Y[7], fma(hq0, F.Y[9], fma(-hq1, F.Y[10], fma(hq3, F.Y[8], ds * fq12.y)))))); \
+                K[7] = fma(hw2, F.Y[4], fma(hw1, F.Y[5], fma(-hw0, F.Y[6], fma(hq0, F.Y[10], fma(hq1, F.Y[9], fma(-hq2, F.Y[8], ds * fq3))))));
+                QROWS(FA, KA, dsA)
+                QROWS(FB, KB, 0.0)
+#undef QROWS
+            }
+            // ---- v rows: K_v = Jvm Y_m + Jvv Y_v + Jvq Y_q + alpha * G_v ; light: Jvv Y_v + beta Jvm
+            {
+                const double2 m01 = ld2(J + J_VM);
+                const double2 m2v0 = ld2(J + J_VM + 2);           // Jvm[2], Jvv[0]
+                const double2 v12 = ld2(J + J_VV + 1), v34 = ld2(J + J_VV + 3), v56 = ld2(J + J_VV + 5), v78 = ld2(J + J_VV + 7);
+                const double g0 = Gc[1], g1 = Gc[2], g2 = Gc[3];
+#define VROW(row, jm, a, b, c, gg)                                                                                      \
+                {                                                                                                         \
+                    const double2 qa = ld2(J + J_VQ + 4 * row), qb = ld2(J + J_VQ + 4 * row + 2);                         \
+                    KA[1 + row] = fma(jm, FA.Y[0], fma(a, FA.Y[1], fma(b, FA.Y[2], fma(c, FA.Y[3], fma(qa.x, FA.Y[4], fma(qa.y, FA.Y[5], fma(qb.x, FA.Y[6], fma(qb.y, FA.Y[7], alA * gg)))))))); \
+                    KB[1 + row] = fma(jm, FB.Y[0], fma(a, FB.Y[1], fma(b, FB.Y[2], fma(c, FB.Y[3], fma(qa.x, FB.Y[4], fma(qa.y, FB.Y[5], fma(qb.x, FB.Y[6], fma(qb.y, FB.Y[7], alB * gg)))))))); \
+                    KL[row] = fma(a, FL.Y[0], fma(b, FL.Y[1], fma(c, FL.Y[2], betaL * jm)));                              \
+                }
+                VROW(0, m01.x, m2v0.y, v12.x, v12.y, g0)
+                VROW(1, m01.y, v34.x, v34.y, v56.x, g1)
+                VROW(2, m2v0.x, v56.y, v78.x, v78.y, g2)
+#undef VROW
+            }
+            // ---- m row and r rows (quadrature): S_r += cr * (sigma * Y_v + dsigma * f_r)
+            {
+                KA[0] = alA * Gc[0];
+                KB[0] = alB * Gc[0];
+                const double2 fr01 = ld2(J + J_FRQ);
+                const double fr2 = J[J_FRQ + 2];
+                const double sg = J[J_FRQ + 7];
+                const double csg = cr * sg, cds = cr * dsA;
+                FA.Sr[0] = fma(csg, FA.Y[1], fma(cds, fr01.x, FA.Sr[0]));
+                FA.Sr[1] = fma(csg, FA.Y[2], fma(cds, fr01.y, FA.Sr[1]));
+                FA.Sr[2] = fma(csg, FA.Y[3], fma(cds, fr2, FA.Sr[2]));
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    FB.Sr[r] = fma(csg, FB.Y[1 + r], FB.Sr[r]);
+                    FL.Sr[r] = fma(csg, FL.Y[r], FL.Sr[r]);
+                }
+            }
+            // all reads of the ring slot are done: hand it back
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[slot]);
+
+            // ---- RK bookkeeping
+            if (st != 3) {
+#pragma unroll
+                for (int r = 0; r < 11; ++r) {
+                    FA.A[r] = fma(wgt, KA[r], FA.A[r]); FA.Y[r] = fma(cy, KA[r], FA.S[r]);
+                    FB.A[r] = fma(wgt, KB[r], FB.A[r]); FB.Y[r] = fma(cy, KB[r], FB.S[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { FL.A[r] = fma(wgt, KL[r], FL.A[r]); FL.Y[r] = fma(cy, KL[r], FL.S[r]); }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 11; ++r) {
+                    FA.S[r] = fma(h6, FA.A[r] + KA[r], FA.S[r]); FA.Y[r] = FA.S[r]; FA.A[r] = 0.0;
+                    FB.S[r] = fma(h6, FB.A[r] + KB[r], FB.S[r]); FB.Y[r] = FB.S[r]; FB.A[r] = 0.0;
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { FL.S[r] = fma(h6, FL.A[r] + KL[r], FL.S[r]); FL.Y[r] = FL.S[r]; FL.A[r] = 0.0; }
+                pca += pcs;
+            }
+        }
+
+        // ---- epilogue: write D columns and z for interval (g*32 + warp*4 + sub)
+        const int t = g * GROUP + warp * 4 + sub;
+        const bool live = t < a.count;
+        const long wi = a.first + (live ? t : a.count - 1);
+        const int b = (int)(wi / ni), i = (int)(wi % ni);
+        double* blk = bt.out_blocks + (size_t)wi * SCVX_BLOCK_DOUBLES;
+        const double* xin = bt.X + ((size_t)b * bt.n_nodes + i) * 14;
+        const double* uin = bt.U + ((size_t)b * bt.n_nodes + i) * 3;
+        auto inp_of = [&](int c) -> double {
+            if (c < 0) return 0.0;
+            if (c < 14) return xin[c];
+            if (c < 20) return uin[c - 14];
+            return bt.sigma[b];
+        };
+        double zp[14];
+#pragma unroll
+        for (int r = 0; r < 14; ++r) zp[r] = 0.0;
+        auto emit_full = [&](const FullCol& F, int c) {
+            if (c < 0) return;
+            // state row order: m, r(3), v(3), q(4), w(3)
+            const double col[14] = { F.S[0], F.Sr[0], F.Sr[1], F.Sr[2], F.S[1], F.S[2], F.S[3], F.S[4], F.S[5], F.S[6], F.S[7],
+                                     F.S[8], F.S[9], F.S[10] };
+            const double xc = inp_of(c);
+            double* o = blk + 14 * (1 + c);
+#pragma unroll
+            for (int r = 0; r < 14; r += 2) {
+                if (live) *reinterpret_cast<double2*>(o + r) = make_double2(col[r], col[r + 1]);
+                zp[r] = fma(col[r], xc, zp[r]); zp[r + 1] = fma(col[r + 1], xc, zp[r + 1]);
+            }
+        };
+        emit_full(FA, colA);
+        emit_full(FB, colB);
+        if (colL >= 0) {
+            const double col[14] = { colL == 0 ? 1.0 : 0.0, FL.Sr[0], FL.Sr[1], FL.Sr[2], FL.S[0], FL.S[1], FL.S[2], 0, 0, 0, 0, 0, 0, 0 };
+            const double xc = inp_of(colL);
+            double* o = blk + 14 * (1 + colL);
+#pragma unroll
+            for (int r = 0; r < 14; r += 2) {
+                if (live) *reinterpret_cast<double2*>(o + r) = make_double2(col[r], col[r + 1]);
+                zp[r] = fma(col[r], xc, zp[r]); zp[r + 1] = fma(col[r + 1], xc, zp[r + 1]);
+            }
+        } else if (l8 >= 4 && l8 < 7) {
+            // position columns: D[:, r_j] = e_{r_j} exactly (nothing depends on position)
+            const int c = l8 - 3;                    // inp columns 1,2,3
+            double* o = blk + 14 * (1 + c);
+#pragma unroll
+            for (int r = 0; r < 14; r += 2)
+                if (live) *reinterpret_cast<double2*>(o + r) = make_double2(r == c ? 1.0 : 0.0, r + 1 == c ? 1.0 : 0.0);
+            zp[c] += xin[c];
+        }
+        // z = endpoint - D * inp  (sum of the 8 lanes of this interval)
+#pragma unroll
+        for (int r = 0; r < 14; ++r) {
+            double v = zp[r];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            zp[r] = v;
+        }
+        if (live && l8 == 7) {
+            double* o = blk + 14 * 22;
+#pragma unroll
+            for (int r = 0; r < 14; r += 2) {
+                const double2 e = *reinterpret_cast<const double2*>(blk + r);      // endpoint written by kernel A
+                *reinterpret_cast<double2*>(o + r) = make_double2(e.x - zp[r], e.y - zp[r + 1]);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals) {
+    const size_t groups = ((size_t)chunk_intervals + GROUP - 1) / GROUP;
+    return groups * (size_t)(4 * npts) * REC * GROUP * sizeof(double);
+}
+
+int scvx_staged_chunk_intervals(int sm_count) { return sm_count * GROUP * 14; }
+
+cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, void* scratch, int chunk_intervals,
+                               int sm_count, cudaStream_t s, int* launches) {
+    const long total = (long)(bt.n_nodes - 1) * bt.B;
+    const size_t smem = sizeof(TangentSmem);
+    {
+        cudaError_t e = cudaFuncSetAttribute(tangent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    for (long first = 0; first < total; first += chunk_intervals) {
+        StagedArgs a;
+        a.bt = bt; a.tb = tb; a.rec = (double*)scratch; a.first = first;
+        a.count = (int)((total - first < chunk_intervals) ? (total - first) : chunk_intervals);
+        a.n_groups = (a.count + GROUP - 1) / GROUP;
+        const int threads = a.n_groups * GROUP;
+        stage_value_kernel<<<(threads + 127) / 128, 128, 0, s>>>(a);
+        const int grid = a.n_groups < sm_count ? a.n_groups : sm_count;
+        tangent_kernel<<<grid, 256, smem, s>>>(a);
+        if (launches) *launches += 2;
+    }
+    return cudaGetLastError();
+}
