@@ -66,6 +66,7 @@ struct scvx_ctx {
     int64_t launches = 0;
     bool timed = false;
     std::vector<scvx_probinfo> hP;
+    bool any_aero = false;
 };
 
 namespace {
@@ -139,7 +140,7 @@ int launch_linearize(scvx_ctx* c, Dev& d, const ScvxBatch& bt, cudaStream_t s) {
     }
     d.scratch_user = s;
     int n = 0;
-    CK(scvx_launch_staged(bt, tb, d.scratch, chunk, d.sm_count, s, &n));
+    CK(scvx_launch_staged(bt, tb, c->any_aero, d.scratch, chunk, d.sm_count, s, &n));
     c->launches += n;
     return 0;
 }
@@ -309,6 +310,8 @@ int scvx_set_params(scvx_ctx* c, const scvx_probinfo* p, int n) {
         if (p[i].aero_kind != SCVX_AERO_EXO && p[i].aero_kind != SCVX_AERO_TABLE)
             return fail(SCVX_ERR_ARG, "record %d: unknown aero_kind %d", i, p[i].aero_kind);
     c->hP.assign(p, p + n);
+    c->any_aero = false;
+    for (int i = 0; i < n; ++i) if (p[i].aero_kind == SCVX_AERO_TABLE) c->any_aero = true;
     for (Dev& d : c->devs) {
         CK(cudaSetDevice(d.id));
         CK(cudaStreamSynchronize(d.slot[0].stream));

@@ -26,10 +26,12 @@
 
 namespace {
 
-constexpr int REC = 25;          // stage record entries: m, v(3), q(4), w(3), u(3), f_m, f_v(3), f_q(4), f_w(3)
+constexpr int REC_EXO = 25;      // stage record entries: m, v(3), q(4), w(3), u(3), f_m, f_v(3), f_q(4), f_w(3)
+constexpr int REC_AERO = 43;     // + dF_aero/dv (9, row-major) + dF_aero/db (9), b = C(q) e1
+constexpr int REC_MAX = REC_AERO;
 constexpr int NJ = 78;           // Jacobian record entries per interval per stage (2 x odd: conflict-free STS.128)
-constexpr int RING = 6;          // ring slots
-constexpr int LOOKAHEAD = 4;     // producer runs this many stages ahead of the consumers (< RING)
+constexpr int RING = 5;          // ring slots
+constexpr int LOOKAHEAD = 3;     // producer runs this many stages ahead of the consumers (< RING)
 constexpr int GROUP = 32;        // intervals per CTA pass
 constexpr int NWARP = 8;
 
@@ -48,7 +50,8 @@ struct StagedArgs {
     ScvxBatch bt;
     ScvxTables tb;
     double* rec;                 // stage records of this chunk
-    long first;                  // first interval (global index) of this chunk
+    int rec_n;                   // entries per stage record (REC_EXO or REC_AERO)
+    int first;                   // first interval (global index) of this chunk (total intervals < 2^31)
     int count;                   // intervals in this chunk
     int n_groups;                // ceil(count / 32)
 };
@@ -56,19 +59,166 @@ struct StagedArgs {
 // ------------------------------------------------------------------------------------------------
 // Kernel A: value trajectory + stage records.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void rhs_value(const scvx_probinfo& P, const ScvxTables& tb, const double x[14],
-                                          const double u[3], double f[14]) {
-    // unscaled f(x,u) (dx_static without the `.* mult`, dynamics.jl:54-77)
-    rhs_t<double>(P, tb, x, u, 1.0, f);
+// spline value + gradient w.r.t. the physical coordinates (0 when strictly outside: Flat extrapolation)
+__device__ __forceinline__ void spline_grad(const double* __restrict__ coef, const ScvxTables& t, double x, double y,
+                                            double& gx, double& gy) {
+    const int L1 = t.n1 + 2;
+    double xi = (x - t.x0) * t.inv_dx + 1.0, yi = (y - t.y0) * t.inv_dy + 1.0;
+    double sx = t.inv_dx, sy = t.inv_dy;
+    if (xi > (double)t.n1) { xi = (double)t.n1; sx = 0.0; } else if (xi < 1.0) { xi = 1.0; sx = 0.0; }
+    if (yi > (double)t.n2) { yi = (double)t.n2; sy = 0.0; } else if (yi < 1.0) { yi = 1.0; sy = 0.0; }
+    int i = (int)floor(xi); i = max(min(i, t.n1 - 1), 1);
+    int j = (int)floor(yi); j = max(min(j, t.n2 - 1), 1);
+    const double dx = xi - (double)i, dy = yi - (double)j, ox = 1.0 - dx, oy = 1.0 - dy;
+    const double wx[4] = { ox * ox * ox * (1.0 / 6.0), (2.0 / 3.0) - dx * dx + 0.5 * dx * dx * dx,
+                           (2.0 / 3.0) - ox * ox + 0.5 * ox * ox * ox, dx * dx * dx * (1.0 / 6.0) };
+    const double gxw[4] = { -0.5 * ox * ox, -2.0 * dx + 1.5 * dx * dx, 2.0 * ox - 1.5 * ox * ox, 0.5 * dx * dx };
+    const double wy[4] = { oy * oy * oy * (1.0 / 6.0), (2.0 / 3.0) - dy * dy + 0.5 * dy * dy * dy,
+                           (2.0 / 3.0) - oy * oy + 0.5 * oy * oy * oy, dy * dy * dy * (1.0 / 6.0) };
+    const double gyw[4] = { -0.5 * oy * oy, -2.0 * dy + 1.5 * dy * dy, 2.0 * oy - 1.5 * oy * oy, 0.5 * dy * dy };
+    const double* base = coef + (i - 1) + (size_t)(j - 1) * L1;
+    double ax = 0.0, ay = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const double* p = base + (size_t)b * L1;
+        const double c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2), c3 = __ldg(p + 3);
+        const double rv = wx[0] * c0 + wx[1] * c1 + wx[2] * c2 + wx[3] * c3;
+        const double rg = gxw[0] * c0 + gxw[1] * c1 + gxw[2] * c2 + gxw[3] * c3;
+        ax = fma(wy[b], rg, ax);
+        ay = fma(gyw[b], rv, ay);
+    }
+    gx = ax * sx; gy = ay * sy;
 }
 
-__global__ void __launch_bounds__(128) stage_value_kernel(StagedArgs a) {
+// spline value only
+__device__ __forceinline__ double spline_val(const double* __restrict__ coef, const ScvxTables& t, double x, double y) {
+    return spline_eval<double>(coef, t, x, y);
+}
+
+// Jacobian of the aerodynamic force F(b, v) (aerodynamics.jl:38-58) w.r.t. v and b = C(q) e1: exact derivative
+// of the executed branch (|dp| >= 0.95 drag only; clamp active only strictly outside [-1,1]).
+__device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const ScvxTables& tb, const double b[3],
+                                               const double v[3], double F[3], double Fv[3][3], double Fb[3][3]) {
+    const double vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const double nv = sqrt(vv), inv = 1.0 / nv;
+    const double vh[3] = { v[0] * inv, v[1] * inv, v[2] * inv };
+    const double bvdot = b[0] * v[0] + b[1] * v[1] + b[2] * v[2];
+    const double dp = bvdot * inv;
+    const double nb = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]), inb = 1.0 / nb;
+    const double car = dp * inb;
+    double ca = car, mc = 1.0;
+    if (car > 1.0) { ca = 1.0; mc = 0.0; } else if (car < -1.0) { ca = -1.0; mc = 0.0; }
+    const double mach = nv * (1.0 / P.sos);
+    // d(ca)/dv, d(ca)/db ; d(mach)/dv
+    double cav[3], cab[3], mv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        cav[k] = mc * (b[k] - dp * vh[k]) * inv * inb;
+        cab[k] = mc * (vh[k] - car * b[k] * inb) * inb;
+        mv[k] = vh[k] * (1.0 / P.sos);
+    }
+    const double fs = P.force_scalar;
+    const double drag = spline_val(tb.drag, tb, ca, mach) * fs;
+    double gx, gy;
+    spline_grad(tb.drag, tb, ca, mach, gx, gy);
+    gx *= fs; gy *= fs;
+    double dv[3], db[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { dv[k] = gx * cav[k] + gy * mv[k]; db[k] = gx * cab[k]; }
+    const double dn = drag * inv;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        F[r] = dn * v[r];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Fv[r][c] = vh[r] * dv[c] + dn * ((r == c ? 1.0 : 0.0) - vh[r] * vh[c]);
+            Fb[r][c] = vh[r] * db[c];
+        }
+    }
+    if (fabs(dp) >= 0.95) return;
+    const double lift = spline_val(tb.lift, tb, ca, mach) * fs;
+    spline_grad(tb.lift, tb, ca, mach, gx, gy);
+    gx *= fs; gy *= fs;
+    double lv[3], lb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lv[k] = gx * cav[k] + gy * mv[k]; lb[k] = gx * cab[k]; }
+    // l = (-(v x b)) x v = v (v.b) - b (v.v)
+    const double l[3] = { v[0] * bvdot - b[0] * vv, v[1] * bvdot - b[1] * vv, v[2] * bvdot - b[2] * vv };
+    const double nl = sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]), inl = 1.0 / nl;
+    const double lh[3] = { l[0] * inl, l[1] * inl, l[2] * inl };
+    // dl/dv = (v.b) I + v b^T - 2 b v^T ;  dl/db = v v^T - (v.v) I
+    double Lv[3][3], Lb[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Lv[r][c] = (r == c ? bvdot : 0.0) + v[r] * b[c] - 2.0 * b[r] * v[c];
+            Lb[r][c] = v[r] * v[c] - (r == c ? vv : 0.0);
+        }
+    const double ln = lift * inl;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) F[r] = fma(ln, l[r], F[r]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        // (I - lh lh^T) * L[:,c]
+        const double pv = lh[0] * Lv[0][c] + lh[1] * Lv[1][c] + lh[2] * Lv[2][c];
+        const double pb = lh[0] * Lb[0][c] + lh[1] * Lb[1][c] + lh[2] * Lb[2][c];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            Fv[r][c] += lh[r] * lv[c] + ln * (Lv[r][c] - lh[r] * pv);
+            Fb[r][c] += lh[r] * lb[c] + ln * (Lb[r][c] - lh[r] * pb);
+        }
+    }
+}
+
+// unscaled f(x,u) (dx_static without the `.* mult`, dynamics.jl:54-77) together with the Jacobians of the
+// aerodynamic force w.r.t. v and b = C(q) e1 (zero for the exo-atmospheric variant).
+__device__ __forceinline__ void rhs_value(const scvx_probinfo& P, const ScvxTables& tb, const double x[14],
+                                          const double u[3], double f[14], double Fv[3][3], double Fb[3][3]) {
+    const double q0 = x[7], q1 = x[8], q2 = x[9], q3 = x[10];
+    const double w0 = x[11], w1 = x[12], w2 = x[13];
+    const double p1 = q1 * q2, p2 = q0 * q3, p3 = q1 * q3, p4 = q0 * q2, p5 = q2 * q3, p6 = q0 * q1;
+    const double c00 = 1.0 - 2.0 * (q2 * q2 + q3 * q3), c01 = 2.0 * (p1 - p2), c02 = 2.0 * (p3 + p4);
+    const double c10 = 2.0 * (p1 + p2), c11 = 1.0 - 2.0 * (q1 * q1 + q3 * q3), c12 = 2.0 * (p5 - p6);
+    const double c20 = 2.0 * (p3 - p4), c21 = 2.0 * (p5 + p6), c22 = 1.0 - 2.0 * (q1 * q1 + q2 * q2);
+    double F[3] = { 0.0, 0.0, 0.0 };
+    if (P.aero_kind == SCVX_AERO_TABLE) {
+        const double bv[3] = { c00, c10, c20 };
+        aero_force_jac(P, tb, bv, x + 4, F, Fv, Fb);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { Fv[r][c] = 0.0; Fb[r][c] = 0.0; }
+    }
+    const double im = 1.0 / x[0];
+    f[0] = -P.a * sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    f[1] = x[4]; f[2] = x[5]; f[3] = x[6];
+    f[4] = (c00 * u[0] + c01 * u[1] + c02 * u[2] + F[0]) * im - P.g0;
+    f[5] = (c10 * u[0] + c11 * u[1] + c12 * u[2] + F[1]) * im;
+    f[6] = (c20 * u[0] + c21 * u[1] + c22 * u[2] + F[2]) * im;
+    f[7]  = 0.5 * (-(w0 * q1) - w1 * q2 - w2 * q3);
+    f[8]  = 0.5 * (w0 * q0 + w2 * q2 - w1 * q3);
+    f[9]  = 0.5 * (w1 * q0 - w2 * q1 + w0 * q3);
+    f[10] = 0.5 * (w2 * q0 + w1 * q1 - w0 * q2);
+    const double h0 = P.jB[0] * w0 + P.jB[3] * w1 + P.jB[6] * w2;
+    const double h1 = P.jB[1] * w0 + P.jB[4] * w1 + P.jB[7] * w2;
+    const double h2 = P.jB[2] * w0 + P.jB[5] * w1 + P.jB[8] * w2;
+    const double m0 = (P.rTB[1] * u[2] - P.rTB[2] * u[1]) - (w1 * h2 - w2 * h1);
+    const double m1 = (P.rTB[2] * u[0] - P.rTB[0] * u[2]) - (w2 * h0 - w0 * h2);
+    const double m2 = (P.rTB[0] * u[1] - P.rTB[1] * u[0]) - (w0 * h1 - w1 * h0);
+    f[11] = P.jBi[0] * m0 + P.jBi[3] * m1 + P.jBi[6] * m2;
+    f[12] = P.jBi[1] * m0 + P.jBi[4] * m1 + P.jBi[7] * m2;
+    f[13] = P.jBi[2] * m0 + P.jBi[5] * m1 + P.jBi[8] * m2;
+}
+
+__global__ void __launch_bounds__(128, 3) stage_value_kernel(StagedArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n_groups * GROUP) return;
     const ScvxBatch& bt = a.bt;
     const int ni = bt.n_nodes - 1;
     const bool live = t < a.count;
-    const long w = a.first + (live ? t : a.count - 1);         // padded lanes recompute the last interval
+    const int w = a.first + (live ? t : a.count - 1);          // padded lanes recompute the last interval
     const int b = (int)(w / ni), i = (int)(w % ni);
     const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
     const double* xin = bt.X + ((size_t)b * bt.n_nodes + i) * 14;
@@ -81,7 +231,7 @@ __global__ void __launch_bounds__(128) stage_value_kernel(StagedArgs a) {
     for (int c = 0; c < 3; ++c) { um[c] = uin[c]; up[c] = uin[3 + c]; }
 
     const int nst = 4 * bt.npts;
-    double* rec = a.rec + ((size_t)(t >> 5) * nst) * (REC * GROUP) + (t & 31);
+    double* rec = a.rec + ((size_t)(t >> 5) * nst) * ((size_t)a.rec_n * GROUP) + (t & 31);
     const double h = bt.dt / (double)bt.npts;
     const double pcs = 1.0 / (double)bt.npts;
     const double s = (bt.mode == SCVX_MODE_LITERAL) ? 1.0 : h;
@@ -93,12 +243,21 @@ __global__ void __launch_bounds__(128) stage_value_kernel(StagedArgs a) {
 #pragma unroll 1
         for (int st = 0; st < 4; ++st) {
             const double pc = (st == 0) ? pca : (st == 3 ? pca + pcs : pca + 0.5 * pcs);
-            double uc[3], f[14];
+            double uc[3], f[14], Fv[3][3], Fb[3][3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) uc[c] = (1.0 - pc) * um[c] + pc * up[c];
-            rhs_value(P, a.tb, y, uc, f);
-            // record: m, v, q, w, u, f_m, f_v, f_q, f_w
-            double* rp = rec + (size_t)(it * 4 + st) * (REC * GROUP);
+            rhs_value(P, a.tb, y, uc, f, Fv, Fb);
+            // record: m, v, q, w, u, f_m, f_v, f_q, f_w [, dF/dv, dF/db]
+            double* rp = rec + (size_t)(it * 4 + st) * ((size_t)a.rec_n * GROUP);
+            if (a.rec_n == REC_AERO) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        rp[(25 + 3 * r + c) * GROUP] = Fv[r][c];
+                        rp[(34 + 3 * r + c) * GROUP] = Fb[r][c];
+                    }
+            }
             rp[0 * GROUP] = y[0];
 #pragma unroll
             for (int r = 0; r < 10; ++r) rp[(1 + r) * GROUP] = y[4 + r];
@@ -176,117 +335,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 
-// spline value + gradient w.r.t. the physical coordinates (0 when strictly outside: Flat extrapolation)
-__device__ __forceinline__ void spline_grad(const double* __restrict__ coef, const ScvxTables& t, double x, double y,
-                                            double& gx, double& gy) {
-    const int L1 = t.n1 + 2;
-    double xi = (x - t.x0) * t.inv_dx + 1.0, yi = (y - t.y0) * t.inv_dy + 1.0;
-    double sx = t.inv_dx, sy = t.inv_dy;
-    if (xi > (double)t.n1) { xi = (double)t.n1; sx = 0.0; } else if (xi < 1.0) { xi = 1.0; sx = 0.0; }
-    if (yi > (double)t.n2) { yi = (double)t.n2; sy = 0.0; } else if (yi < 1.0) { yi = 1.0; sy = 0.0; }
-    int i = (int)floor(xi); i = max(min(i, t.n1 - 1), 1);
-    int j = (int)floor(yi); j = max(min(j, t.n2 - 1), 1);
-    const double dx = xi - (double)i, dy = yi - (double)j, ox = 1.0 - dx, oy = 1.0 - dy;
-    const double wx[4] = { ox * ox * ox * (1.0 / 6.0), (2.0 / 3.0) - dx * dx + 0.5 * dx * dx * dx,
-                           (2.0 / 3.0) - ox * ox + 0.5 * ox * ox * ox, dx * dx * dx * (1.0 / 6.0) };
-    const double gxw[4] = { -0.5 * ox * ox, -2.0 * dx + 1.5 * dx * dx, 2.0 * ox - 1.5 * ox * ox, 0.5 * dx * dx };
-    const double wy[4] = { oy * oy * oy * (1.0 / 6.0), (2.0 / 3.0) - dy * dy + 0.5 * dy * dy * dy,
-                           (2.0 / 3.0) - oy * oy + 0.5 * oy * oy * oy, dy * dy * dy * (1.0 / 6.0) };
-    const double gyw[4] = { -0.5 * oy * oy, -2.0 * dy + 1.5 * dy * dy, 2.0 * oy - 1.5 * oy * oy, 0.5 * dy * dy };
-    const double* base = coef + (i - 1) + (size_t)(j - 1) * L1;
-    double ax = 0.0, ay = 0.0;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        const double* p = base + (size_t)b * L1;
-        const double c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2), c3 = __ldg(p + 3);
-        const double rv = wx[0] * c0 + wx[1] * c1 + wx[2] * c2 + wx[3] * c3;
-        const double rg = gxw[0] * c0 + gxw[1] * c1 + gxw[2] * c2 + gxw[3] * c3;
-        ax = fma(wy[b], rg, ax);
-        ay = fma(gyw[b], rv, ay);
-    }
-    gx = ax * sx; gy = ay * sy;
-}
-
-// spline value only
-__device__ __forceinline__ double spline_val(const double* __restrict__ coef, const ScvxTables& t, double x, double y) {
-    return spline_eval<double>(coef, t, x, y);
-}
-
-// Jacobian of the aerodynamic force F(b, v) (aerodynamics.jl:38-58) w.r.t. v and b = C(q) e1: exact derivative
-// of the executed branch (|dp| >= 0.95 drag only; clamp active only strictly outside [-1,1]).
-__device__ __forceinline__ void aero_jac(const scvx_probinfo& P, const ScvxTables& tb, const double b[3],
-                                         const double v[3], double Fv[3][3], double Fb[3][3]) {
-    const double vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-    const double nv = sqrt(vv), inv = 1.0 / nv;
-    const double vh[3] = { v[0] * inv, v[1] * inv, v[2] * inv };
-    const double bvdot = b[0] * v[0] + b[1] * v[1] + b[2] * v[2];
-    const double dp = bvdot * inv;
-    const double nb = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]), inb = 1.0 / nb;
-    const double car = dp * inb;
-    double ca = car, mc = 1.0;
-    if (car > 1.0) { ca = 1.0; mc = 0.0; } else if (car < -1.0) { ca = -1.0; mc = 0.0; }
-    const double mach = nv * (1.0 / P.sos);
-    // d(ca)/dv, d(ca)/db ; d(mach)/dv
-    double cav[3], cab[3], mv[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        cav[k] = mc * (b[k] - dp * vh[k]) * inv * inb;
-        cab[k] = mc * (vh[k] - car * b[k] * inb) * inb;
-        mv[k] = vh[k] * (1.0 / P.sos);
-    }
-    const double fs = P.force_scalar;
-    const double drag = spline_val(tb.drag, tb, ca, mach) * fs;
-    double gx, gy;
-    spline_grad(tb.drag, tb, ca, mach, gx, gy);
-    gx *= fs; gy *= fs;
-    double dv[3], db[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { dv[k] = gx * cav[k] + gy * mv[k]; db[k] = gx * cab[k]; }
-    const double dn = drag * inv;
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            Fv[r][c] = vh[r] * dv[c] + dn * ((r == c ? 1.0 : 0.0) - vh[r] * vh[c]);
-            Fb[r][c] = vh[r] * db[c];
-        }
-    if (fabs(dp) >= 0.95) return;
-    const double lift = spline_val(tb.lift, tb, ca, mach) * fs;
-    spline_grad(tb.lift, tb, ca, mach, gx, gy);
-    gx *= fs; gy *= fs;
-    double lv[3], lb[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { lv[k] = gx * cav[k] + gy * mv[k]; lb[k] = gx * cab[k]; }
-    // l = (-(v x b)) x v = v (v.b) - b (v.v)
-    const double l[3] = { v[0] * bvdot - b[0] * vv, v[1] * bvdot - b[1] * vv, v[2] * bvdot - b[2] * vv };
-    const double nl = sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]), inl = 1.0 / nl;
-    const double lh[3] = { l[0] * inl, l[1] * inl, l[2] * inl };
-    // dl/dv = (v.b) I + v b^T - 2 b v^T ;  dl/db = v v^T - (v.v) I
-    double Lv[3][3], Lb[3][3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            Lv[r][c] = (r == c ? bvdot : 0.0) + v[r] * b[c] - 2.0 * b[r] * v[c];
-            Lb[r][c] = v[r] * v[c] - (r == c ? vv : 0.0);
-        }
-    const double ln = lift * inl;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        // (I - lh lh^T) * L[:,c]
-        const double pv = lh[0] * Lv[0][c] + lh[1] * Lv[1][c] + lh[2] * Lv[2][c];
-        const double pb = lh[0] * Lb[0][c] + lh[1] * Lb[1][c] + lh[2] * Lb[2][c];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            Fv[r][c] += lh[r] * lv[c] + ln * (Lv[r][c] - lh[r] * pv);
-            Fb[r][c] += lh[r] * lb[c] + ln * (Lb[r][c] - lh[r] * pb);
-        }
-    }
-}
-
 // rec: this lane's stage record (stride GROUP doubles between entries, in shared memory);
 // out: this lane's NJ-double Jacobian record in the ring.
-__device__ __forceinline__ void produce_stage(const scvx_probinfo& P, const ScvxTables& tb, double sigma,
+__device__ __noinline__ void produce_stage(const scvx_probinfo& P, bool aero_rec, double sigma,
                                               const double* __restrict__ rec, double* __restrict__ out) {
     const double m = rec[0];
     const double v[3] = { rec[1 * GROUP], rec[2 * GROUP], rec[3 * GROUP] };
@@ -338,10 +389,12 @@ __device__ __forceinline__ void produce_stage(const scvx_probinfo& P, const Scvx
     Jq[8] = 2.0 * (q1 * u1 - q2 * u0);             Jq[9] = 2.0 * (q3 * u0 + q0 * u1) - 4.0 * q1 * u2;
     Jq[10] = 2.0 * (q3 * u1 - q0 * u0) - 4.0 * q2 * u2; Jq[11] = 2.0 * (q1 * u0 + q2 * u1);
     double Jvv[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
-    if (P.aero_kind == SCVX_AERO_TABLE) {
-        const double bvec[3] = { c00, c10, c20 };
+    if (aero_rec) {
         double Fv[3][3], Fb[3][3];
-        aero_jac(P, tb, bvec, v, Fv, Fb);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { Fv[r][c] = rec[(25 + 3 * r + c) * GROUP]; Fb[r][c] = rec[(34 + 3 * r + c) * GROUP]; }
         // db/dq
         const double B[3][4] = { { 0.0, 0.0, -4.0 * q2, -4.0 * q3 },
                                  { 2.0 * q3, 2.0 * q2, 2.0 * q1, 2.0 * q0 },
@@ -386,7 +439,7 @@ __device__ __forceinline__ void produce_stage(const scvx_probinfo& P, const Scvx
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) TangentSmem {
     double ring[RING][GROUP][NJ];            // Jacobian records
-    double recbuf[NWARP][REC * GROUP];       // per-warp stage-record staging (TMA destination)
+    double recbuf[NWARP][REC_MAX * GROUP];   // per-warp stage-record staging (TMA destination)
     uint64_t full[RING];
     uint64_t empty[RING];
     uint64_t recfull[NWARP];
@@ -425,7 +478,7 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
 
     // groups handled by this CTA: g = blockIdx.x, blockIdx.x + gridDim.x, ...
     const int my_groups = (a.n_groups > (int)blockIdx.x) ? (a.n_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const long total_stages = (long)my_groups * nst;       // global stage counter T = it * nst + s
+    const int total_stages = my_groups * nst;               // global stage counter T = it * nst + s
 
     // ---- static per-lane column configuration
     // full slots: lanes 0..2: (u-_j, u+_j); lane 3: (sigma, -); lane 4: (w0,w1); 5: (w2,q0); 6: (q1,q2); 7: (q3,-)
@@ -445,42 +498,46 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
     }
 
     // producer bookkeeping: this warp produces global stages T with T % NWARP == warp
-    long nextP = warp;                               // next stage this warp has to produce
+    int nextP = warp;                                // next global stage this warp has to produce
+    int p_it = 0, p_s = warp;                        // ... as (group pass, stage) ; nst >= 4
+    while (p_s >= nst) { p_s -= nst; ++p_it; }
     uint32_t rec_phase = 0;
-    auto issue_record = [&](long T) {                // lane 0 only: TMA the stage record of global stage T
-        const int it = (int)(T / nst), s = (int)(T % nst);
+    auto issue_record = [&](int it, int s) {         // lane 0 only: TMA the stage record of (pass it, stage s)
         const int g = blockIdx.x + it * gridDim.x;
-        const double* src = a.rec + ((size_t)g * nst + s) * (REC * GROUP);
-        mbar_expect_tx(&sm.recfull[warp], REC * GROUP * 8);
-        bulk_g2s(sm.recbuf[warp], src, REC * GROUP * 8, &sm.recfull[warp]);
+        const uint32_t bytes = (uint32_t)a.rec_n * GROUP * 8;
+        const double* src = a.rec + ((size_t)g * nst + s) * ((size_t)a.rec_n * GROUP);
+        mbar_expect_tx(&sm.recfull[warp], bytes);
+        bulk_g2s(sm.recbuf[warp], src, bytes, &sm.recfull[warp]);
     };
-    if (lane == 0 && nextP < total_stages) issue_record(nextP);
+    if (lane == 0 && nextP < total_stages) issue_record(p_it, p_s);
 
-    auto produce = [&](long T) {
-        const int it = (int)(T / nst);
-        const int g = blockIdx.x + it * gridDim.x;
+    auto produce = [&]() {                           // produce global stage nextP = (p_it, p_s), then advance
+        const int g = blockIdx.x + p_it * gridDim.x;
         int t = g * GROUP + lane; if (t >= a.count) t = a.count - 1;
-        const long wi = a.first + t;
-        const int b = (int)(wi / ni);
+        const int b = (a.first + t) / ni;
         const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
         const double sigma = bt.sigma[b];
-        const int slot = (int)(T % RING);
-        const long use = T / RING;
+        const int slot = nextP % RING;
+        const int use = nextP / RING;
         mbar_wait(&sm.recfull[warp], rec_phase); rec_phase ^= 1;
         if (use > 0) mbar_wait(&sm.empty[slot], (uint32_t)((use - 1) & 1));
-        produce_stage(P, a.tb, sigma, sm.recbuf[warp] + lane, &sm.ring[slot][lane][0]);
+        produce_stage(P, a.rec_n == REC_AERO, sigma, sm.recbuf[warp] + lane, &sm.ring[slot][lane][0]);
         mbar_arrive(&sm.full[slot]);
+        nextP += NWARP; p_s += NWARP;
+        while (p_s >= nst) { p_s -= nst; ++p_it; }
         __syncwarp();
-        if (lane == 0 && T + NWARP < total_stages) { fence_proxy_async(); issue_record(T + NWARP); }
+        if (lane == 0 && nextP < total_stages) { fence_proxy_async(); issue_record(p_it, p_s); }
     };
 
     // prologue: stages 0..LOOKAHEAD-1
     for (int k = 0; k < LOOKAHEAD; ++k)
-        if (nextP == k && nextP < total_stages) { produce(nextP); nextP += NWARP; }
+        if (nextP == k && nextP < total_stages) produce();
 
     FullCol FA, FB;
     LightCol FL;
-    long T = 0;
+    int T = 0;
+    int c_slot = 0;
+    uint32_t c_phase = 0;
     for (int it = 0; it < my_groups; ++it) {
         const int g = blockIdx.x + it * gridDim.x;
         // ---- initial tangent: S = [I | 0]
@@ -502,7 +559,7 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
         double pca = 0.0;
         for (int s = 0; s < nst; ++s, ++T) {
             // producer duty for stage T + LOOKAHEAD
-            if (nextP == T + LOOKAHEAD && nextP < total_stages) { produce(nextP); nextP += NWARP; }
+            if (nextP == T + LOOKAHEAD && nextP < total_stages) produce();
 
             const int st = s & 3;
             const double pc = (st == 0) ? pca : (st == 3 ? pca + pcs : pca + 0.5 * pcs);
@@ -510,63 +567,21 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
             const double cy = (st == 2) ? sstep : 0.5 * sstep;
             const double cr = h6 * wgt;
             const double alA = fma(a1A, pc, a0A), alB = fma(a1B, pc, a0B);
-            const int slot = (int)(T % RING);
-            mbar_wait(&sm.full[slot], (uint32_t)((T / RING) & 1));
+            const int slot = c_slot;
+            mbar_wait(&sm.full[slot], c_phase);
+            if (++c_slot == RING) { c_slot = 0; c_phase ^= 1; }
             const double* J = &sm.ring[slot][warp * 4 + sub][0];
             const double* Gc = J + J_G + 7 * gcol;
-            double KA[11], KB[11], KL[3];
+            const bool last = (st == 3);
+            // In-place RK bookkeeping of one row: non-final stages accumulate and form the next stage tangent,
+            // the final stage closes the step.  Rows are processed in cascade order (r, v, m, q, w): a row block
+            // is overwritten only after every block that reads its old stage value has been formed.
+#define UPD(F, idx, Kv)                                                                                 \
+            if (!last) { F.A[idx] = fma(wgt, (Kv), F.A[idx]); F.Y[idx] = fma(cy, (Kv), F.S[idx]); }      \
+            else { F.S[idx] = fma(h6, F.A[idx] + (Kv), F.S[idx]); F.Y[idx] = F.S[idx]; F.A[idx] = 0.0; }
 
-            // ---- w rows: K_w = Jww * Y_w + alpha * G_w
+            // ---- r rows (pure quadrature): S_r += cr * (sigma * Y_v + dsigma * f_r)
             {
-                const double2 j01 = ld2(J + J_WW), j23 = ld2(J + J_WW + 2), j45 = ld2(J + J_WW + 4), j67 = ld2(J + J_WW + 6);
-                const double j8 = J[J_WW + 8];
-                const double g0 = Gc[4], g1 = Gc[5], g2 = Gc[6];
-                KA[8] = fma(j01.x, FA.Y[8], fma(j01.y, FA.Y[9], fma(j23.x, FA.Y[10], alA * g0)));
-                KA[9] = fma(j23.y, FA.Y[8], fma(j45.x, FA.Y[9], fma(j45.y, FA.Y[10], alA * g1)));
-                KA[10] = fma(j67.x, FA.Y[8], fma(j67.y, FA.Y[9], fma(j8, FA.Y[10], alA * g2)));
-                KB[8] = fma(j01.x, FB.Y[8], fma(j01.y, FB.Y[9], fma(j23.x, FB.Y[10], alB * g0)));
-                KB[9] = fma(j23.y, FB.Y[8], fma(j45.x, FB.Y[9], fma(j45.y, FB.Y[10], alB * g1)));
-                KB[10] = fma(j67.x, FB.Y[8], fma(j67.y, FB.Y[9], fma(j8, FB.Y[10], alB * g2)));
-            }
-            // ---- q rows: K_q = Omega(hw) Y_q + Omega(Y_w) hq + dsigma * f_q
-            {
-                const double hw0 = J[J_HW], hw1 = J[J_HW + 1], hw2 = J[J_HW + 2];
-                const double2 hq01 = ld2(J + J_HQ), hq23 = ld2(J + J_HQ + 2);
-                const double hq0 = hq01.x, hq1 = hq01.y, hq2 = hq23.x, hq3 = hq23.y;
-                const double fq0 = J[J_FRQ + 3];
-                const double2 fq12 = ld2(J + J_FRQ + 4);
-                const double fq3 = J[J_FRQ + 6];
-#define QROWS(F, K, ds)                                                                                                   \
-                K[4] = fma(-hw0, F.Y[5], fma(-hw1, F.Y[6], fma(-hw2, F.Y[7], fma(-hq1, F.Y[8], fma(-hq2, F.Y[9], fma(-hq3, F.Y[10], ds * fq0)))))); \
-                K[5] = fma(hw0, F.Y[4], fma(hw2, F.Y[6], fma(-hw1, F.Y[7], fma(hq0, F.Y[8], fma(hq2, F.Y[10], fma(-hq3, F.Y[9], ds * fq12.x)))))); \
-                K[6] = fma(hw1, F.Y[4], fma(-hw2, F.Y[5], fma(hw0, F.Y[7], fma(hq0, F.Y[9], fma(-hq1, F.Y[10], fma(hq3, F.Y[8], ds * fq12.y)))))); \
-                K[7] = fma(hw2, F.Y[4], fma(hw1, F.Y[5], fma(-hw0, F.Y[6], fma(hq0, F.Y[10], fma(hq1, F.Y[9], fma(-hq2, F.Y[8], ds * fq3))))));
-                QROWS(FA, KA, dsA)
-                QROWS(FB, KB, 0.0)
-#undef QROWS
-            }
-            // ---- v rows: K_v = Jvm Y_m + Jvv Y_v + Jvq Y_q + alpha * G_v ; light: Jvv Y_v + beta Jvm
-            {
-                const double2 m01 = ld2(J + J_VM);
-                const double2 m2v0 = ld2(J + J_VM + 2);           // Jvm[2], Jvv[0]
-                const double2 v12 = ld2(J + J_VV + 1), v34 = ld2(J + J_VV + 3), v56 = ld2(J + J_VV + 5), v78 = ld2(J + J_VV + 7);
-                const double g0 = Gc[1], g1 = Gc[2], g2 = Gc[3];
-#define VROW(row, jm, a, b, c, gg)                                                                                      \
-                {                                                                                                         \
-                    const double2 qa = ld2(J + J_VQ + 4 * row), qb = ld2(J + J_VQ + 4 * row + 2);                         \
-                    KA[1 + row] = fma(jm, FA.Y[0], fma(a, FA.Y[1], fma(b, FA.Y[2], fma(c, FA.Y[3], fma(qa.x, FA.Y[4], fma(qa.y, FA.Y[5], fma(qb.x, FA.Y[6], fma(qb.y, FA.Y[7], alA * gg)))))))); \
-                    KB[1 + row] = fma(jm, FB.Y[0], fma(a, FB.Y[1], fma(b, FB.Y[2], fma(c, FB.Y[3], fma(qa.x, FB.Y[4], fma(qa.y, FB.Y[5], fma(qb.x, FB.Y[6], fma(qb.y, FB.Y[7], alB * gg)))))))); \
-                    KL[row] = fma(a, FL.Y[0], fma(b, FL.Y[1], fma(c, FL.Y[2], betaL * jm)));                              \
-                }
-                VROW(0, m01.x, m2v0.y, v12.x, v12.y, g0)
-                VROW(1, m01.y, v34.x, v34.y, v56.x, g1)
-                VROW(2, m2v0.x, v56.y, v78.x, v78.y, g2)
-#undef VROW
-            }
-            // ---- m row and r rows (quadrature): S_r += cr * (sigma * Y_v + dsigma * f_r)
-            {
-                KA[0] = alA * Gc[0];
-                KB[0] = alB * Gc[0];
                 const double2 fr01 = ld2(J + J_FRQ);
                 const double fr2 = J[J_FRQ + 2];
                 const double sg = J[J_FRQ + 7];
@@ -580,35 +595,78 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
                     FL.Sr[r] = fma(csg, FL.Y[r], FL.Sr[r]);
                 }
             }
-            // all reads of the ring slot are done: hand it back
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.empty[slot]);
-
-            // ---- RK bookkeeping
-            if (st != 3) {
-#pragma unroll
-                for (int r = 0; r < 11; ++r) {
-                    FA.A[r] = fma(wgt, KA[r], FA.A[r]); FA.Y[r] = fma(cy, KA[r], FA.S[r]);
-                    FB.A[r] = fma(wgt, KB[r], FB.A[r]); FB.Y[r] = fma(cy, KB[r], FB.S[r]);
+            // ---- v rows: K_v = Jvm Y_m + Jvv Y_v + Jvq Y_q + alpha * G_v ; light: Jvv Y_v + beta Jvm
+            {
+                const double2 m01 = ld2(J + J_VM);
+                const double2 m2v0 = ld2(J + J_VM + 2);           // Jvm[2], Jvv[0]
+                const double2 v12 = ld2(J + J_VV + 1), v34 = ld2(J + J_VV + 3), v56 = ld2(J + J_VV + 5), v78 = ld2(J + J_VV + 7);
+                const double g0 = Gc[1], g1 = Gc[2], g2 = Gc[3];
+                double kA[3], kB[3], kL[3];
+#define VROW(row, jm, a, b, c, gg)                                                                                      \
+                {                                                                                                         \
+                    const double2 qa = ld2(J + J_VQ + 4 * row), qb = ld2(J + J_VQ + 4 * row + 2);                         \
+                    kA[row] = fma(jm, FA.Y[0], fma(a, FA.Y[1], fma(b, FA.Y[2], fma(c, FA.Y[3], fma(qa.x, FA.Y[4], fma(qa.y, FA.Y[5], fma(qb.x, FA.Y[6], fma(qb.y, FA.Y[7], alA * gg)))))))); \
+                    kB[row] = fma(jm, FB.Y[0], fma(a, FB.Y[1], fma(b, FB.Y[2], fma(c, FB.Y[3], fma(qa.x, FB.Y[4], fma(qa.y, FB.Y[5], fma(qb.x, FB.Y[6], fma(qb.y, FB.Y[7], alB * gg)))))))); \
+                    kL[row] = fma(a, FL.Y[0], fma(b, FL.Y[1], fma(c, FL.Y[2], betaL * jm)));                              \
                 }
+                VROW(0, m01.x, m2v0.y, v12.x, v12.y, g0)
+                VROW(1, m01.y, v34.x, v34.y, v56.x, g1)
+                VROW(2, m2v0.x, v56.y, v78.x, v78.y, g2)
+#undef VROW
 #pragma unroll
-                for (int r = 0; r < 3; ++r) { FL.A[r] = fma(wgt, KL[r], FL.A[r]); FL.Y[r] = fma(cy, KL[r], FL.S[r]); }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 11; ++r) {
-                    FA.S[r] = fma(h6, FA.A[r] + KA[r], FA.S[r]); FA.Y[r] = FA.S[r]; FA.A[r] = 0.0;
-                    FB.S[r] = fma(h6, FB.A[r] + KB[r], FB.S[r]); FB.Y[r] = FB.S[r]; FB.A[r] = 0.0;
-                }
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { FL.S[r] = fma(h6, FL.A[r] + KL[r], FL.S[r]); FL.Y[r] = FL.S[r]; FL.A[r] = 0.0; }
-                pca += pcs;
+                for (int r = 0; r < 3; ++r) { UPD(FA, 1 + r, kA[r]) UPD(FB, 1 + r, kB[r]) UPD(FL, r, kL[r]) }
             }
+            // ---- m row: K_m = alpha * G_m
+            {
+                const double gmv = Gc[0];
+                UPD(FA, 0, alA * gmv) UPD(FB, 0, alB * gmv)
+            }
+            // ---- q rows: K_q = Omega(hw) Y_q + Omega(Y_w) hq + dsigma * f_q
+            {
+                const double hw0 = J[J_HW], hw1 = J[J_HW + 1], hw2 = J[J_HW + 2];
+                const double2 hq01 = ld2(J + J_HQ), hq23 = ld2(J + J_HQ + 2);
+                const double hq0 = hq01.x, hq1 = hq01.y, hq2 = hq23.x, hq3 = hq23.y;
+                const double fq0 = J[J_FRQ + 3];
+                const double2 fq12 = ld2(J + J_FRQ + 4);
+                const double fq3 = J[J_FRQ + 6];
+                double kA[4], kB[4];
+#define QROWS(F, K, ds)                                                                                                   \
+                K[0] = fma(-hw0, F.Y[5], fma(-hw1, F.Y[6], fma(-hw2, F.Y[7], fma(-hq1, F.Y[8], fma(-hq2, F.Y[9], fma(-hq3, F.Y[10], ds * fq0)))))); \
+                K[1] = fma(hw0, F.Y[4], fma(hw2, F.Y[6], fma(-hw1, F.Y[7], fma(hq0, F.Y[8], fma(hq2, F.Y[10], fma(-hq3, F.Y[9], ds * fq12.x)))))); \
+                K[2] = fma(hw1, F.Y[4], fma(-hw2, F.Y[5], fma(hw0, F.Y[7], fma(hq0, F.Y[9], fma(-hq1, F.Y[10], fma(hq3, F.Y[8], ds * fq12.y)))))); \
+                K[3] = fma(hw2, F.Y[4], fma(hw1, F.Y[5], fma(-hw0, F.Y[6], fma(hq0, F.Y[10], fma(hq1, F.Y[9], fma(-hq2, F.Y[8], ds * fq3))))));
+                QROWS(FA, kA, dsA)
+                QROWS(FB, kB, 0.0)
+#undef QROWS
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { UPD(FA, 4 + r, kA[r]) UPD(FB, 4 + r, kB[r]) }
+            }
+            // ---- w rows: K_w = Jww * Y_w + alpha * G_w
+            {
+                const double2 j01 = ld2(J + J_WW), j23 = ld2(J + J_WW + 2), j45 = ld2(J + J_WW + 4), j67 = ld2(J + J_WW + 6);
+                const double j8 = J[J_WW + 8];
+                const double g0 = Gc[4], g1 = Gc[5], g2 = Gc[6];
+                double kA[3], kB[3];
+                kA[0] = fma(j01.x, FA.Y[8], fma(j01.y, FA.Y[9], fma(j23.x, FA.Y[10], alA * g0)));
+                kA[1] = fma(j23.y, FA.Y[8], fma(j45.x, FA.Y[9], fma(j45.y, FA.Y[10], alA * g1)));
+                kA[2] = fma(j67.x, FA.Y[8], fma(j67.y, FA.Y[9], fma(j8, FA.Y[10], alA * g2)));
+                kB[0] = fma(j01.x, FB.Y[8], fma(j01.y, FB.Y[9], fma(j23.x, FB.Y[10], alB * g0)));
+                kB[1] = fma(j23.y, FB.Y[8], fma(j45.x, FB.Y[9], fma(j45.y, FB.Y[10], alB * g1)));
+                kB[2] = fma(j67.x, FB.Y[8], fma(j67.y, FB.Y[9], fma(j8, FB.Y[10], alB * g2)));
+                // all reads of the ring slot are done: hand it back
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[slot]);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { UPD(FA, 8 + r, kA[r]) UPD(FB, 8 + r, kB[r]) }
+            }
+#undef UPD
+            if (last) pca += pcs;
         }
 
         // ---- epilogue: write D columns and z for interval (g*32 + warp*4 + sub)
         const int t = g * GROUP + warp * 4 + sub;
         const bool live = t < a.count;
-        const long wi = a.first + (live ? t : a.count - 1);
+        const int wi = a.first + (live ? t : a.count - 1);
         const int b = (int)(wi / ni), i = (int)(wi % ni);
         double* blk = bt.out_blocks + (size_t)wi * SCVX_BLOCK_DOUBLES;
         const double* xin = bt.X + ((size_t)b * bt.n_nodes + i) * 14;
@@ -679,13 +737,13 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
 
 size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals) {
     const size_t groups = ((size_t)chunk_intervals + GROUP - 1) / GROUP;
-    return groups * (size_t)(4 * npts) * REC * GROUP * sizeof(double);
+    return groups * (size_t)(4 * npts) * REC_MAX * GROUP * sizeof(double);
 }
 
 int scvx_staged_chunk_intervals(int sm_count) { return sm_count * GROUP * 14; }
 
-cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, void* scratch, int chunk_intervals,
-                               int sm_count, cudaStream_t s, int* launches) {
+cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, void* scratch,
+                               int chunk_intervals, int sm_count, cudaStream_t s, int* launches) {
     const long total = (long)(bt.n_nodes - 1) * bt.B;
     const size_t smem = sizeof(TangentSmem);
     {
@@ -694,7 +752,8 @@ cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, void* 
     }
     for (long first = 0; first < total; first += chunk_intervals) {
         StagedArgs a;
-        a.bt = bt; a.tb = tb; a.rec = (double*)scratch; a.first = first;
+        a.bt = bt; a.tb = tb; a.rec = (double*)scratch; a.first = (int)first;
+        a.rec_n = any_aero ? REC_AERO : REC_EXO;
         a.count = (int)((total - first < chunk_intervals) ? (total - first) : chunk_intervals);
         a.n_groups = (a.count + GROUP - 1) / GROUP;
         const int threads = a.n_groups * GROUP;
