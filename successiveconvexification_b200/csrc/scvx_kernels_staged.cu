@@ -301,6 +301,91 @@ __global__ void __launch_bounds__(128, 3) stage_value_kernel(StagedArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Kernel A2: the four "light" tangent columns d/d(m, v0, v1, v2) — one THREAD per interval.
+// Only the v and r rows of these columns are non-trivial: K_v = Jvv Y_v (+ Jvm for the mass
+// column), r rows are a quadrature of the v rows.  Reads m, f_v and dF/dv from the stage records, writes the
+// seven columns d/d(m, r, v) of the block and the partial z = endpoint - D[:, m r v] * inp[m r v].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) light_columns_kernel(StagedArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.count) return;
+    const ScvxBatch& bt = a.bt;
+    const int ni = bt.n_nodes - 1;
+    const int w = a.first + t;
+    const int b = w / ni, i = w % ni;
+    const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
+    const double sigma = bt.sigma[b], g0 = P.g0;
+    const bool aero = (a.rec_n == REC_AERO);
+    const int nst = 4 * bt.npts;
+    const double* rec = a.rec + ((size_t)(t >> 5) * nst) * ((size_t)a.rec_n * GROUP) + (t & 31);
+    const double h = bt.dt / (double)bt.npts;
+    const double sstep = (bt.mode == SCVX_MODE_LITERAL) ? 1.0 : h;
+    const double h6 = h * (1.0 / 6.0);
+    double S[4][3], A[4][3], Y[4][3], Sr[4][3];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { S[c][r] = (c == r + 1) ? 1.0 : 0.0; Y[c][r] = S[c][r]; A[c][r] = 0.0; Sr[c][r] = 0.0; }
+    for (int s = 0; s < nst; ++s) {
+        const int st = s & 3;
+        const double* rp = rec + (size_t)s * ((size_t)a.rec_n * GROUP);
+        const double sm = sigma / rp[0];
+        double Jvv[3][3], Jvm[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            Jvm[r] = -sm * (rp[(15 + r) * GROUP] + (r == 0 ? g0 : 0.0));
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Jvv[r][c] = aero ? sm * rp[(25 + 3 * r + c) * GROUP] : 0.0;
+        }
+        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+        const double cy = (st == 2) ? sstep : 0.5 * sstep;
+        const double csg = h6 * wgt * sigma;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double K[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                Sr[c][r] = fma(csg, Y[c][r], Sr[c][r]);
+                K[r] = fma(Jvv[r][0], Y[c][0], fma(Jvv[r][1], Y[c][1], fma(Jvv[r][2], Y[c][2], c == 0 ? Jvm[r] : 0.0)));
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                if (st != 3) { A[c][r] = fma(wgt, K[r], A[c][r]); Y[c][r] = fma(cy, K[r], S[c][r]); }
+                else { S[c][r] = fma(h6, A[c][r] + K[r], S[c][r]); Y[c][r] = S[c][r]; A[c][r] = 0.0; }
+            }
+        }
+    }
+    double* blk = bt.out_blocks + (size_t)w * SCVX_BLOCK_DOUBLES;
+    const double* xin = bt.X + ((size_t)b * bt.n_nodes + i) * 14;
+    // columns: inp 0 (m), 1..3 (r), 4..6 (v)
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        double col[14];
+#pragma unroll
+        for (int r = 0; r < 14; ++r) col[r] = 0.0;
+        if (c == 0) { col[0] = 1.0; for (int r = 0; r < 3; ++r) { col[1 + r] = Sr[0][r]; col[4 + r] = S[0][r]; } }
+        else if (c < 4) col[c] = 1.0;
+        else { for (int r = 0; r < 3; ++r) { col[1 + r] = Sr[c - 3][r]; col[4 + r] = S[c - 3][r]; } }
+        double* o = blk + 14 * (1 + c);
+#pragma unroll
+        for (int r = 0; r < 14; r += 2) *reinterpret_cast<double2*>(o + r) = make_double2(col[r], col[r + 1]);
+    }
+    // partial z (kernel B subtracts the remaining 14 columns)
+    double z[14];
+#pragma unroll
+    for (int r = 0; r < 14; ++r) z[r] = blk[r];
+    z[0] -= xin[0];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        z[1 + r] -= Sr[0][r] * xin[0] + xin[1 + r] + Sr[1][r] * xin[4] + Sr[2][r] * xin[5] + Sr[3][r] * xin[6];
+        z[4 + r] -= S[0][r] * xin[0] + S[1][r] * xin[4] + S[2][r] * xin[5] + S[3][r] * xin[6];
+    }
+    double* o = blk + 14 * 22;
+#pragma unroll
+    for (int r = 0; r < 14; r += 2) *reinterpret_cast<double2*>(o + r) = make_double2(z[r], z[r + 1]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // mbarrier / TMA bulk-copy helpers (PTX)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -451,9 +536,6 @@ __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_ca
 struct FullCol {
     double S[11], A[11], Y[11], Sr[3];
 };
-struct LightCol {
-    double S[3], A[3], Y[3], Sr[3];
-};
 
 __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -482,20 +564,16 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
 
     // ---- static per-lane column configuration
     // full slots: lanes 0..2: (u-_j, u+_j); lane 3: (sigma, -); lane 4: (w0,w1); 5: (w2,q0); 6: (q1,q2); 7: (q3,-)
-    int colA, colB, colL, gcol;
-    double a0A, a1A, a0B, a1B, dsA, betaL;
-    {
-        colA = -1; colB = -1; colL = -1; gcol = 3;
-        a0A = a1A = a0B = a1B = dsA = betaL = 0.0;
-        if (l8 < 3) { colA = 14 + l8; colB = 17 + l8; gcol = l8; a0A = 1.0; a1A = -1.0; a0B = 0.0; a1B = 1.0; }
-        else if (l8 == 3) { colA = 20; a0A = 1.0; dsA = 1.0; }
-        else if (l8 == 4) { colA = 11; colB = 12; }
-        else if (l8 == 5) { colA = 13; colB = 7; }
-        else if (l8 == 6) { colA = 8; colB = 9; }
-        else { colA = 10; }
-        if (l8 == 0) { colL = 0; betaL = 1.0; }
-        else if (l8 < 4) colL = 3 + l8;            // v0..v2 -> inp columns 4,5,6
-    }
+    int colA = -1, colB = -1, gcol = 3;
+    if (l8 < 3) { colA = 14 + l8; colB = 17 + l8; gcol = l8; }
+    else if (l8 == 3) colA = 20;
+    else if (l8 == 4) { colA = 11; colB = 12; }
+    else if (l8 == 5) { colA = 13; colB = 7; }
+    else if (l8 == 6) { colA = 8; colB = 9; }
+    else colA = 10;
+    // direct-term coefficients, re-derived from l8 where used (keeps them out of long-lived registers):
+    //   alpha_A = 1-pc (u- columns) | 1 (sigma column) | 0 ;  alpha_B = pc (u+ columns) | 0 ;
+    //   dsigma_A = 1 for the sigma column
 
     // producer bookkeeping: this warp produces global stages T with T % NWARP == warp
     int nextP = warp;                                // next global stage this warp has to produce
@@ -534,7 +612,6 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
         if (nextP == k && nextP < total_stages) produce();
 
     FullCol FA, FB;
-    LightCol FL;
     int T = 0;
     int c_slot = 0;
     uint32_t c_phase = 0;
@@ -550,11 +627,7 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
             FA.Y[r] = FA.S[r]; FB.Y[r] = FB.S[r];
         }
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            FA.Sr[r] = FB.Sr[r] = FL.Sr[r] = 0.0;
-            FL.S[r] = (colL == r + 4) ? 1.0 : 0.0;
-            FL.A[r] = 0.0; FL.Y[r] = FL.S[r];
-        }
+        for (int r = 0; r < 3; ++r) FA.Sr[r] = FB.Sr[r] = 0.0;
 
         double pca = 0.0;
         for (int s = 0; s < nst; ++s, ++T) {
@@ -566,7 +639,8 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
             const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
             const double cy = (st == 2) ? sstep : 0.5 * sstep;
             const double cr = h6 * wgt;
-            const double alA = fma(a1A, pc, a0A), alB = fma(a1B, pc, a0B);
+            const double alA = (l8 < 3) ? 1.0 - pc : (l8 == 3 ? 1.0 : 0.0), alB = (l8 < 3) ? pc : 0.0;
+            const double dsA = (l8 == 3) ? 1.0 : 0.0;
             const int slot = c_slot;
             mbar_wait(&sm.full[slot], c_phase);
             if (++c_slot == RING) { c_slot = 0; c_phase ^= 1; }
@@ -590,31 +664,27 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
                 FA.Sr[1] = fma(csg, FA.Y[2], fma(cds, fr01.y, FA.Sr[1]));
                 FA.Sr[2] = fma(csg, FA.Y[3], fma(cds, fr2, FA.Sr[2]));
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    FB.Sr[r] = fma(csg, FB.Y[1 + r], FB.Sr[r]);
-                    FL.Sr[r] = fma(csg, FL.Y[r], FL.Sr[r]);
-                }
+                for (int r = 0; r < 3; ++r) FB.Sr[r] = fma(csg, FB.Y[1 + r], FB.Sr[r]);
             }
-            // ---- v rows: K_v = Jvm Y_m + Jvv Y_v + Jvq Y_q + alpha * G_v ; light: Jvv Y_v + beta Jvm
+            // ---- v rows: K_v = Jvm Y_m + Jvv Y_v + Jvq Y_q + alpha * G_v
             {
                 const double2 m01 = ld2(J + J_VM);
                 const double2 m2v0 = ld2(J + J_VM + 2);           // Jvm[2], Jvv[0]
                 const double2 v12 = ld2(J + J_VV + 1), v34 = ld2(J + J_VV + 3), v56 = ld2(J + J_VV + 5), v78 = ld2(J + J_VV + 7);
                 const double g0 = Gc[1], g1 = Gc[2], g2 = Gc[3];
-                double kA[3], kB[3], kL[3];
+                double kA[3], kB[3];
 #define VROW(row, jm, a, b, c, gg)                                                                                      \
                 {                                                                                                         \
                     const double2 qa = ld2(J + J_VQ + 4 * row), qb = ld2(J + J_VQ + 4 * row + 2);                         \
                     kA[row] = fma(jm, FA.Y[0], fma(a, FA.Y[1], fma(b, FA.Y[2], fma(c, FA.Y[3], fma(qa.x, FA.Y[4], fma(qa.y, FA.Y[5], fma(qb.x, FA.Y[6], fma(qb.y, FA.Y[7], alA * gg)))))))); \
                     kB[row] = fma(jm, FB.Y[0], fma(a, FB.Y[1], fma(b, FB.Y[2], fma(c, FB.Y[3], fma(qa.x, FB.Y[4], fma(qa.y, FB.Y[5], fma(qb.x, FB.Y[6], fma(qb.y, FB.Y[7], alB * gg)))))))); \
-                    kL[row] = fma(a, FL.Y[0], fma(b, FL.Y[1], fma(c, FL.Y[2], betaL * jm)));                              \
                 }
                 VROW(0, m01.x, m2v0.y, v12.x, v12.y, g0)
                 VROW(1, m01.y, v34.x, v34.y, v56.x, g1)
                 VROW(2, m2v0.x, v56.y, v78.x, v78.y, g2)
 #undef VROW
 #pragma unroll
-                for (int r = 0; r < 3; ++r) { UPD(FA, 1 + r, kA[r]) UPD(FB, 1 + r, kB[r]) UPD(FL, r, kL[r]) }
+                for (int r = 0; r < 3; ++r) { UPD(FA, 1 + r, kA[r]) UPD(FB, 1 + r, kB[r]) }
             }
             // ---- m row: K_m = alpha * G_m
             {
@@ -695,25 +765,7 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
         };
         emit_full(FA, colA);
         emit_full(FB, colB);
-        if (colL >= 0) {
-            const double col[14] = { colL == 0 ? 1.0 : 0.0, FL.Sr[0], FL.Sr[1], FL.Sr[2], FL.S[0], FL.S[1], FL.S[2], 0, 0, 0, 0, 0, 0, 0 };
-            const double xc = inp_of(colL);
-            double* o = blk + 14 * (1 + colL);
-#pragma unroll
-            for (int r = 0; r < 14; r += 2) {
-                if (live) *reinterpret_cast<double2*>(o + r) = make_double2(col[r], col[r + 1]);
-                zp[r] = fma(col[r], xc, zp[r]); zp[r + 1] = fma(col[r + 1], xc, zp[r + 1]);
-            }
-        } else if (l8 >= 4 && l8 < 7) {
-            // position columns: D[:, r_j] = e_{r_j} exactly (nothing depends on position)
-            const int c = l8 - 3;                    // inp columns 1,2,3
-            double* o = blk + 14 * (1 + c);
-#pragma unroll
-            for (int r = 0; r < 14; r += 2)
-                if (live) *reinterpret_cast<double2*>(o + r) = make_double2(r == c ? 1.0 : 0.0, r + 1 == c ? 1.0 : 0.0);
-            zp[c] += xin[c];
-        }
-        // z = endpoint - D * inp  (sum of the 8 lanes of this interval)
+        // z = (partial z of kernel A2) - D[:, heavy columns] * inp  (sum over the 8 lanes of this interval)
 #pragma unroll
         for (int r = 0; r < 14; ++r) {
             double v = zp[r];
@@ -726,7 +778,7 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
             double* o = blk + 14 * 22;
 #pragma unroll
             for (int r = 0; r < 14; r += 2) {
-                const double2 e = *reinterpret_cast<const double2*>(blk + r);      // endpoint written by kernel A
+                const double2 e = *reinterpret_cast<const double2*>(o + r);        // partial z written by kernel A2
                 *reinterpret_cast<double2*>(o + r) = make_double2(e.x - zp[r], e.y - zp[r + 1]);
             }
         }
@@ -758,9 +810,10 @@ cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool a
         a.n_groups = (a.count + GROUP - 1) / GROUP;
         const int threads = a.n_groups * GROUP;
         stage_value_kernel<<<(threads + 127) / 128, 128, 0, s>>>(a);
+        light_columns_kernel<<<(a.count + 127) / 128, 128, 0, s>>>(a);
         const int grid = a.n_groups < sm_count ? a.n_groups : sm_count;
         tangent_kernel<<<grid, 256, smem, s>>>(a);
-        if (launches) *launches += 2;
+        if (launches) *launches += 3;
     }
     return cudaGetLastError();
 }
