@@ -38,7 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     for s in srcs:
         o = os.path.splitext(s)[0] + ".o"
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        extra = os.environ.get("SCVX_NVCC_EXTRA", "").split()
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         subprocess.check_call(cmd)
         objs.append(o)
     subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs)

@@ -30,8 +30,14 @@ constexpr int REC_EXO = 25;      // stage record entries: m, v(3), q(4), w(3), u
 constexpr int REC_AERO = 43;     // + dF_aero/dv (9, row-major) + dF_aero/db (9), b = C(q) e1
 constexpr int REC_MAX = REC_AERO;
 constexpr int NJ = 78;           // Jacobian record entries per interval per stage (2 x odd: conflict-free STS.128)
-constexpr int RING = 5;          // ring slots
-constexpr int LOOKAHEAD = 3;     // producer runs this many stages ahead of the consumers (< RING)
+#ifndef SCVX_RING
+#define SCVX_RING 6
+#endif
+#ifndef SCVX_LOOKAHEAD
+#define SCVX_LOOKAHEAD 3
+#endif
+constexpr int RING = SCVX_RING;  // ring slots
+constexpr int LOOKAHEAD = SCVX_LOOKAHEAD;   // producer runs this many stages ahead of the consumers (< RING)
 constexpr int GROUP = 32;        // intervals per CTA pass
 constexpr int NWARP = 8;
 
@@ -39,9 +45,7 @@ constexpr int NWARP = 8;
 constexpr int J_WW = 0;          // 9  sigma * d(wdot)/dw, row-major
 constexpr int J_HW = 9;          // 3  sigma*w/2
 constexpr int J_HQ = 12;         // 4  sigma*q/2
-constexpr int J_VM = 16;         // 3  sigma * d(vdot)/dm
-constexpr int J_VV = 19;         // 9  sigma * d(vdot)/dv (aero), row-major
-constexpr int J_VQ = 28;         // 12 sigma * d(vdot)/dq, row-major 3x4
+constexpr int J_V = 16;          // 3 rows x 8: [d(vdot_r)/dm, d(vdot_r)/dv (3), d(vdot_r)/dq (4)], all times sigma
 constexpr int J_G = 40;          // 4 columns (u0,u1,u2,f) x 7 rows (m, v0..2, w0..2)
 constexpr int J_FRQ = 68;        // 7  f_r (= v) and f_q of the unscaled rhs (sigma column only)
 constexpr int J_SIG = 75;        // 1  sigma
@@ -108,16 +112,16 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
     const double car = dp * inb;
     double ca = car, mc = 1.0;
     if (car > 1.0) { ca = 1.0; mc = 0.0; } else if (car < -1.0) { ca = -1.0; mc = 0.0; }
-    const double mach = nv * (1.0 / P.sos);
+    const double mach = nv * (1.0 / __ldg(&P.sos));
     // d(ca)/dv, d(ca)/db ; d(mach)/dv
     double cav[3], cab[3], mv[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         cav[k] = mc * (b[k] - dp * vh[k]) * inv * inb;
         cab[k] = mc * (vh[k] - car * b[k] * inb) * inb;
-        mv[k] = vh[k] * (1.0 / P.sos);
+        mv[k] = vh[k] * (1.0 / __ldg(&P.sos));
     }
-    const double fs = P.force_scalar;
+    const double fs = __ldg(&P.force_scalar);
     const double drag = spline_val(tb.drag, tb, ca, mach) * fs;
     double gx, gy;
     spline_grad(tb.drag, tb, ca, mach, gx, gy);
@@ -182,7 +186,7 @@ __device__ __forceinline__ void rhs_value(const scvx_probinfo& P, const ScvxTabl
     const double c10 = 2.0 * (p1 + p2), c11 = 1.0 - 2.0 * (q1 * q1 + q3 * q3), c12 = 2.0 * (p5 - p6);
     const double c20 = 2.0 * (p3 - p4), c21 = 2.0 * (p5 + p6), c22 = 1.0 - 2.0 * (q1 * q1 + q2 * q2);
     double F[3] = { 0.0, 0.0, 0.0 };
-    if (P.aero_kind == SCVX_AERO_TABLE) {
+    if (__ldg(&P.aero_kind) == SCVX_AERO_TABLE) {
         const double bv[3] = { c00, c10, c20 };
         aero_force_jac(P, tb, bv, x + 4, F, Fv, Fb);
     } else {
@@ -192,24 +196,24 @@ __device__ __forceinline__ void rhs_value(const scvx_probinfo& P, const ScvxTabl
             for (int c = 0; c < 3; ++c) { Fv[r][c] = 0.0; Fb[r][c] = 0.0; }
     }
     const double im = 1.0 / x[0];
-    f[0] = -P.a * sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    f[0] = -__ldg(&P.a) * sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
     f[1] = x[4]; f[2] = x[5]; f[3] = x[6];
-    f[4] = (c00 * u[0] + c01 * u[1] + c02 * u[2] + F[0]) * im - P.g0;
+    f[4] = (c00 * u[0] + c01 * u[1] + c02 * u[2] + F[0]) * im - __ldg(&P.g0);
     f[5] = (c10 * u[0] + c11 * u[1] + c12 * u[2] + F[1]) * im;
     f[6] = (c20 * u[0] + c21 * u[1] + c22 * u[2] + F[2]) * im;
     f[7]  = 0.5 * (-(w0 * q1) - w1 * q2 - w2 * q3);
     f[8]  = 0.5 * (w0 * q0 + w2 * q2 - w1 * q3);
     f[9]  = 0.5 * (w1 * q0 - w2 * q1 + w0 * q3);
     f[10] = 0.5 * (w2 * q0 + w1 * q1 - w0 * q2);
-    const double h0 = P.jB[0] * w0 + P.jB[3] * w1 + P.jB[6] * w2;
-    const double h1 = P.jB[1] * w0 + P.jB[4] * w1 + P.jB[7] * w2;
-    const double h2 = P.jB[2] * w0 + P.jB[5] * w1 + P.jB[8] * w2;
-    const double m0 = (P.rTB[1] * u[2] - P.rTB[2] * u[1]) - (w1 * h2 - w2 * h1);
-    const double m1 = (P.rTB[2] * u[0] - P.rTB[0] * u[2]) - (w2 * h0 - w0 * h2);
-    const double m2 = (P.rTB[0] * u[1] - P.rTB[1] * u[0]) - (w0 * h1 - w1 * h0);
-    f[11] = P.jBi[0] * m0 + P.jBi[3] * m1 + P.jBi[6] * m2;
-    f[12] = P.jBi[1] * m0 + P.jBi[4] * m1 + P.jBi[7] * m2;
-    f[13] = P.jBi[2] * m0 + P.jBi[5] * m1 + P.jBi[8] * m2;
+    const double h0 = __ldg(&P.jB[0]) * w0 + __ldg(&P.jB[3]) * w1 + __ldg(&P.jB[6]) * w2;
+    const double h1 = __ldg(&P.jB[1]) * w0 + __ldg(&P.jB[4]) * w1 + __ldg(&P.jB[7]) * w2;
+    const double h2 = __ldg(&P.jB[2]) * w0 + __ldg(&P.jB[5]) * w1 + __ldg(&P.jB[8]) * w2;
+    const double m0 = (__ldg(&P.rTB[1]) * u[2] - __ldg(&P.rTB[2]) * u[1]) - (w1 * h2 - w2 * h1);
+    const double m1 = (__ldg(&P.rTB[2]) * u[0] - __ldg(&P.rTB[0]) * u[2]) - (w2 * h0 - w0 * h2);
+    const double m2 = (__ldg(&P.rTB[0]) * u[1] - __ldg(&P.rTB[1]) * u[0]) - (w0 * h1 - w1 * h0);
+    f[11] = __ldg(&P.jBi[0]) * m0 + __ldg(&P.jBi[3]) * m1 + __ldg(&P.jBi[6]) * m2;
+    f[12] = __ldg(&P.jBi[1]) * m0 + __ldg(&P.jBi[4]) * m1 + __ldg(&P.jBi[7]) * m2;
+    f[13] = __ldg(&P.jBi[2]) * m0 + __ldg(&P.jBi[5]) * m1 + __ldg(&P.jBi[8]) * m2;
 }
 
 __global__ void __launch_bounds__(128, 3) stage_value_kernel(StagedArgs a) {
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(128, 3) stage_value_kernel(StagedArgs a) {
             const double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
             double* o = bt.out_tlb + ((size_t)b * bt.n_nodes + i + k) * 4;
             *reinterpret_cast<double2*>(o) = make_double2(-(u[0] / nu), -(u[1] / nu));
-            *reinterpret_cast<double2*>(o + 2) = make_double2(-(u[2] / nu), P.Tmin - nu);
+            *reinterpret_cast<double2*>(o + 2) = make_double2(-(u[2] / nu), __ldg(&P.Tmin) - nu);
         }
     }
 }
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(128) light_columns_kernel(StagedArgs a) {
     const int w = a.first + t;
     const int b = w / ni, i = w % ni;
     const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
-    const double sigma = bt.sigma[b], g0 = P.g0;
+    const double sigma = __ldg(bt.sigma + b), g0 = __ldg(&P.g0);
     const bool aero = (a.rec_n == REC_AERO);
     const int nst = 4 * bt.npts;
     const double* rec = a.rec + ((size_t)(t >> 5) * nst) * ((size_t)a.rec_n * GROUP) + (t & 31);
@@ -424,6 +428,13 @@ __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpre
 // out: this lane's NJ-double Jacobian record in the ring.
 __device__ __noinline__ void produce_stage(const scvx_probinfo& P, bool aero_rec, double sigma,
                                               const double* __restrict__ rec, double* __restrict__ out) {
+    // parameters first, as one batch of independent read-only loads (one latency, not one per use)
+    const double Pa = __ldg(&P.a), Pg0 = __ldg(&P.g0);
+    double jB[9], jBi[9], rT[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { jB[k] = __ldg(&P.jB[k]); jBi[k] = __ldg(&P.jBi[k]); }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rT[k] = __ldg(&P.rTB[k]);
     const double m = rec[0];
     const double v[3] = { rec[1 * GROUP], rec[2 * GROUP], rec[3 * GROUP] };
     const double q0 = rec[4 * GROUP], q1 = rec[5 * GROUP], q2 = rec[6 * GROUP], q3 = rec[7 * GROUP];
@@ -437,7 +448,6 @@ __device__ __noinline__ void produce_stage(const scvx_probinfo& P, bool aero_rec
 
     // ---- rotational block: Jww = -sigma * jBi * ([w]x jB - [jB w]x)
     {
-        const double* jB = P.jB; const double* jBi = P.jBi;
         const double L0 = jB[0] * w0 + jB[3] * w1 + jB[6] * w2;
         const double L1 = jB[1] * w0 + jB[4] * w1 + jB[7] * w2;
         const double L2 = jB[2] * w0 + jB[5] * w1 + jB[8] * w2;
@@ -492,17 +502,18 @@ __device__ __noinline__ void produce_stage(const scvx_probinfo& P, bool aero_rec
             for (int c = 0; c < 3; ++c) Jvv[3 * r + c] = sm * Fv[r][c];
         }
     }
-    // Jvm = -sigma * ((C u + F)/m) / m = -(sigma/m) * (f_v + g0 e1)
-    st2(out + J_VM + 0, -sm * (fv[0] + P.g0), -sm * fv[1]);
-    st2(out + J_VM + 2, -sm * fv[2], Jvv[0]);
-    st2(out + J_VV + 1, Jvv[1], Jvv[2]); st2(out + J_VV + 3, Jvv[3], Jvv[4]);
-    st2(out + J_VV + 5, Jvv[5], Jvv[6]); st2(out + J_VV + 7, Jvv[7], Jvv[8]);
+    // Jvm = -sigma * ((C u + F)/m) / m = -(sigma/m) * (f_v + g0 e1); one 8-double row per v component
 #pragma unroll
-    for (int k = 0; k < 12; k += 2) st2(out + J_VQ + k, sm * Jq[k], sm * Jq[k + 1]);
+    for (int r = 0; r < 3; ++r) {
+        double* o = out + J_V + 8 * r;
+        st2(o + 0, -sm * (fv[r] + (r == 0 ? Pg0 : 0.0)), Jvv[3 * r]);
+        st2(o + 2, Jvv[3 * r + 1], Jvv[3 * r + 2]);
+        st2(o + 4, sm * Jq[4 * r], sm * Jq[4 * r + 1]);
+        st2(o + 6, sm * Jq[4 * r + 2], sm * Jq[4 * r + 3]);
+    }
     // ---- direct (control / sigma) columns: G[col][row], rows m, v0..2, w0..2
     const double nu = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
-    const double gm = -sigma * P.a / nu;
-    const double* jBi = P.jBi; const double* rT = P.rTB;
+    const double gm = -sigma * Pa / nu;
     // jBi * (rTB x e_j): rTB x e0 = (0, r2, -r1); x e1 = (-r2, 0, r0); x e2 = (r1, -r0, 0)
     double G[28];
     G[0] = gm * u0; G[1] = sm * c00; G[2] = sm * c10; G[3] = sm * c20;
@@ -536,6 +547,99 @@ __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_ca
 struct FullCol {
     double S[11], A[11], Y[11], Sr[3];
 };
+
+
+// One rk4 stage of TWO full tangent columns (8-lane variant).  ST = stage within the step (compile time, so the
+// rk4 weights fold into the instruction stream and there is no control flow inside the stage).
+// Rows are processed in cascade order (r, v, m, q, w): a row block is overwritten only after every block that
+// reads its old stage value has been formed.
+template <int ST>
+__device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const double* __restrict__ J, const int gcol,
+                                               const int l8, const double pc, const double sstep, const double h6,
+                                               uint64_t* empty_bar, const int lane) {
+    constexpr bool last = (ST == 3);
+    constexpr double wgt = (ST == 0 || ST == 3) ? 1.0 : 2.0;
+    const double cy = (ST == 2) ? sstep : 0.5 * sstep;
+    const double alA = (l8 < 3) ? 1.0 - pc : (l8 == 3 ? 1.0 : 0.0), alB = (l8 < 3) ? pc : 0.0;
+    const double dsA = (l8 == 3) ? 1.0 : 0.0;
+    const double* Gc = J + J_G + 7 * gcol;
+    auto upd = [&](FullCol& F, const int idx, const double K) {
+        if constexpr (!last) { F.A[idx] = fma(wgt, K, F.A[idx]); F.Y[idx] = fma(cy, K, F.S[idx]); }
+        else { F.S[idx] = fma(h6, F.A[idx] + K, F.S[idx]); F.Y[idx] = F.S[idx]; F.A[idx] = 0.0; }
+    };
+    // ---- r rows (pure quadrature): S_r += cr * (sigma * Y_v + dsigma * f_r)
+    {
+        const double2 fr01 = ld2(J + J_FRQ);
+        const double fr2 = J[J_FRQ + 2];
+        const double sg = J[J_FRQ + 7];
+        const double cr = h6 * wgt;
+        const double csg = cr * sg, cds = cr * dsA;
+        FA.Sr[0] = fma(csg, FA.Y[1], fma(cds, fr01.x, FA.Sr[0]));
+        FA.Sr[1] = fma(csg, FA.Y[2], fma(cds, fr01.y, FA.Sr[1]));
+        FA.Sr[2] = fma(csg, FA.Y[3], fma(cds, fr2, FA.Sr[2]));
+#pragma unroll
+        for (int r = 0; r < 3; ++r) FB.Sr[r] = fma(csg, FB.Y[1 + r], FB.Sr[r]);
+    }
+    // ---- v rows: K_v = Jvm Y_m + Jvv Y_v + Jvq Y_q + alpha * G_v
+    {
+        double kA[3], kB[3];
+#pragma unroll
+        for (int row = 0; row < 3; ++row) {
+            const double2 c01 = ld2(J + J_V + 8 * row), c23 = ld2(J + J_V + 8 * row + 2);
+            const double2 qa = ld2(J + J_V + 8 * row + 4), qb = ld2(J + J_V + 8 * row + 6);
+            const double gg = Gc[1 + row];
+            kA[row] = fma(c01.x, FA.Y[0], fma(c01.y, FA.Y[1], fma(c23.x, FA.Y[2], fma(c23.y, FA.Y[3], alA * gg)))) +
+                      fma(qa.x, FA.Y[4], fma(qa.y, FA.Y[5], fma(qb.x, FA.Y[6], qb.y * FA.Y[7])));
+            kB[row] = fma(c01.x, FB.Y[0], fma(c01.y, FB.Y[1], fma(c23.x, FB.Y[2], fma(c23.y, FB.Y[3], alB * gg)))) +
+                      fma(qa.x, FB.Y[4], fma(qa.y, FB.Y[5], fma(qb.x, FB.Y[6], qb.y * FB.Y[7])));
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { upd(FA, 1 + r, kA[r]); upd(FB, 1 + r, kB[r]); }
+    }
+    // ---- m row: K_m = alpha * G_m
+    {
+        const double gmv = Gc[0];
+        upd(FA, 0, alA * gmv); upd(FB, 0, alB * gmv);
+    }
+    // ---- q rows: K_q = Omega(hw) Y_q + Omega(Y_w) hq + dsigma * f_q
+    {
+        const double hw0 = J[J_HW], hw1 = J[J_HW + 1], hw2 = J[J_HW + 2];
+        const double2 hq01 = ld2(J + J_HQ), hq23 = ld2(J + J_HQ + 2);
+        const double hq0 = hq01.x, hq1 = hq01.y, hq2 = hq23.x, hq3 = hq23.y;
+        const double fq0 = J[J_FRQ + 3];
+        const double2 fq12 = ld2(J + J_FRQ + 4);
+        const double fq3 = J[J_FRQ + 6];
+        double kA[4], kB[4];
+#define QROWS(F, K, ds)                                                                                                                     \
+        K[0] = fma(-hw0, F.Y[5], fma(-hw1, F.Y[6], fma(-hw2, F.Y[7], ds * fq0))) + fma(-hq1, F.Y[8], fma(-hq2, F.Y[9], -hq3 * F.Y[10]));     \
+        K[1] = fma(hw0, F.Y[4], fma(hw2, F.Y[6], fma(-hw1, F.Y[7], ds * fq12.x))) + fma(hq0, F.Y[8], fma(hq2, F.Y[10], -hq3 * F.Y[9]));      \
+        K[2] = fma(hw1, F.Y[4], fma(-hw2, F.Y[5], fma(hw0, F.Y[7], ds * fq12.y))) + fma(hq0, F.Y[9], fma(-hq1, F.Y[10], hq3 * F.Y[8]));      \
+        K[3] = fma(hw2, F.Y[4], fma(hw1, F.Y[5], fma(-hw0, F.Y[6], ds * fq3))) + fma(hq0, F.Y[10], fma(hq1, F.Y[9], -hq2 * F.Y[8]));
+        QROWS(FA, kA, dsA)
+        QROWS(FB, kB, 0.0)
+#undef QROWS
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { upd(FA, 4 + r, kA[r]); upd(FB, 4 + r, kB[r]); }
+    }
+    // ---- w rows: K_w = Jww * Y_w + alpha * G_w
+    {
+        const double2 j01 = ld2(J + J_WW), j23 = ld2(J + J_WW + 2), j45 = ld2(J + J_WW + 4), j67 = ld2(J + J_WW + 6);
+        const double j8 = J[J_WW + 8];
+        const double g0 = Gc[4], g1 = Gc[5], g2 = Gc[6];
+        double kA[3], kB[3];
+        kA[0] = fma(j01.x, FA.Y[8], fma(j01.y, FA.Y[9], fma(j23.x, FA.Y[10], alA * g0)));
+        kA[1] = fma(j23.y, FA.Y[8], fma(j45.x, FA.Y[9], fma(j45.y, FA.Y[10], alA * g1)));
+        kA[2] = fma(j67.x, FA.Y[8], fma(j67.y, FA.Y[9], fma(j8, FA.Y[10], alA * g2)));
+        kB[0] = fma(j01.x, FB.Y[8], fma(j01.y, FB.Y[9], fma(j23.x, FB.Y[10], alB * g0)));
+        kB[1] = fma(j23.y, FB.Y[8], fma(j45.x, FB.Y[9], fma(j45.y, FB.Y[10], alB * g1)));
+        kB[2] = fma(j67.x, FB.Y[8], fma(j67.y, FB.Y[9], fma(j8, FB.Y[10], alB * g2)));
+        // all reads of the ring slot are done: hand it back
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { upd(FA, 8 + r, kA[r]); upd(FB, 8 + r, kB[r]); }
+    }
+}
 
 __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -612,6 +716,8 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
         if (nextP == k && nextP < total_stages) produce();
 
     FullCol FA, FB;
+    double park[72];
+    volatile double* vp = park;
     int T = 0;
     int c_slot = 0;
     uint32_t c_phase = 0;
@@ -630,107 +736,38 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
         for (int r = 0; r < 3; ++r) FA.Sr[r] = FB.Sr[r] = 0.0;
 
         double pca = 0.0;
-        for (int s = 0; s < nst; ++s, ++T) {
-            // producer duty for stage T + LOOKAHEAD
-            if (nextP == T + LOOKAHEAD && nextP < total_stages) produce();
-
-            const int st = s & 3;
-            const double pc = (st == 0) ? pca : (st == 3 ? pca + pcs : pca + 0.5 * pcs);
-            const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
-            const double cy = (st == 2) ? sstep : 0.5 * sstep;
-            const double cr = h6 * wgt;
-            const double alA = (l8 < 3) ? 1.0 - pc : (l8 == 3 ? 1.0 : 0.0), alB = (l8 < 3) ? pc : 0.0;
-            const double dsA = (l8 == 3) ? 1.0 : 0.0;
-            const int slot = c_slot;
-            mbar_wait(&sm.full[slot], c_phase);
-            if (++c_slot == RING) { c_slot = 0; c_phase ^= 1; }
-            const double* J = &sm.ring[slot][warp * 4 + sub][0];
-            const double* Gc = J + J_G + 7 * gcol;
-            const bool last = (st == 3);
-            // In-place RK bookkeeping of one row: non-final stages accumulate and form the next stage tangent,
-            // the final stage closes the step.  Rows are processed in cascade order (r, v, m, q, w): a row block
-            // is overwritten only after every block that reads its old stage value has been formed.
-#define UPD(F, idx, Kv)                                                                                 \
-            if (!last) { F.A[idx] = fma(wgt, (Kv), F.A[idx]); F.Y[idx] = fma(cy, (Kv), F.S[idx]); }      \
-            else { F.S[idx] = fma(h6, F.A[idx] + (Kv), F.S[idx]); F.Y[idx] = F.S[idx]; F.A[idx] = 0.0; }
-
-            // ---- r rows (pure quadrature): S_r += cr * (sigma * Y_v + dsigma * f_r)
-            {
-                const double2 fr01 = ld2(J + J_FRQ);
-                const double fr2 = J[J_FRQ + 2];
-                const double sg = J[J_FRQ + 7];
-                const double csg = cr * sg, cds = cr * dsA;
-                FA.Sr[0] = fma(csg, FA.Y[1], fma(cds, fr01.x, FA.Sr[0]));
-                FA.Sr[1] = fma(csg, FA.Y[2], fma(cds, fr01.y, FA.Sr[1]));
-                FA.Sr[2] = fma(csg, FA.Y[3], fma(cds, fr2, FA.Sr[2]));
-#pragma unroll
-                for (int r = 0; r < 3; ++r) FB.Sr[r] = fma(csg, FB.Y[1 + r], FB.Sr[r]);
+#pragma unroll 1
+        for (int step = 0; step < bt.npts; ++step) {
+#define STAGE8(ST, PC)                                                                                  \
+            {                                                                                             \
+                if (nextP == T + LOOKAHEAD && nextP < total_stages) {                                      \
+                    /* manual live-range split: park the tangent state in local memory across the producer   \
+                       call so that it never competes with the producer for registers inside the hot loop */ \
+                    _Pragma("unroll") for (int r = 0; r < 11; ++r) {                                          \
+                        vp[r] = FA.S[r]; vp[11 + r] = FA.A[r]; vp[22 + r] = FA.Y[r];                          \
+                        vp[36 + r] = FB.S[r]; vp[47 + r] = FB.A[r]; vp[58 + r] = FB.Y[r];                     \
+                    }                                                                                         \
+                    _Pragma("unroll") for (int r = 0; r < 3; ++r) { vp[33 + r] = FA.Sr[r]; vp[69 + r] = FB.Sr[r]; } \
+                    produce();                                                                                \
+                    _Pragma("unroll") for (int r = 0; r < 11; ++r) {                                          \
+                        FA.S[r] = vp[r]; FA.A[r] = vp[11 + r]; FA.Y[r] = vp[22 + r];                          \
+                        FB.S[r] = vp[36 + r]; FB.A[r] = vp[47 + r]; FB.Y[r] = vp[58 + r];                     \
+                    }                                                                                         \
+                    _Pragma("unroll") for (int r = 0; r < 3; ++r) { FA.Sr[r] = vp[33 + r]; FB.Sr[r] = vp[69 + r]; } \
+                }                                                                                             \
+                const int slot = c_slot;                                                                  \
+                mbar_wait(&sm.full[slot], c_phase);                                                       \
+                if (++c_slot == RING) { c_slot = 0; c_phase ^= 1; }                                       \
+                consume_stage8<ST>(FA, FB, &sm.ring[slot][warp * 4 + sub][0], gcol, l8, (PC), sstep, h6,  \
+                                   &sm.empty[slot], lane);                                                \
+                ++T;                                                                                      \
             }
-            // ---- v rows: K_v = Jvm Y_m + Jvv Y_v + Jvq Y_q + alpha * G_v
-            {
-                const double2 m01 = ld2(J + J_VM);
-                const double2 m2v0 = ld2(J + J_VM + 2);           // Jvm[2], Jvv[0]
-                const double2 v12 = ld2(J + J_VV + 1), v34 = ld2(J + J_VV + 3), v56 = ld2(J + J_VV + 5), v78 = ld2(J + J_VV + 7);
-                const double g0 = Gc[1], g1 = Gc[2], g2 = Gc[3];
-                double kA[3], kB[3];
-#define VROW(row, jm, a, b, c, gg)                                                                                      \
-                {                                                                                                         \
-                    const double2 qa = ld2(J + J_VQ + 4 * row), qb = ld2(J + J_VQ + 4 * row + 2);                         \
-                    kA[row] = fma(jm, FA.Y[0], fma(a, FA.Y[1], fma(b, FA.Y[2], fma(c, FA.Y[3], fma(qa.x, FA.Y[4], fma(qa.y, FA.Y[5], fma(qb.x, FA.Y[6], fma(qb.y, FA.Y[7], alA * gg)))))))); \
-                    kB[row] = fma(jm, FB.Y[0], fma(a, FB.Y[1], fma(b, FB.Y[2], fma(c, FB.Y[3], fma(qa.x, FB.Y[4], fma(qa.y, FB.Y[5], fma(qb.x, FB.Y[6], fma(qb.y, FB.Y[7], alB * gg)))))))); \
-                }
-                VROW(0, m01.x, m2v0.y, v12.x, v12.y, g0)
-                VROW(1, m01.y, v34.x, v34.y, v56.x, g1)
-                VROW(2, m2v0.x, v56.y, v78.x, v78.y, g2)
-#undef VROW
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { UPD(FA, 1 + r, kA[r]) UPD(FB, 1 + r, kB[r]) }
-            }
-            // ---- m row: K_m = alpha * G_m
-            {
-                const double gmv = Gc[0];
-                UPD(FA, 0, alA * gmv) UPD(FB, 0, alB * gmv)
-            }
-            // ---- q rows: K_q = Omega(hw) Y_q + Omega(Y_w) hq + dsigma * f_q
-            {
-                const double hw0 = J[J_HW], hw1 = J[J_HW + 1], hw2 = J[J_HW + 2];
-                const double2 hq01 = ld2(J + J_HQ), hq23 = ld2(J + J_HQ + 2);
-                const double hq0 = hq01.x, hq1 = hq01.y, hq2 = hq23.x, hq3 = hq23.y;
-                const double fq0 = J[J_FRQ + 3];
-                const double2 fq12 = ld2(J + J_FRQ + 4);
-                const double fq3 = J[J_FRQ + 6];
-                double kA[4], kB[4];
-#define QROWS(F, K, ds)                                                                                                   \
-                K[0] = fma(-hw0, F.Y[5], fma(-hw1, F.Y[6], fma(-hw2, F.Y[7], fma(-hq1, F.Y[8], fma(-hq2, F.Y[9], fma(-hq3, F.Y[10], ds * fq0)))))); \
-                K[1] = fma(hw0, F.Y[4], fma(hw2, F.Y[6], fma(-hw1, F.Y[7], fma(hq0, F.Y[8], fma(hq2, F.Y[10], fma(-hq3, F.Y[9], ds * fq12.x)))))); \
-                K[2] = fma(hw1, F.Y[4], fma(-hw2, F.Y[5], fma(hw0, F.Y[7], fma(hq0, F.Y[9], fma(-hq1, F.Y[10], fma(hq3, F.Y[8], ds * fq12.y)))))); \
-                K[3] = fma(hw2, F.Y[4], fma(hw1, F.Y[5], fma(-hw0, F.Y[6], fma(hq0, F.Y[10], fma(hq1, F.Y[9], fma(-hq2, F.Y[8], ds * fq3))))));
-                QROWS(FA, kA, dsA)
-                QROWS(FB, kB, 0.0)
-#undef QROWS
-#pragma unroll
-                for (int r = 0; r < 4; ++r) { UPD(FA, 4 + r, kA[r]) UPD(FB, 4 + r, kB[r]) }
-            }
-            // ---- w rows: K_w = Jww * Y_w + alpha * G_w
-            {
-                const double2 j01 = ld2(J + J_WW), j23 = ld2(J + J_WW + 2), j45 = ld2(J + J_WW + 4), j67 = ld2(J + J_WW + 6);
-                const double j8 = J[J_WW + 8];
-                const double g0 = Gc[4], g1 = Gc[5], g2 = Gc[6];
-                double kA[3], kB[3];
-                kA[0] = fma(j01.x, FA.Y[8], fma(j01.y, FA.Y[9], fma(j23.x, FA.Y[10], alA * g0)));
-                kA[1] = fma(j23.y, FA.Y[8], fma(j45.x, FA.Y[9], fma(j45.y, FA.Y[10], alA * g1)));
-                kA[2] = fma(j67.x, FA.Y[8], fma(j67.y, FA.Y[9], fma(j8, FA.Y[10], alA * g2)));
-                kB[0] = fma(j01.x, FB.Y[8], fma(j01.y, FB.Y[9], fma(j23.x, FB.Y[10], alB * g0)));
-                kB[1] = fma(j23.y, FB.Y[8], fma(j45.x, FB.Y[9], fma(j45.y, FB.Y[10], alB * g1)));
-                kB[2] = fma(j67.x, FB.Y[8], fma(j67.y, FB.Y[9], fma(j8, FB.Y[10], alB * g2)));
-                // all reads of the ring slot are done: hand it back
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.empty[slot]);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { UPD(FA, 8 + r, kA[r]) UPD(FB, 8 + r, kB[r]) }
-            }
-#undef UPD
-            if (last) pca += pcs;
+            STAGE8(0, pca)
+            STAGE8(1, pca + 0.5 * pcs)
+            STAGE8(2, pca + 0.5 * pcs)
+            STAGE8(3, pca + pcs)
+#undef STAGE8
+            pca += pcs;
         }
 
         // ---- epilogue: write D columns and z for interval (g*32 + warp*4 + sub)
@@ -785,6 +822,243 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Kernel B, 16-lane variant: ONE full tangent column per lane, 16 lanes per interval, 2 intervals per warp,
+// 16 warps (512 threads, <= 128 registers) per CTA, still 32 intervals in flight per SM.  Twice the warps per
+// scheduler of the 8-lane variant for the same FP64 work: the stage loop is latency bound, not issue bound.
+// Stage records are staged in a pool of NB buffers indexed by the global stage number; the warp that will
+// produce stage T issues its TMA bulk copy PREFETCH stages before it produces.
+// ------------------------------------------------------------------------------------------------
+constexpr int NWARP16 = 16;
+constexpr int NB16 = 6;            // record buffers; must be >= LOOKAHEAD + PREFETCH + 1
+constexpr int PREFETCH16 = 2;
+static_assert(NB16 >= LOOKAHEAD + PREFETCH16 + 1, "record buffer pool too small");
+
+struct __align__(16) Tangent16Smem {
+    double ring[RING][GROUP][NJ];
+    double recbuf[NB16][REC_MAX * GROUP];
+    uint64_t full[RING];
+    uint64_t empty[RING];
+    uint64_t recfull[NB16];
+};
+
+__global__ void __launch_bounds__(512, 1) tangent16_kernel(StagedArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Tangent16Smem& sm = *reinterpret_cast<Tangent16Smem*>(smem_raw);
+    const ScvxBatch& bt = a.bt;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int l16 = lane & 15;                 // column lane within the interval
+    const int sub = lane >> 4;                 // interval within the warp (0..1)
+    const int ni = bt.n_nodes - 1;
+    const int nst = 4 * bt.npts;
+    const double h = bt.dt / (double)bt.npts;
+    const double pcs = 1.0 / (double)bt.npts;
+    const double sstep = (bt.mode == SCVX_MODE_LITERAL) ? 1.0 : h;
+    const double h6 = h * (1.0 / 6.0);
+
+    if (tid == 0) {
+        for (int r = 0; r < RING; ++r) { mbar_init(&sm.full[r], 32); mbar_init(&sm.empty[r], NWARP16); }
+        for (int q = 0; q < NB16; ++q) mbar_init(&sm.recfull[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int my_groups = (a.n_groups > (int)blockIdx.x) ? (a.n_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total_stages = my_groups * nst;
+
+    // column of this lane: 0..2 u-_j | 3..5 u+_j | 6 sigma | 7..9 w_j | 10..13 q_j | 14,15 idle
+    int col = -1, gcol = 3;
+    if (l16 < 3) { col = 14 + l16; gcol = l16; }
+    else if (l16 < 6) { col = 14 + l16; gcol = l16 - 3; }
+    else if (l16 == 6) col = 20;
+    else if (l16 < 10) col = 4 + l16;            // w_j -> inp columns 11..13
+    else if (l16 < 14) col = l16 - 3;            // q_j -> inp columns 7..10
+
+    auto issue_record = [&](int Tp) {             // one lane: TMA the stage record of global stage Tp
+        const int it = Tp / nst, s = Tp - it * nst;
+        const int g = blockIdx.x + it * gridDim.x;
+        const uint32_t bytes = (uint32_t)a.rec_n * GROUP * 8;
+        const double* src = a.rec + ((size_t)g * nst + s) * ((size_t)a.rec_n * GROUP);
+        const int q = Tp % NB16;
+        fence_proxy_async();
+        mbar_expect_tx(&sm.recfull[q], bytes);
+        bulk_g2s(sm.recbuf[q], src, bytes, &sm.recfull[q]);
+    };
+    auto produce = [&](int Tp) {                  // whole warp, lane = interval
+        const int it = Tp / nst;
+        const int g = blockIdx.x + it * gridDim.x;
+        int t = g * GROUP + lane; if (t >= a.count) t = a.count - 1;
+        const int b = (a.first + t) / ni;
+        const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
+        const double sigma = bt.sigma[b];
+        const int slot = Tp % RING, use = Tp / RING;
+        const int q = Tp % NB16;
+        mbar_wait(&sm.recfull[q], (uint32_t)((Tp / NB16) & 1));
+        if (use > 0) mbar_wait(&sm.empty[slot], (uint32_t)((use - 1) & 1));
+        produce_stage(P, a.rec_n == REC_AERO, sigma, sm.recbuf[q] + lane, &sm.ring[slot][lane][0]);
+        mbar_arrive(&sm.full[slot]);
+    };
+
+    // prologue: records of stages 0..LOOKAHEAD+PREFETCH-1 in flight, stages 0..LOOKAHEAD-1 produced
+    for (int k = 0; k < LOOKAHEAD + PREFETCH16; ++k)
+        if ((k % NWARP16) == warp && lane == 0 && k < total_stages) issue_record(k);
+    for (int k = 0; k < LOOKAHEAD; ++k)
+        if ((k % NWARP16) == warp && k < total_stages) produce(k);
+
+    FullCol F;
+    double park[36];
+    volatile double* vp = park;
+    int T = 0, c_slot = 0;
+    uint32_t c_phase = 0;
+    for (int it = 0; it < my_groups; ++it) {
+        const int g = blockIdx.x + it * gridDim.x;
+#pragma unroll
+        for (int r = 0; r < 11; ++r) {
+            F.S[r] = (r >= 4 && col == r + 3) ? 1.0 : 0.0;       // local rows: 0 m, 1..3 v, 4..7 q, 8..10 w
+            F.A[r] = 0.0; F.Y[r] = F.S[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) F.Sr[r] = 0.0;
+
+        double pca = 0.0;
+#pragma unroll 1
+        for (int s = 0; s < nst; ++s, ++T) {
+            {   // producer duties of this warp
+                const int Ti = T + LOOKAHEAD + PREFETCH16;
+                if ((Ti & (NWARP16 - 1)) == warp && lane == 0 && Ti < total_stages) issue_record(Ti);
+                const int Tp = T + LOOKAHEAD;
+                if ((Tp & (NWARP16 - 1)) == warp && Tp < total_stages) {
+                    // manual live-range split: park the tangent state in local memory across the producer call
+#pragma unroll
+                    for (int r = 0; r < 11; ++r) { vp[r] = F.S[r]; vp[11 + r] = F.A[r]; vp[22 + r] = F.Y[r]; }
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) vp[33 + r] = F.Sr[r];
+                    produce(Tp);
+#pragma unroll
+                    for (int r = 0; r < 11; ++r) { F.S[r] = vp[r]; F.A[r] = vp[11 + r]; F.Y[r] = vp[22 + r]; }
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) F.Sr[r] = vp[33 + r];
+                }
+            }
+            const int st = s & 3;
+            const bool last = (st == 3);
+            const double pc = (st == 0) ? pca : (last ? pca + pcs : pca + 0.5 * pcs);
+            const double wgt = (st == 0 || last) ? 1.0 : 2.0;
+            const double cy = (st == 2) ? sstep : 0.5 * sstep;
+            const double cr = h6 * wgt;
+            const double al = (l16 < 3) ? 1.0 - pc : (l16 < 6 ? pc : (l16 == 6 ? 1.0 : 0.0));
+            const double ds = (l16 == 6) ? 1.0 : 0.0;
+            const int slot = c_slot;
+            mbar_wait(&sm.full[slot], c_phase);
+            if (++c_slot == RING) { c_slot = 0; c_phase ^= 1; }
+            const double* J = &sm.ring[slot][warp * 2 + sub][0];
+            const double* Gc = J + J_G + 7 * gcol;
+#define UPD1(idx, Kv)                                                                               \
+            if (!last) { F.A[idx] = fma(wgt, (Kv), F.A[idx]); F.Y[idx] = fma(cy, (Kv), F.S[idx]); }  \
+            else { F.S[idx] = fma(h6, F.A[idx] + (Kv), F.S[idx]); F.Y[idx] = F.S[idx]; F.A[idx] = 0.0; }
+            // ---- r rows (quadrature)
+            {
+                const double2 fr01 = ld2(J + J_FRQ);
+                const double fr2 = J[J_FRQ + 2];
+                const double sg = J[J_FRQ + 7];
+                const double csg = cr * sg, cds = cr * ds;
+                F.Sr[0] = fma(csg, F.Y[1], fma(cds, fr01.x, F.Sr[0]));
+                F.Sr[1] = fma(csg, F.Y[2], fma(cds, fr01.y, F.Sr[1]));
+                F.Sr[2] = fma(csg, F.Y[3], fma(cds, fr2, F.Sr[2]));
+            }
+            // ---- v rows
+            {
+                double k[3];
+#define VROW1(row)                                                                                                      \
+                {                                                                                                         \
+                    const double2 c01 = ld2(J + J_V + 8 * row), c23 = ld2(J + J_V + 8 * row + 2);                         \
+                    const double2 qa = ld2(J + J_V + 8 * row + 4), qb = ld2(J + J_V + 8 * row + 6);                       \
+                    const double t0 = fma(c01.x, F.Y[0], fma(c01.y, F.Y[1], fma(c23.x, F.Y[2], fma(c23.y, F.Y[3], al * Gc[1 + row])))); \
+                    const double t1 = fma(qa.x, F.Y[4], fma(qa.y, F.Y[5], fma(qb.x, F.Y[6], qb.y * F.Y[7])));             \
+                    k[row] = t0 + t1;                                                                                     \
+                }
+                VROW1(0)
+                VROW1(1)
+                VROW1(2)
+#undef VROW1
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { UPD1(1 + r, k[r]) }
+            }
+            // ---- m row
+            { const double gmv = Gc[0]; UPD1(0, al * gmv) }
+            // ---- q rows
+            {
+                const double hw0 = J[J_HW], hw1 = J[J_HW + 1], hw2 = J[J_HW + 2];
+                const double2 hq01 = ld2(J + J_HQ), hq23 = ld2(J + J_HQ + 2);
+                const double hq0 = hq01.x, hq1 = hq01.y, hq2 = hq23.x, hq3 = hq23.y;
+                const double fq0 = J[J_FRQ + 3];
+                const double2 fq12 = ld2(J + J_FRQ + 4);
+                const double fq3 = J[J_FRQ + 6];
+                double k[4];
+                k[0] = fma(-hw0, F.Y[5], fma(-hw1, F.Y[6], fma(-hw2, F.Y[7], ds * fq0))) + fma(-hq1, F.Y[8], fma(-hq2, F.Y[9], -hq3 * F.Y[10]));
+                k[1] = fma(hw0, F.Y[4], fma(hw2, F.Y[6], fma(-hw1, F.Y[7], ds * fq12.x))) + fma(hq0, F.Y[8], fma(hq2, F.Y[10], -hq3 * F.Y[9]));
+                k[2] = fma(hw1, F.Y[4], fma(-hw2, F.Y[5], fma(hw0, F.Y[7], ds * fq12.y))) + fma(hq0, F.Y[9], fma(-hq1, F.Y[10], hq3 * F.Y[8]));
+                k[3] = fma(hw2, F.Y[4], fma(hw1, F.Y[5], fma(-hw0, F.Y[6], ds * fq3))) + fma(hq0, F.Y[10], fma(hq1, F.Y[9], -hq2 * F.Y[8]));
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { UPD1(4 + r, k[r]) }
+            }
+            // ---- w rows
+            {
+                const double2 j01 = ld2(J + J_WW), j23 = ld2(J + J_WW + 2), j45 = ld2(J + J_WW + 4), j67 = ld2(J + J_WW + 6);
+                const double j8 = J[J_WW + 8];
+                const double g0 = Gc[4], g1 = Gc[5], g2 = Gc[6];
+                double k[3];
+                k[0] = fma(j01.x, F.Y[8], fma(j01.y, F.Y[9], fma(j23.x, F.Y[10], al * g0)));
+                k[1] = fma(j23.y, F.Y[8], fma(j45.x, F.Y[9], fma(j45.y, F.Y[10], al * g1)));
+                k[2] = fma(j67.x, F.Y[8], fma(j67.y, F.Y[9], fma(j8, F.Y[10], al * g2)));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[slot]);       // all reads of the ring slot are done
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { UPD1(8 + r, k[r]) }
+            }
+#undef UPD1
+            if (last) pca += pcs;
+        }
+
+        // ---- epilogue: this lane's column of D, and z
+        const int t = g * GROUP + warp * 2 + sub;
+        const bool live = t < a.count;
+        const int wi = a.first + (live ? t : a.count - 1);
+        const int b = wi / ni, i = wi - b * ni;
+        double* blk = bt.out_blocks + (size_t)wi * SCVX_BLOCK_DOUBLES;
+        double xc = 0.0;
+        if (col >= 0) {
+            if (col < 14) xc = bt.X[((size_t)b * bt.n_nodes + i) * 14 + col];
+            else if (col < 20) xc = bt.U[((size_t)b * bt.n_nodes + i) * 3 + (col - 14)];
+            else xc = bt.sigma[b];
+        }
+        const double cv[14] = { F.S[0], F.Sr[0], F.Sr[1], F.Sr[2], F.S[1], F.S[2], F.S[3], F.S[4], F.S[5], F.S[6], F.S[7],
+                                F.S[8], F.S[9], F.S[10] };
+        if (live && col >= 0) {
+            double* o = blk + 14 * (1 + col);
+#pragma unroll
+            for (int r = 0; r < 14; r += 2) *reinterpret_cast<double2*>(o + r) = make_double2(cv[r], cv[r + 1]);
+        }
+        double zlast = 0.0, zprev = 0.0;
+#pragma unroll
+        for (int r = 0; r < 14; ++r) {
+            double v = (col >= 0) ? cv[r] * xc : 0.0;
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            // lane r (of the 16) keeps row r
+            if (l16 == r) zlast = v;
+            (void)zprev;
+        }
+        if (live && l16 < 14) {
+            double* o = blk + 14 * 22 + l16;
+            *o = *o - zlast;                                        // partial z written by kernel A2
+        }
+    }
+}
+
 }  // namespace
 
 size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals) {
@@ -795,11 +1069,13 @@ size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals) {
 int scvx_staged_chunk_intervals(int sm_count) { return sm_count * GROUP * 14; }
 
 cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, void* scratch,
-                               int chunk_intervals, int sm_count, cudaStream_t s, int* launches) {
+                               int chunk_intervals, int sm_count, cudaStream_t s, int* launches, int lanes) {
     const long total = (long)(bt.n_nodes - 1) * bt.B;
-    const size_t smem = sizeof(TangentSmem);
+    const size_t smem = (lanes == 8) ? sizeof(TangentSmem) : sizeof(Tangent16Smem);
     {
-        cudaError_t e = cudaFuncSetAttribute(tangent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = (lanes == 8)
+            ? cudaFuncSetAttribute(tangent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+            : cudaFuncSetAttribute(tangent16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     for (long first = 0; first < total; first += chunk_intervals) {
@@ -812,7 +1088,8 @@ cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool a
         stage_value_kernel<<<(threads + 127) / 128, 128, 0, s>>>(a);
         light_columns_kernel<<<(a.count + 127) / 128, 128, 0, s>>>(a);
         const int grid = a.n_groups < sm_count ? a.n_groups : sm_count;
-        tangent_kernel<<<grid, 256, smem, s>>>(a);
+        if (lanes == 8) tangent_kernel<<<grid, 256, smem, s>>>(a);
+        else tangent16_kernel<<<grid, 512, smem, s>>>(a);
         if (launches) *launches += 3;
     }
     return cudaGetLastError();
