@@ -549,17 +549,15 @@ struct FullCol {
 };
 
 
-// One rk4 stage of TWO full tangent columns (8-lane variant).  ST = stage within the step (compile time, so the
-// rk4 weights fold into the instruction stream and there is no control flow inside the stage).
+// One rk4 stage of TWO full tangent columns (8-lane variant).  LAST = final stage of the step (compile time, so
+// there is no control flow inside the stage; two instantiations keep the hot loop inside the instruction cache).
 // Rows are processed in cascade order (r, v, m, q, w): a row block is overwritten only after every block that
 // reads its old stage value has been formed.
-template <int ST>
+template <bool LAST>
 __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const double* __restrict__ J, const int gcol,
-                                               const int l8, const double pc, const double sstep, const double h6,
-                                               uint64_t* empty_bar, const int lane) {
-    constexpr bool last = (ST == 3);
-    constexpr double wgt = (ST == 0 || ST == 3) ? 1.0 : 2.0;
-    const double cy = (ST == 2) ? sstep : 0.5 * sstep;
+                                               const int l8, const double pc, const double wgt, const double cy,
+                                               const double h6, uint64_t* empty_bar, const int lane) {
+    constexpr bool last = LAST;
     const double alA = (l8 < 3) ? 1.0 - pc : (l8 == 3 ? 1.0 : 0.0), alB = (l8 < 3) ? pc : 0.0;
     const double dsA = (l8 == 3) ? 1.0 : 0.0;
     const double* Gc = J + J_G + 7 * gcol;
@@ -737,37 +735,39 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
 
         double pca = 0.0;
 #pragma unroll 1
-        for (int step = 0; step < bt.npts; ++step) {
-#define STAGE8(ST, PC)                                                                                  \
-            {                                                                                             \
-                if (nextP == T + LOOKAHEAD && nextP < total_stages) {                                      \
-                    /* manual live-range split: park the tangent state in local memory across the producer   \
-                       call so that it never competes with the producer for registers inside the hot loop */ \
-                    _Pragma("unroll") for (int r = 0; r < 11; ++r) {                                          \
-                        vp[r] = FA.S[r]; vp[11 + r] = FA.A[r]; vp[22 + r] = FA.Y[r];                          \
-                        vp[36 + r] = FB.S[r]; vp[47 + r] = FB.A[r]; vp[58 + r] = FB.Y[r];                     \
-                    }                                                                                         \
-                    _Pragma("unroll") for (int r = 0; r < 3; ++r) { vp[33 + r] = FA.Sr[r]; vp[69 + r] = FB.Sr[r]; } \
-                    produce();                                                                                \
-                    _Pragma("unroll") for (int r = 0; r < 11; ++r) {                                          \
-                        FA.S[r] = vp[r]; FA.A[r] = vp[11 + r]; FA.Y[r] = vp[22 + r];                          \
-                        FB.S[r] = vp[36 + r]; FB.A[r] = vp[47 + r]; FB.Y[r] = vp[58 + r];                     \
-                    }                                                                                         \
-                    _Pragma("unroll") for (int r = 0; r < 3; ++r) { FA.Sr[r] = vp[33 + r]; FB.Sr[r] = vp[69 + r]; } \
-                }                                                                                             \
-                const int slot = c_slot;                                                                  \
-                mbar_wait(&sm.full[slot], c_phase);                                                       \
-                if (++c_slot == RING) { c_slot = 0; c_phase ^= 1; }                                       \
-                consume_stage8<ST>(FA, FB, &sm.ring[slot][warp * 4 + sub][0], gcol, l8, (PC), sstep, h6,  \
-                                   &sm.empty[slot], lane);                                                \
-                ++T;                                                                                      \
+        for (int s = 0; s < nst; ++s, ++T) {
+            if (nextP == T + LOOKAHEAD && nextP < total_stages) {
+                // manual live-range split: park the tangent state in local memory across the producer call so
+                // that it never competes with the producer for registers inside the hot loop
+#pragma unroll
+                for (int r = 0; r < 11; ++r) {
+                    vp[r] = FA.S[r]; vp[11 + r] = FA.A[r]; vp[22 + r] = FA.Y[r];
+                    vp[36 + r] = FB.S[r]; vp[47 + r] = FB.A[r]; vp[58 + r] = FB.Y[r];
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { vp[33 + r] = FA.Sr[r]; vp[69 + r] = FB.Sr[r]; }
+                produce();
+#pragma unroll
+                for (int r = 0; r < 11; ++r) {
+                    FA.S[r] = vp[r]; FA.A[r] = vp[11 + r]; FA.Y[r] = vp[22 + r];
+                    FB.S[r] = vp[36 + r]; FB.A[r] = vp[47 + r]; FB.Y[r] = vp[58 + r];
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { FA.Sr[r] = vp[33 + r]; FB.Sr[r] = vp[69 + r]; }
             }
-            STAGE8(0, pca)
-            STAGE8(1, pca + 0.5 * pcs)
-            STAGE8(2, pca + 0.5 * pcs)
-            STAGE8(3, pca + pcs)
-#undef STAGE8
-            pca += pcs;
+            const int st = s & 3;
+            const int slot = c_slot;
+            mbar_wait(&sm.full[slot], c_phase);
+            if (++c_slot == RING) { c_slot = 0; c_phase ^= 1; }
+            const double* J = &sm.ring[slot][warp * 4 + sub][0];
+            if (st == 3) {
+                consume_stage8<true>(FA, FB, J, gcol, l8, pca + pcs, 1.0, 0.0, h6, &sm.empty[slot], lane);
+                pca += pcs;
+            } else {
+                const double pc = (st == 0) ? pca : pca + 0.5 * pcs;
+                consume_stage8<false>(FA, FB, J, gcol, l8, pc, st == 0 ? 1.0 : 2.0, st == 2 ? sstep : 0.5 * sstep, h6,
+                                      &sm.empty[slot], lane);
+            }
         }
 
         // ---- epilogue: write D columns and z for interval (g*32 + warp*4 + sub)
