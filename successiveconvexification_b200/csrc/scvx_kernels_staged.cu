@@ -63,9 +63,10 @@ struct StagedArgs {
 // ------------------------------------------------------------------------------------------------
 // Kernel A: value trajectory + stage records.
 // ------------------------------------------------------------------------------------------------
-// spline value + gradient w.r.t. the physical coordinates (0 when strictly outside: Flat extrapolation)
-__device__ __forceinline__ void spline_grad(const double* __restrict__ coef, const ScvxTables& t, double x, double y,
-                                            double& gx, double& gy) {
+// spline value and gradient w.r.t. the physical coordinates (gradient 0 when strictly outside: Flat extrapolation);
+// one pass over the 16 coefficients serves all three.
+__device__ __forceinline__ void spline_val_grad(const double* __restrict__ coef, const ScvxTables& t, double x, double y,
+                                                double& val, double& gx, double& gy) {
     const int L1 = t.n1 + 2;
     double xi = (x - t.x0) * t.inv_dx + 1.0, yi = (y - t.y0) * t.inv_dy + 1.0;
     double sx = t.inv_dx, sy = t.inv_dy;
@@ -81,22 +82,18 @@ __device__ __forceinline__ void spline_grad(const double* __restrict__ coef, con
                            (2.0 / 3.0) - oy * oy + 0.5 * oy * oy * oy, dy * dy * dy * (1.0 / 6.0) };
     const double gyw[4] = { -0.5 * oy * oy, -2.0 * dy + 1.5 * dy * dy, 2.0 * oy - 1.5 * oy * oy, 0.5 * dy * dy };
     const double* base = coef + (i - 1) + (size_t)(j - 1) * L1;
-    double ax = 0.0, ay = 0.0;
+    double av = 0.0, ax = 0.0, ay = 0.0;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
         const double* p = base + (size_t)b * L1;
         const double c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2), c3 = __ldg(p + 3);
         const double rv = wx[0] * c0 + wx[1] * c1 + wx[2] * c2 + wx[3] * c3;
         const double rg = gxw[0] * c0 + gxw[1] * c1 + gxw[2] * c2 + gxw[3] * c3;
+        av = fma(wy[b], rv, av);
         ax = fma(wy[b], rg, ax);
         ay = fma(gyw[b], rv, ay);
     }
-    gx = ax * sx; gy = ay * sy;
-}
-
-// spline value only
-__device__ __forceinline__ double spline_val(const double* __restrict__ coef, const ScvxTables& t, double x, double y) {
-    return spline_eval<double>(coef, t, x, y);
+    val = av; gx = ax * sx; gy = ay * sy;
 }
 
 // Jacobian of the aerodynamic force F(b, v) (aerodynamics.jl:38-58) w.r.t. v and b = C(q) e1: exact derivative
@@ -122,10 +119,9 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
         mv[k] = vh[k] * (1.0 / __ldg(&P.sos));
     }
     const double fs = __ldg(&P.force_scalar);
-    const double drag = spline_val(tb.drag, tb, ca, mach) * fs;
-    double gx, gy;
-    spline_grad(tb.drag, tb, ca, mach, gx, gy);
-    gx *= fs; gy *= fs;
+    double drag, gx, gy;
+    spline_val_grad(tb.drag, tb, ca, mach, drag, gx, gy);
+    drag *= fs; gx *= fs; gy *= fs;
     double dv[3], db[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { dv[k] = gx * cav[k] + gy * mv[k]; db[k] = gx * cab[k]; }
@@ -140,9 +136,9 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
         }
     }
     if (fabs(dp) >= 0.95) return;
-    const double lift = spline_val(tb.lift, tb, ca, mach) * fs;
-    spline_grad(tb.lift, tb, ca, mach, gx, gy);
-    gx *= fs; gy *= fs;
+    double lift;
+    spline_val_grad(tb.lift, tb, ca, mach, lift, gx, gy);
+    lift *= fs; gx *= fs; gy *= fs;
     double lv[3], lb[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { lv[k] = gx * cav[k] + gy * mv[k]; lb[k] = gx * cab[k]; }
@@ -216,7 +212,10 @@ __device__ __forceinline__ void rhs_value(const scvx_probinfo& P, const ScvxTabl
     f[13] = __ldg(&P.jBi[2]) * m0 + __ldg(&P.jBi[5]) * m1 + __ldg(&P.jBi[8]) * m2;
 }
 
-__global__ void __launch_bounds__(128, 3) stage_value_kernel(StagedArgs a) {
+#ifndef SCVX_A_MINBLOCKS
+#define SCVX_A_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(StagedArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n_groups * GROUP) return;
     const ScvxBatch& bt = a.bt;
@@ -310,7 +309,7 @@ __global__ void __launch_bounds__(128, 3) stage_value_kernel(StagedArgs a) {
 // column), r rows are a quadrature of the v rows.  Reads m, f_v and dF/dv from the stage records, writes the
 // seven columns d/d(m, r, v) of the block and the partial z = endpoint - D[:, m r v] * inp[m r v].
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) light_columns_kernel(StagedArgs a) {
+__global__ void __launch_bounds__(128, 3) light_columns_kernel(StagedArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.count) return;
     const ScvxBatch& bt = a.bt;
@@ -330,16 +329,32 @@ __global__ void __launch_bounds__(128) light_columns_kernel(StagedArgs a) {
     for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int r = 0; r < 3; ++r) { S[c][r] = (c == r + 1) ? 1.0 : 0.0; Y[c][r] = S[c][r]; A[c][r] = 0.0; Sr[c][r] = 0.0; }
+    // software-pipelined record reads: the 13 values of stage s+1 are in flight while stage s is computed
+    const size_t rstride = (size_t)a.rec_n * GROUP;
+    double nx[13];
+    auto fetch = [&](int s) {
+        const double* rp = rec + (size_t)s * rstride;
+        nx[0] = __ldg(rp);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) nx[1 + r] = __ldg(rp + (15 + r) * GROUP);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) nx[4 + k] = aero ? __ldg(rp + (25 + k) * GROUP) : 0.0;
+    };
+    fetch(0);
+#pragma unroll 1
     for (int s = 0; s < nst; ++s) {
         const int st = s & 3;
-        const double* rp = rec + (size_t)s * ((size_t)a.rec_n * GROUP);
-        const double sm = sigma / rp[0];
+        double cu[13];
+#pragma unroll
+        for (int k = 0; k < 13; ++k) cu[k] = nx[k];
+        if (s + 1 < nst) fetch(s + 1);
+        const double sm = sigma / cu[0];
         double Jvv[3][3], Jvm[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            Jvm[r] = -sm * (rp[(15 + r) * GROUP] + (r == 0 ? g0 : 0.0));
+            Jvm[r] = -sm * (cu[1 + r] + (r == 0 ? g0 : 0.0));
 #pragma unroll
-            for (int c = 0; c < 3; ++c) Jvv[r][c] = aero ? sm * rp[(25 + 3 * r + c) * GROUP] : 0.0;
+            for (int c = 0; c < 3; ++c) Jvv[r][c] = sm * cu[4 + 3 * r + c];
         }
         const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
         const double cy = (st == 2) ? sstep : 0.5 * sstep;
