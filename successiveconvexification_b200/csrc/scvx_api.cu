@@ -114,19 +114,18 @@ int check_ready(scvx_ctx* c, int B) {
 int launch_linearize(scvx_ctx* c, Dev& d, const ScvxBatch& bt, cudaStream_t s) {
     const ScvxTables tb = tables_of(d);
     int k = c->kernel;
-    if (k == SCVX_KERNEL_AUTO) k = SCVX_KERNEL_FUSED;
+    if (k == SCVX_KERNEL_AUTO) k = SCVX_KERNEL_STAGED;
     if (k == SCVX_KERNEL_DUALWARP) {
         CK(scvx_launch_dualwarp(bt, tb, s));
         c->launches += 1;
         return 0;
     }
-    // STAGED / FUSED: the stage-record scratch is shared by everything enqueued on this device, so work on the other
+    // STAGED: the stage-record scratch is shared by everything enqueued on this device, so work on the other
     // pipeline stream must have consumed it before it is overwritten.
     const long total = (long)(bt.n_nodes - 1) * bt.B;
     int chunk = scvx_staged_chunk_intervals(d.sm_count);
     if (total < chunk) chunk = (int)((total + 31) / 32 * 32);
-    const size_t need = (k == SCVX_KERNEL_FUSED) ? scvx_fused_scratch_bytes(bt.npts, chunk, d.sm_count)
-                                                 : scvx_staged_scratch_bytes(bt.npts, chunk);
+    const size_t need = scvx_staged_scratch_bytes(bt.npts, chunk);
     if (need > d.scratch_cap) {
         CK(cudaDeviceSynchronize());
         if (d.scratch) cudaFree(d.scratch);
@@ -141,8 +140,7 @@ int launch_linearize(scvx_ctx* c, Dev& d, const ScvxBatch& bt, cudaStream_t s) {
     }
     d.scratch_user = s;
     int n = 0;
-    if (k == SCVX_KERNEL_FUSED) CK(scvx_launch_fused(bt, tb, c->any_aero, d.scratch, chunk, d.sm_count, s, &n));
-    else CK(scvx_launch_staged(bt, tb, c->any_aero, d.scratch, chunk, d.sm_count, s, &n));
+    CK(scvx_launch_staged(bt, tb, c->any_aero, d.scratch, chunk, d.sm_count, s, &n));
     c->launches += n;
     return 0;
 }
@@ -402,7 +400,7 @@ int scvx_set_stream(scvx_ctx* c, void* stream) {
 
 int scvx_set_kernel(scvx_ctx* c, int which) {
     if (!c) return fail(SCVX_ERR_ARG, "null context");
-    if (which < SCVX_KERNEL_AUTO || which > SCVX_KERNEL_FUSED) return fail(SCVX_ERR_ARG, "unknown kernel id %d", which);
+    if (which < SCVX_KERNEL_AUTO || which > SCVX_KERNEL_STAGED) return fail(SCVX_ERR_ARG, "unknown kernel id %d", which);
     c->kernel = which;
     return 0;
 }

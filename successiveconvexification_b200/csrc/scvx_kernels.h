@@ -15,7 +15,3 @@ int scvx_staged_chunk_intervals(int sm_count);
 cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, void* scratch,
                                int chunk_intervals, int sm_count, cudaStream_t s, int* launches);
 
-// FUSED path (scvx_kernels_fused.cu): value kernel, fused Jacobian-production + TMA-fed tangent kernel, light columns.
-size_t scvx_fused_scratch_bytes(int npts, int chunk_intervals, int sm_count);
-cudaError_t scvx_launch_fused(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, void* scratch,
-                              int chunk_intervals, int sm_count, cudaStream_t s, int* launches);

@@ -421,7 +421,9 @@ size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals) {
     return groups * (size_t)(4 * npts) * REC_MAX * GROUP * sizeof(double);
 }
 
-int scvx_staged_chunk_intervals(int sm_count) { return sm_count * GROUP * 14; }
+// chunk = whole waves of both kernels: the value kernel keeps SCVX_A_MINBLOCKS x 128 threads per SM resident, the
+// tangent kernel 32 intervals per SM; 2 value waves = 16 tangent passes per SM at the default setting.
+int scvx_staged_chunk_intervals(int sm_count) { return sm_count * 128 * SCVX_A_MINBLOCKS * 2; }
 
 cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, void* scratch,
                                int chunk_intervals, int sm_count, cudaStream_t s, int* launches) {
