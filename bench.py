@@ -45,23 +45,55 @@ BYTES_PER_INTERVAL = 8 * (21 + 14 * 23) + 8 * (14 + 4)                          
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML in-process (a sample
+    every ~20 ms); falls back to polling nvidia-smi when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except Exception:
+                return index
+        return index
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = get(self.h)
+        flags = [("Active" if r & m else "Not Active") for m in (0x8, 0x40, 0x20, 0x4)]   # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        self.rows.append([str(sm), str(mx), str(pw)] + flags)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02 if self.nvml is not None else 0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -74,12 +106,13 @@ class ClockSampler:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"]}
         sm = sorted(float(r[0]) for r in self.rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference_run(prob, steps, warmup, traj_per_thread):
@@ -87,7 +120,8 @@ def cpu_reference_run(prob, steps, warmup, traj_per_thread):
     from oracle import oracle
     from successiveconvexification_b200 import workloads
     tb = oracle.OracleTables.from_aero(prob.aero)
-    threads = oracle.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it is allowed to run on
+    threads = max(oracle.max_threads(), len(os.sched_getaffinity(0)))
     n_traj = max(8, traj_per_thread * threads)
     X, U, sigma, P = workloads.monte_carlo_batch(prob, K_NODES, n_traj, SEED)
     times = []
@@ -106,11 +140,11 @@ def cpu_reference_run(prob, steps, warmup, traj_per_thread):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--traj-per-gpu", type=int, default=TRAJ_PER_GPU)
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 dualwarp, 2 staged")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto (= staged), 1 dualwarp, 2 staged")
     ap.add_argument("--mode", type=int, default=0, help="0 LITERAL (parity contract), 1 TEXTBOOK")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -153,6 +187,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -271,7 +307,7 @@ def main():
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         v, threads, sample, _ = cpu_reference_run(prob, steps=1, warmup=1, traj_per_thread=400)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": sample + "; C++ restatement of the reference Julia path (Julia unavailable)"}
