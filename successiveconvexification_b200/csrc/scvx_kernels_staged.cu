@@ -154,6 +154,20 @@ __global__ void __launch_bounds__(128, 3) light_columns_kernel(StagedArgs a) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) nx[4 + k] = aero ? __ldg(rp + (25 + k) * GROUP) : 0.0;
     };
+    // ... and the lines of stage s+PF are pulled into L2 by prefetch instructions (no register cost): the records
+    // were written by the value kernel a whole chunk ago and are in DRAM by now
+    constexpr int PF = 6;
+    auto prefetch_l2 = [&](int s) {
+        const double* rp = rec + (size_t)s * rstride;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+#pragma unroll
+        for (int r = 0; r < 3; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (15 + r) * GROUP));
+        if (aero) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (25 + k) * GROUP));
+        }
+    };
+    for (int s = 0; s < PF && s < nst; ++s) prefetch_l2(s);
     fetch(0);
 #pragma unroll 1
     for (int s = 0; s < nst; ++s) {
@@ -161,6 +175,7 @@ __global__ void __launch_bounds__(128, 3) light_columns_kernel(StagedArgs a) {
         double cu[13];
 #pragma unroll
         for (int k = 0; k < 13; ++k) cu[k] = nx[k];
+        if (s + PF < nst) prefetch_l2(s + PF);
         if (s + 1 < nst) fetch(s + 1);
         const double sm = sigma / cu[0];
         double Jvv[3][3], Jvm[3];
@@ -421,9 +436,10 @@ size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals) {
     return groups * (size_t)(4 * npts) * REC_MAX * GROUP * sizeof(double);
 }
 
-// chunk = whole waves of both kernels: the value kernel keeps SCVX_A_MINBLOCKS x 128 threads per SM resident, the
-// tangent kernel 32 intervals per SM; 2 value waves = 16 tangent passes per SM at the default setting.
-int scvx_staged_chunk_intervals(int sm_count) { return sm_count * 128 * SCVX_A_MINBLOCKS * 2; }
+// chunk = whole waves of all three kernels: the value kernel keeps 2 x 128 threads per SM resident (255 registers),
+// the light-column kernel 3 x 128 (168 registers), the tangent kernel 32 intervals per pass: 768 intervals per SM =
+// 3 / 2 waves / 24 passes.
+int scvx_staged_chunk_intervals(int sm_count) { return sm_count * 768; }
 
 cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, void* scratch,
                                int chunk_intervals, int sm_count, cudaStream_t s, int* launches) {
