@@ -212,3 +212,73 @@ def test_edge_cases_and_errors(dyn, cache_aero, prob_aero):
 def test_fp64_peak_microbenchmark(cache_aero):
     tf = cache_aero.sim_prob.measure_fp64_peak()
     assert 5.0 < tf < 80.0
+
+
+def _device_properties(blocks, dX, dU, dS):
+    """Size-independent properties evaluated on the device (torch): affine closure z = endpoint - D*inp, exact
+    position columns, finiteness.  blocks (B, ni, 23, 14) device tensor."""
+    import torch
+    B, ni = blocks.shape[0], blocks.shape[1]
+    D = blocks[:, :, 1:22, :]
+    inp = torch.cat([dX[:, :-1], dU[:, :-1], dU[:, 1:], dS[:, None, None].expand(B, ni, 1)], dim=-1)
+    z = blocks[:, :, 0, :] - torch.einsum("bicr,bic->bir", D, inp)
+    scale = float(D.abs().max())
+    zerr = float((z - blocks[:, :, 22, :]).abs().max())
+    expect = torch.zeros((3, 14), dtype=torch.float64, device=blocks.device)
+    expect[[0, 1, 2], [1, 2, 3]] = 1.0
+    pos_ok = bool((D[:, :, 1:4, :] == expect).all())
+    return zerr, scale, pos_ok, bool(torch.isfinite(blocks).all())
+
+
+def test_c3_full_size_properties(dyn, cache_aero, prob_aero, oracle_tables):
+    """BASELINE config 3 at full size: aero tables, K=100, 4096 perturbed trajectories (409 600 intervals), TEXTBOOK
+    with the survey's sigma ~ U(1,15): properties on the device + a random sample against the oracle."""
+    import torch
+    from successiveconvexification_b200 import workloads
+    ctx = cache_aero.sim_prob
+    ctx.set_kernel(0)
+    B, K = 4096, 100
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, K, B, 1001)
+    dX, dU, dS = (torch.from_numpy(a).cuda() for a in (X, U, sigma))
+    out = torch.empty((B, K, 23, 14), dtype=torch.float64, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.linearize_ptr(dX.data_ptr(), dU.data_ptr(), dS.data_ptr(), 1 / (K + 1), 10, 1, K + 1, B, out.data_ptr())
+    torch.cuda.synchronize()
+    zerr, scale, pos_ok, finite = _device_properties(out, dX, dU, dS)
+    assert finite and pos_ok and zerr <= 1e-12 * scale
+    pick = np.random.default_rng(9).choice(B, 8, replace=False)
+    ref, _, _, _ = _oracle().linearize_batch(P, oracle_tables, X[pick], U[pick], sigma[pick], 1 / (K + 1), 10, 1,
+                                            False, False)
+    assert_parity(out[torch.from_numpy(pick).cuda()].cpu().numpy(), ref)
+
+
+def test_c4_full_size_properties(dyn, prob_aero, oracle_tables):
+    """BASELINE config 4 at full size: K=400, 16384 trajectories (6.55 M intervals, 16.9 GB of blocks, device
+    resident), per-trajectory mass / alpha / thrust-bound sweep.  Properties on the device, sampled oracle parity."""
+    import torch
+    from successiveconvexification_b200 import workloads
+    B, K = 16384, 400
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, K, B, 1002, sweep=True)
+    cache = dyn.make_cache(prob_aero)
+    ptr, n, keep = workloads.as_c_params(P)
+    ctx = cache.sim_prob
+    ctx.set_params_raw(ptr, n)
+    dX, dU, dS = (torch.from_numpy(a).cuda() for a in (X, U, sigma))
+    out = torch.empty((B, K, 23, 14), dtype=torch.float64, device="cuda")
+    tlb = torch.empty((B, K + 1, 4), dtype=torch.float64, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.linearize_ptr(dX.data_ptr(), dU.data_ptr(), dS.data_ptr(), 1 / (K + 1), 10, 1, K + 1, B, out.data_ptr(), 0,
+                      tlb.data_ptr())
+    torch.cuda.synchronize()
+    # properties in slabs of 2048 trajectories to bound temporary memory
+    for b0 in range(0, B, 2048):
+        sl = slice(b0, b0 + 2048)
+        zerr, scale, pos_ok, finite = _device_properties(out[sl], dX[sl], dU[sl], dS[sl])
+        assert finite and pos_ok and zerr <= 1e-12 * scale
+    nu = torch.linalg.norm(dU, dim=-1)
+    tmin = torch.from_numpy(np.ascontiguousarray(P["Tmin"])).cuda()
+    assert float((tlb[..., 3] - (tmin[:, None] - nu)).abs().max()) <= 1e-15
+    pick = np.random.default_rng(10).choice(B, 2, replace=False)
+    ref, _, _, _ = _oracle().linearize_batch(P[pick], oracle_tables, X[pick], U[pick], sigma[pick], 1 / (K + 1), 10, 1,
+                                            False, False)
+    assert_parity(out[torch.from_numpy(pick).cuda()].cpu().numpy(), ref)
