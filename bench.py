@@ -179,6 +179,11 @@ def main():
         print(json.dumps(line), flush=True)
         return 0
 
+    # keep stdout for the single JSON line: anything libraries print meanwhile (e.g. the NCCL version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from successiveconvexification_b200 import dynamics, sharding
@@ -317,7 +322,10 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "results_finite": ok, "kernel": args.kernel}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
     return 0
