@@ -82,22 +82,24 @@ __device__ __forceinline__ void spline_val_grad(const double* __restrict__ coef,
 __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const ScvxTables& tb, const double b[3],
                                                const double v[3], double F[3], double Fv[3][3], double Fb[3][3]) {
     const double vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-    const double nv = sqrt(vv), inv = 1.0 / nv;
+    const double inv = rsqrt(vv), nv = vv * inv;              // one long-latency op instead of sqrt + divide
     const double vh[3] = { v[0] * inv, v[1] * inv, v[2] * inv };
     const double bvdot = b[0] * v[0] + b[1] * v[1] + b[2] * v[2];
     const double dp = bvdot * inv;
-    const double nb = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]), inb = 1.0 / nb;
+    const double bb = b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+    const double inb = rsqrt(bb);
     const double car = dp * inb;
     double ca = car, mc = 1.0;
     if (car > 1.0) { ca = 1.0; mc = 0.0; } else if (car < -1.0) { ca = -1.0; mc = 0.0; }
-    const double mach = nv * (1.0 / __ldg(&P.sos));
+    const double isos = 1.0 / __ldg(&P.sos);
+    const double mach = nv * isos;
     // d(ca)/dv, d(ca)/db ; d(mach)/dv
     double cav[3], cab[3], mv[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         cav[k] = mc * (b[k] - dp * vh[k]) * inv * inb;
         cab[k] = mc * (vh[k] - car * b[k] * inb) * inb;
-        mv[k] = vh[k] * (1.0 / __ldg(&P.sos));
+        mv[k] = vh[k] * isos;
     }
     const double fs = __ldg(&P.force_scalar);
     double drag, gx, gy;
@@ -125,7 +127,7 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
     for (int k = 0; k < 3; ++k) { lv[k] = gx * cav[k] + gy * mv[k]; lb[k] = gx * cab[k]; }
     // l = (-(v x b)) x v = v (v.b) - b (v.v)
     const double l[3] = { v[0] * bvdot - b[0] * vv, v[1] * bvdot - b[1] * vv, v[2] * bvdot - b[2] * vv };
-    const double nl = sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]), inl = 1.0 / nl;
+    const double inl = rsqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
     const double lh[3] = { l[0] * inl, l[1] * inl, l[2] * inl };
     // dl/dv = (v.b) I + v b^T - 2 b v^T ;  dl/db = v v^T - (v.v) I
     double Lv[3][3], Lb[3][3];
