@@ -104,6 +104,14 @@ int scvx_linearize_batch(scvx_ctx* ctx, const double* X, const double* U, const 
 int scvx_predict_batch(scvx_ctx* ctx, const double* X, const double* U, const double* sigma,
                        double base_dt, int npts, int mode, int n_nodes, int B, double* out_endpoints);
 
+/* Fused cost / defect evaluation of the SCvx ratio test (rocketland.jl:289-290): per trajectory
+ *   defect_b = sqrt( sum_k || x_{k+1} - endpoint_k ||^2 )   (= Julia's norm over the K defect vectors, = ||lin_err||_F)
+ *   cost_b   = -X[0, n_nodes-1, b] + wNu * defect_b          (J_k; mass of the last node enters with weight -1)
+ * from the lin_err array produced by scvx_linearize_batch at the same inputs, so the accept/reject test needs one
+ * tiny transfer.  lin_err 14 x (n_nodes-1) x B, X 14 x n_nodes x B; out_defect B (required), out_cost B (may be NULL). */
+int scvx_defect_cost_batch(scvx_ctx* ctx, const double* X, const double* lin_err, int n_nodes, int B, double wNu,
+                           double* out_defect, double* out_cost);
+
 /* Stream used for device-pointer calls on the first device (a cudaStream_t; NULL = library stream). */
 int scvx_set_stream(scvx_ctx* ctx, void* cuda_stream);
 /* Kernel selection (SCVX_KERNEL_*). */

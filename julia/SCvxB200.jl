@@ -124,6 +124,19 @@ function predict_batch(ctx::Context, X::Array{Float64,3}, U::Array{Float64,3}, s
     return out
 end
 
+# Fused cost / defect evaluation of the ratio test (reference rocketland.jl:289-290): per trajectory
+# defect = norm(x_{k+1} - endpoint_k for k) and J = -x[1,K+1] + wNu * defect, from linearize_batch's lin_err.
+function defect_cost_batch(ctx::Context, X::Array{Float64,3}, lin_err::Array{Float64,3}, wNu::Float64)
+    n_nodes, B = size(X, 2), size(X, 3)
+    defect = Vector{Float64}(undef, B); cost = Vector{Float64}(undef, B)
+    GC.@preserve X lin_err defect cost begin
+        check(ccall((:scvx_defect_cost_batch, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}),
+                    ctx.handle, X, lin_err, n_nodes, B, wNu, defect, cost))
+    end
+    return defect, cost
+end
+
 # IntegratorCache(prob, info) replacement (reference dynamics.jl:258-260): context + parameters + tables.
 # `aero_samples = (drag, lift, torque, aoa_range, mach_range)` are the matrices / ranges of aerodynamics.jl:17-21.
 function make_cache(prob::DescentProblem, info::ProbInfo; device_ids::Vector{Int}=[0], aero_samples=nothing)

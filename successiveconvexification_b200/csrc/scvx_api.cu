@@ -391,6 +391,39 @@ int scvx_predict_batch(scvx_ctx* c, const double* X, const double* U, const doub
     } catch (...) { return fail(SCVX_ERR_STATE, "unexpected C++ exception"); }
 }
 
+int scvx_defect_cost_batch(scvx_ctx* c, const double* X, const double* lin_err, int n_nodes, int B, double wNu,
+                           double* out_defect, double* out_cost) {
+    if (!c) return fail(SCVX_ERR_ARG, "null context");
+    if (!X || !lin_err || !out_defect) return fail(SCVX_ERR_ARG, "X, lin_err and out_defect must be non-null");
+    if (n_nodes < 2) return fail(SCVX_ERR_ARG, "n_nodes=%d: at least two nodes are required", n_nodes);
+    if (B < 0) return fail(SCVX_ERR_ARG, "B=%d is negative", B);
+    if (B == 0) return 0;
+    const bool dev = is_device_ptr(X);
+    if (dev != is_device_ptr(lin_err) || dev != is_device_ptr(out_defect) || (out_cost && dev != is_device_ptr(out_cost)))
+        return fail(SCVX_ERR_ARG, "all array arguments must be either host or device pointers, not a mix");
+    Dev& d = c->devs[0];
+    CK(cudaSetDevice(d.id));
+    if (dev) {
+        cudaStream_t s = c->have_user_stream ? c->user_stream : d.slot[0].stream;
+        CK(scvx_launch_defect_cost(X, lin_err, n_nodes, B, wNu, out_defect, out_cost, s));
+        c->launches += 1;
+        return 0;
+    }
+    // host pointers: small arrays, one staging round trip on the first device
+    Slot& sl = d.slot[0];
+    CK(cudaStreamSynchronize(sl.stream));
+    const size_t nX = (size_t)B * n_nodes * 14, nE = (size_t)B * (n_nodes - 1) * 14;
+    if (grow(&sl.dX, &sl.capX, nX) || grow(&sl.dErr, &sl.capErr, nE) || grow(&sl.dS, &sl.capS, (size_t)2 * B)) return SCVX_ERR_NOMEM;
+    CK(cudaMemcpyAsync(sl.dX, X, nX * 8, cudaMemcpyHostToDevice, sl.stream));
+    CK(cudaMemcpyAsync(sl.dErr, lin_err, nE * 8, cudaMemcpyHostToDevice, sl.stream));
+    CK(scvx_launch_defect_cost(sl.dX, sl.dErr, n_nodes, B, wNu, sl.dS, out_cost ? sl.dS + B : nullptr, sl.stream));
+    c->launches += 1;
+    CK(cudaMemcpyAsync(out_defect, sl.dS, (size_t)B * 8, cudaMemcpyDeviceToHost, sl.stream));
+    if (out_cost) CK(cudaMemcpyAsync(out_cost, sl.dS + B, (size_t)B * 8, cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaStreamSynchronize(sl.stream));
+    return 0;
+}
+
 int scvx_set_stream(scvx_ctx* c, void* stream) {
     if (!c) return fail(SCVX_ERR_ARG, "null context");
     c->user_stream = (cudaStream_t)stream;

@@ -159,6 +159,28 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused cost / defect evaluation (rocketland.jl:289-290): one warp per trajectory reduces its K defect vectors.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) defect_cost_kernel(const double* __restrict__ X, const double* __restrict__ lin_err,
+                                                          int n_nodes, int B, double wNu, double* __restrict__ out_defect,
+                                                          double* __restrict__ out_cost) {
+    const int b = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const int n = (n_nodes - 1) * 14;
+    const double* e = lin_err + (size_t)b * n;
+    double acc = 0.0;
+    for (int k = lane; k < n; k += 32) { const double v = e[k]; acc = fma(v, v, acc); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        const double d = sqrt(acc);
+        out_defect[b] = d;
+        if (out_cost) out_cost[b] = fma(wNu, d, -X[((size_t)b * n_nodes + (n_nodes - 1)) * 14]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
 cudaError_t scvx_launch_dualwarp(const ScvxBatch& bt, const ScvxTables& tb, cudaStream_t s) {
@@ -180,6 +202,14 @@ cudaError_t scvx_launch_prefilter(const double* d_samples, int n1, int n2, doubl
                                   const double* d_cp, cudaStream_t s) {
     prefilter_axis0_kernel<<<(n2 + 63) / 64, 64, 0, s>>>(d_samples, n1, n2, d_tmp, d_cp);
     prefilter_axis1_kernel<<<(n1 + 2 + 63) / 64, 64, 0, s>>>(d_tmp, n1, n2, d_coef, d_cp);
+    return cudaGetLastError();
+}
+
+cudaError_t scvx_launch_defect_cost(const double* X, const double* lin_err, int n_nodes, int B, double wNu,
+                                    double* out_defect, double* out_cost, cudaStream_t s) {
+    if (B <= 0) return cudaSuccess;
+    const long threads = (long)B * 32;
+    defect_cost_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(X, lin_err, n_nodes, B, wNu, out_defect, out_cost);
     return cudaGetLastError();
 }
 

@@ -207,6 +207,11 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n }" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive from one elected lane WITHOUT a divergent branch (predicated instruction: no BSSY/BSYNC reconvergence)
+__device__ __forceinline__ void mbar_arrive_lane0(uint64_t* bar, int lane) {
+    asm volatile("{\n .reg .pred p;\n .reg .b64 st;\n setp.eq.s32 p, %1, 0;\n @p mbarrier.arrive.shared::cta.b64 st, [%0];\n }"
+                 ::"r"(smem_u32(bar)), "r"(lane) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n }" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -443,7 +448,7 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
         kB[2] = fma(j67.x, FB.Y[8], fma(j67.y, FB.Y[9], fma(j8, FB.Y[10], alB * g2)));
         // all reads of the ring slot are done: hand it back
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar);
+        mbar_arrive_lane0(empty_bar, lane);
 #pragma unroll
         for (int r = 0; r < 3; ++r) { upd(FA, 8 + r, kA[r]); upd(FB, 8 + r, kB[r]); }
     }

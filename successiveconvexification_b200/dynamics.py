@@ -113,6 +113,10 @@ class DeviceContext:
         _lib.check(self._lib.scvx_linearize_batch(self._h, X, U, sigma, base_dt, npts, mode, n_nodes, B,
                                                   out_blocks, out_lin_err or None, out_tlb or None))
 
+    def defect_cost_ptr(self, X, lin_err, n_nodes, B, wNu, out_defect, out_cost=0):
+        _lib.check(self._lib.scvx_defect_cost_batch(self._h, X, lin_err, n_nodes, B, float(wNu), out_defect,
+                                                    out_cost or None))
+
     def predict_ptr(self, X, U, sigma, base_dt, npts, mode, n_nodes, B, out):
         _lib.check(self._lib.scvx_predict_batch(self._h, X, U, sigma, base_dt, npts, mode, n_nodes, B, out))
 
@@ -181,6 +185,21 @@ def predict_batch(cache: IntegratorCache, X, U, sigma, base_dt: float, npts: int
     ctx.predict_ptr(X.ctypes.data, U.ctypes.data, sigma.ctypes.data, float(base_dt), int(npts), int(mode),
                     n_nodes, B, out.ctypes.data)
     return out
+
+
+def defect_cost(cache: IntegratorCache, X, lin_err, wNu: float):
+    """Fused cost / defect evaluation of the SCvx ratio test (rocketland.jl:289-290): per trajectory
+    `defect = norm(x_{k+1} - predict_state(x_k, ...) for k)` and `J = -x[1, K+1] + wNu * defect`, from the `lin_err`
+    array of `linearize_batch` at the same inputs.  -> (defect (B,), cost (B,))."""
+    ctx = _ctx(cache)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    lin_err = np.ascontiguousarray(lin_err, dtype=np.float64)
+    B, n_nodes, _ = X.shape
+    if lin_err.shape != (B, n_nodes - 1, 14):
+        raise ValueError("expected lin_err (B, n_nodes-1, 14)")
+    defect, cost = np.empty(B), np.empty(B)
+    ctx.defect_cost_ptr(X.ctypes.data, lin_err.ctypes.data, n_nodes, B, wNu, defect.ctypes.data, cost.ctypes.data)
+    return defect, cost
 
 
 def blocks_to_linres(blocks_one_traj: np.ndarray):

@@ -188,6 +188,29 @@ def test_device_pointer_path_torch(dyn, cache_aero, prob_aero, oracle_tables, ke
     assert np.abs(tlb.cpu().numpy() - rtlb).max() <= 1e-15
 
 
+def test_fused_defect_cost(dyn, cache_aero, prob_aero):
+    """J_k of the ratio test (rocketland.jl:289-290) from the same launch's lin_err."""
+    import torch
+    from successiveconvexification_b200 import workloads
+    cache_aero.sim_prob.set_kernel(0)
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, 50, 300, 77, sigma_range=(0.8, 1.5))
+    blocks, err, _ = dyn.linearize_batch(cache_aero, X, U, sigma, 1 / 51)
+    defect, cost = dyn.defect_cost(cache_aero, X, err, prob_aero.wNu)
+    # the reference's expression: norm over k of (x_{k+1} - predict_state(x_k, ...)), then -x[1,K+1] + wNu * norm
+    pred = dyn.predict_batch(cache_aero, X, U, sigma, 1 / 51)
+    ref_d = np.sqrt(((X[:, 1:] - pred) ** 2).sum(axis=(1, 2)))
+    assert defect == pytest.approx(ref_d, rel=1e-12)
+    assert cost == pytest.approx(-X[:, -1, 0] + prob_aero.wNu * ref_d, rel=1e-12)
+    # device-pointer form
+    dX, dE = torch.from_numpy(X).cuda(), torch.from_numpy(err).cuda()
+    dD = torch.empty(300, dtype=torch.float64, device="cuda")
+    ctx = cache_aero.sim_prob
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.defect_cost_ptr(dX.data_ptr(), dE.data_ptr(), 51, 300, prob_aero.wNu, dD.data_ptr())
+    torch.cuda.synchronize()
+    assert dD.cpu().numpy() == pytest.approx(ref_d, rel=1e-12)
+
+
 def test_edge_cases_and_errors(dyn, cache_aero, prob_aero):
     from successiveconvexification_b200 import _lib, workloads
     X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, 1, 3, 8, sigma_range=(0.8, 1.5))     # n_nodes = 2
