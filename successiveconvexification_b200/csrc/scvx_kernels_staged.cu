@@ -429,6 +429,191 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
 }
 
 
+
+// ------------------------------------------------------------------------------------------------
+// Kernel B, step-synchronised variant (default).  Same mapping as tangent_kernel (8 lanes per interval, two full
+// columns per lane, rotating lane = interval producer, TMA-fed stage records, mbarrier-guarded ring), but production
+// and hand-over happen once per rk4 STEP instead of once per stage:
+//   * the ring holds two steps (2 x 4 stage slabs); at the start of consumer step m the four warps of the other half
+//     each produce one stage of step m+1 (one whole step of slack);
+//   * consumers wait ONE "full" barrier per step and release the four slabs with ONE "empty" arrive per step;
+//   * at a step boundary the stage tangent equals S and the accumulator is zero, so a producing warp parks 28 instead
+//     of 72 doubles around the producer call;
+//   * four record buffers (one per stage of a step); the warp that has just read buffer k re-arms its TMA for the
+//     next step.
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) StepSmem {
+    double ring[8][GROUP][NJ];               // [half * 4 + stage][interval][entry]
+    double recbuf[4][REC_MAX * GROUP];       // stage records of the step being produced (TMA destination)
+    uint64_t full_step[2];
+    uint64_t empty_step[2];
+    uint64_t recfull[2][4];                  // [half][stage]: one waiting warp per barrier (it observes every phase)
+};
+
+__global__ void __launch_bounds__(256, 1) tangent_step_kernel(StagedArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StepSmem& sm = *reinterpret_cast<StepSmem*>(smem_raw);
+    const ScvxBatch& bt = a.bt;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int l8 = lane & 7, sub = lane >> 3;
+    const int ni = bt.n_nodes - 1;
+    const int npts = bt.npts, nst = 4 * npts;
+    const double h = bt.dt / (double)npts;
+    const double pcs = 1.0 / (double)npts;
+    const double sstep = (bt.mode == SCVX_MODE_LITERAL) ? 1.0 : h;
+    const double h6 = h * (1.0 / 6.0);
+
+    if (tid == 0) {
+        for (int r = 0; r < 2; ++r) { mbar_init(&sm.full_step[r], 4 * 32); mbar_init(&sm.empty_step[r], NWARP); }
+        for (int k = 0; k < 8; ++k) mbar_init(&sm.recfull[k >> 2][k & 3], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int my_groups = (a.n_groups > (int)blockIdx.x) ? (a.n_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total_steps = my_groups * npts;          // global step counter n = pass * npts + local step
+
+    int colA = -1, colB = -1, gcol = 3;
+    if (l8 < 3) { colA = 14 + l8; colB = 17 + l8; gcol = l8; }
+    else if (l8 == 3) colA = 20;
+    else if (l8 == 4) { colA = 11; colB = 12; }
+    else if (l8 == 5) { colA = 13; colB = 7; }
+    else if (l8 == 6) { colA = 8; colB = 9; }
+    else colA = 10;
+
+    const int kq = warp & 3;                            // stage (within a step) this warp produces
+    auto issue_record = [&](int n) {                    // one lane: TMA the record of (global step n, stage kq)
+        const int it = n / npts, ls = n - it * npts;
+        const int g = blockIdx.x + it * gridDim.x;
+        const uint32_t bytes = (uint32_t)a.rec_n * GROUP * 8;
+        const double* src = a.rec + ((size_t)g * nst + 4 * ls + kq) * ((size_t)a.rec_n * GROUP);
+        fence_proxy_async();
+        mbar_expect_tx(&sm.recfull[n & 1][kq], bytes);
+        bulk_g2s(sm.recbuf[kq], src, bytes, &sm.recfull[n & 1][kq]);
+    };
+    auto produce = [&](int n) {                         // whole warp (lane = interval): stage kq of global step n
+        const int it = n / npts;
+        const int g = blockIdx.x + it * gridDim.x;
+        int t = g * GROUP + lane; if (t >= a.count) t = a.count - 1;
+        const int b = (a.first + t) / ni;
+        const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
+        const double sigma = __ldg(bt.sigma + b);
+        const int half = n & 1, use = n >> 1;
+        mbar_wait(&sm.recfull[half][kq], (uint32_t)(use & 1));      // this warp is the only waiter of recfull[half][kq]
+        if (use > 0) mbar_wait(&sm.empty_step[half], (uint32_t)((use - 1) & 1));
+        produce_stage(P, a.rec_n == REC_AERO, sigma, sm.recbuf[kq] + lane, &sm.ring[half * 4 + kq][lane][0]);
+        mbar_arrive(&sm.full_step[half]);
+        __syncwarp();                                    // every lane has finished reading recbuf[kq]
+        if (lane == 0 && n + 1 < total_steps) issue_record(n + 1);
+    };
+
+    // prologue: warps 0..3 fetch and produce step 0 (and re-arm the record buffers for step 1)
+    if (warp < 4 && total_steps > 0) {
+        if (lane == 0) issue_record(0);
+        produce(0);
+    }
+
+    FullCol FA, FB;
+    double park[28];
+    volatile double* vp = park;
+    int n = 0;                                           // global consumer step
+    for (int it = 0; it < my_groups; ++it) {
+        const int g = blockIdx.x + it * gridDim.x;
+#pragma unroll
+        for (int r = 0; r < 11; ++r) {
+            FA.S[r] = (r >= 4 && colA == r + 3) ? 1.0 : 0.0;       // local rows: 0 m, 1..3 v, 4..7 q, 8..10 w
+            FB.S[r] = (r >= 4 && colB == r + 3) ? 1.0 : 0.0;
+            FA.A[r] = 0.0; FB.A[r] = 0.0;
+            FA.Y[r] = FA.S[r]; FB.Y[r] = FB.S[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) FA.Sr[r] = FB.Sr[r] = 0.0;
+
+        double pca = 0.0;
+#pragma unroll 1
+        for (int ls = 0; ls < npts; ++ls, ++n) {
+            // ---- producer duty: the warps of the other half produce step n+1 (Y == S and A == 0 here, so only
+            //      S and the r-row sums have to survive the call)
+            if ((warp >> 2) == ((n + 1) & 1) && n + 1 < total_steps) {
+#pragma unroll
+                for (int r = 0; r < 11; ++r) { vp[r] = FA.S[r]; vp[11 + r] = FB.S[r]; }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { vp[22 + r] = FA.Sr[r]; vp[25 + r] = FB.Sr[r]; }
+                produce(n + 1);
+#pragma unroll
+                for (int r = 0; r < 11; ++r) {
+                    FA.S[r] = vp[r]; FB.S[r] = vp[11 + r];
+                    FA.Y[r] = FA.S[r]; FB.Y[r] = FB.S[r]; FA.A[r] = 0.0; FB.A[r] = 0.0;
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { FA.Sr[r] = vp[22 + r]; FB.Sr[r] = vp[25 + r]; }
+            }
+            // ---- consume the four stages of step n
+            const int half = n & 1;
+            mbar_wait(&sm.full_step[half], (uint32_t)((n >> 1) & 1));
+            const double* J0 = &sm.ring[half * 4][warp * 4 + sub][0];
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k) {
+                const double pc = (k == 0) ? pca : pca + 0.5 * pcs;
+                consume_stage8<false>(FA, FB, J0 + k * (GROUP * NJ), gcol, l8, pc, k == 0 ? 1.0 : 2.0,
+                                      k == 2 ? sstep : 0.5 * sstep, h6, nullptr, lane);
+            }
+            consume_stage8<true>(FA, FB, J0 + 3 * (GROUP * NJ), gcol, l8, pca + pcs, 1.0, 0.0, h6, nullptr, lane);
+            __syncwarp();
+            mbar_arrive_lane0(&sm.empty_step[half], lane);           // the four slabs of this step are free again
+            pca += pcs;
+        }
+
+        // ---- epilogue: write D columns and z for interval (g*32 + warp*4 + sub)
+        const int t = g * GROUP + warp * 4 + sub;
+        const bool live = t < a.count;
+        const int wi = a.first + (live ? t : a.count - 1);
+        const int b = wi / ni, i = wi - b * ni;
+        double* blk = bt.out_blocks + (size_t)wi * SCVX_BLOCK_DOUBLES;
+        const double* xin = bt.X + ((size_t)b * bt.n_nodes + i) * 14;
+        const double* uin = bt.U + ((size_t)b * bt.n_nodes + i) * 3;
+        auto inp_of = [&](int c) -> double {
+            if (c < 0) return 0.0;
+            if (c < 14) return xin[c];
+            if (c < 20) return uin[c - 14];
+            return bt.sigma[b];
+        };
+        double zp[14];
+#pragma unroll
+        for (int r = 0; r < 14; ++r) zp[r] = 0.0;
+        auto emit_full = [&](const FullCol& F, int c) {
+            if (c < 0) return;
+            const double col[14] = { F.S[0], F.Sr[0], F.Sr[1], F.Sr[2], F.S[1], F.S[2], F.S[3], F.S[4], F.S[5], F.S[6], F.S[7],
+                                     F.S[8], F.S[9], F.S[10] };
+            const double xc = inp_of(c);
+            double* o = blk + 14 * (1 + c);
+#pragma unroll
+            for (int r = 0; r < 14; r += 2) {
+                if (live) *reinterpret_cast<double2*>(o + r) = make_double2(col[r], col[r + 1]);
+                zp[r] = fma(col[r], xc, zp[r]); zp[r + 1] = fma(col[r + 1], xc, zp[r + 1]);
+            }
+        };
+        emit_full(FA, colA);
+        emit_full(FB, colB);
+#pragma unroll
+        for (int r = 0; r < 14; ++r) {
+            double v = zp[r];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            zp[r] = v;
+        }
+        if (live && l8 == 7) {
+            double* o = blk + 14 * 22;
+#pragma unroll
+            for (int r = 0; r < 14; r += 2) {
+                const double2 e = *reinterpret_cast<const double2*>(o + r);        // partial z (light_columns_kernel)
+                *reinterpret_cast<double2*>(o + r) = make_double2(e.x - zp[r], e.y - zp[r + 1]);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals) {
@@ -442,11 +627,13 @@ size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals) {
 int scvx_staged_chunk_intervals(int sm_count) { return sm_count * 768; }
 
 cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, void* scratch,
-                               int chunk_intervals, int sm_count, cudaStream_t s, int* launches) {
+                               int chunk_intervals, int sm_count, cudaStream_t s, int* launches, int variant) {
     const long total = (long)(bt.n_nodes - 1) * bt.B;
-    const size_t smem = sizeof(TangentSmem);
+    const size_t smem = (variant == 1) ? sizeof(StepSmem) : sizeof(TangentSmem);
     {
-        cudaError_t e = cudaFuncSetAttribute(tangent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = (variant == 1)
+            ? cudaFuncSetAttribute(tangent_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+            : cudaFuncSetAttribute(tangent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     for (long first = 0; first < total; first += chunk_intervals) {
@@ -459,7 +646,8 @@ cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool a
         stage_value_kernel<<<(threads + 127) / 128, 128, 0, s>>>(a);
         light_columns_kernel<<<(a.count + 127) / 128, 128, 0, s>>>(a);
         const int grid = a.n_groups < sm_count ? a.n_groups : sm_count;
-        tangent_kernel<<<grid, 256, smem, s>>>(a);
+        if (variant == 1) tangent_step_kernel<<<grid, 256, smem, s>>>(a);
+        else tangent_kernel<<<grid, 256, smem, s>>>(a);
         if (launches) *launches += 3;
     }
     return cudaGetLastError();

@@ -446,9 +446,12 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
         kB[0] = fma(j01.x, FB.Y[8], fma(j01.y, FB.Y[9], fma(j23.x, FB.Y[10], alB * g0)));
         kB[1] = fma(j23.y, FB.Y[8], fma(j45.x, FB.Y[9], fma(j45.y, FB.Y[10], alB * g1)));
         kB[2] = fma(j67.x, FB.Y[8], fma(j67.y, FB.Y[9], fma(j8, FB.Y[10], alB * g2)));
-        // all reads of the ring slot are done: hand it back
-        __syncwarp();
-        mbar_arrive_lane0(empty_bar, lane);
+        // all reads of the ring slot are done: hand it back (per-stage hand-over only; the step-synchronised kernel
+        // passes a null barrier and releases a whole step at once)
+        if (empty_bar != nullptr) {
+            __syncwarp();
+            mbar_arrive_lane0(empty_bar, lane);
+        }
 #pragma unroll
         for (int r = 0; r < 3; ++r) { upd(FA, 8 + r, kA[r]); upd(FB, 8 + r, kB[r]); }
     }
