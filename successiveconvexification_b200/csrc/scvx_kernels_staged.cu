@@ -500,8 +500,8 @@ __global__ void __launch_bounds__(256, 1) tangent_step_kernel(StagedArgs a) {
         const double sigma = __ldg(bt.sigma + b);
         const int half = n & 1, use = n >> 1;
         mbar_wait(&sm.recfull[half][kq], (uint32_t)(use & 1));      // this warp is the only waiter of recfull[half][kq]
-        if (use > 0) mbar_wait(&sm.empty_step[half], (uint32_t)((use - 1) & 1));
-        produce_stage(P, a.rec_n == REC_AERO, sigma, sm.recbuf[kq] + lane, &sm.ring[half * 4 + kq][lane][0]);
+        produce_stage(P, a.rec_n == REC_AERO, sigma, sm.recbuf[kq] + lane, &sm.ring[half * 4 + kq][lane][0],
+                      use > 0 ? &sm.empty_step[half] : nullptr, (uint32_t)((use - 1) & 1));
         mbar_arrive(&sm.full_step[half]);
         __syncwarp();                                    // every lane has finished reading recbuf[kq]
         if (lane == 0 && n + 1 < total_steps) issue_record(n + 1);

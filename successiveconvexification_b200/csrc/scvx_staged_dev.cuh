@@ -239,9 +239,13 @@ __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpre
 
 // rec: this lane's stage record (stride GROUP doubles between entries, in shared memory);
 // out: this lane's NJ-double Jacobian record in the ring.
+// `slot_free` (may be null): mbarrier that must have completed phase `slot_parity` before `out` may be written.  The
+// whole record is formed in registers first and the wait sits right before the stores, so a producer that arrives
+// early overlaps its arithmetic with the consumers still reading the slot.
 template <class GetAero>
 __device__ __forceinline__ void produce_core(const scvx_probinfo& P, bool aero_rec, double sigma,
-                                             const double* __restrict__ rec, double* __restrict__ out, GetAero get_aero) {
+                                             const double* __restrict__ rec, double* __restrict__ out, GetAero get_aero,
+                                             uint64_t* slot_free = nullptr, uint32_t slot_parity = 0) {
     // parameters first, as one batch of independent read-only loads (one latency, not one per use)
     const double Pa = __ldg(&P.a), Pg0 = __ldg(&P.g0);
     double jB[9], jBi[9], rT[3];
@@ -261,6 +265,8 @@ __device__ __forceinline__ void produce_core(const scvx_probinfo& P, bool aero_r
     const double sm = sigma / m;
 
     // ---- rotational block: Jww = -sigma * jBi * ([w]x jB - [jB w]x)
+    double Jw[9];
+    const double hs = 0.5 * sigma;
     {
         const double L0 = jB[0] * w0 + jB[3] * w1 + jB[6] * w2;
         const double L1 = jB[1] * w0 + jB[4] * w1 + jB[7] * w2;
@@ -273,17 +279,11 @@ __device__ __forceinline__ void produce_core(const scvx_probinfo& P, bool aero_r
         }
         // minus [L]x = [[0,-L2,L1],[L2,0,-L0],[-L1,L0,0]]
         M[0][1] += L2; M[0][2] -= L1; M[1][0] -= L2; M[1][2] += L0; M[2][0] += L1; M[2][1] -= L0;
-        double Jw[9];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int c = 0; c < 3; ++c)
                 Jw[3 * r + c] = -sigma * (jBi[r] * M[0][c] + jBi[r + 3] * M[1][c] + jBi[r + 6] * M[2][c]);
-        const double hs = 0.5 * sigma;
-        st2(out + J_WW + 0, Jw[0], Jw[1]); st2(out + J_WW + 2, Jw[2], Jw[3]); st2(out + J_WW + 4, Jw[4], Jw[5]);
-        st2(out + J_WW + 6, Jw[6], Jw[7]); st2(out + J_WW + 8, Jw[8], hs * w0);
-        st2(out + J_HW + 1, hs * w1, hs * w2);
-        st2(out + J_HQ + 0, hs * q0, hs * q1); st2(out + J_HQ + 2, hs * q2, hs * q3);
     }
     // ---- translational block
     const double c00 = 1.0 - 2.0 * (q2 * q2 + q3 * q3), c01 = 2.0 * (q1 * q2 - q0 * q3), c02 = 2.0 * (q1 * q3 + q0 * q2);
@@ -314,13 +314,13 @@ __device__ __forceinline__ void produce_core(const scvx_probinfo& P, bool aero_r
         }
     }
     // Jvm = -sigma * ((C u + F)/m) / m = -(sigma/m) * (f_v + g0 e1); one 8-double row per v component
+    double V[24];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        double* o = out + J_V + 8 * r;
-        st2(o + 0, -sm * (fv[r] + (r == 0 ? Pg0 : 0.0)), Jvv[3 * r]);
-        st2(o + 2, Jvv[3 * r + 1], Jvv[3 * r + 2]);
-        st2(o + 4, sm * Jq[4 * r], sm * Jq[4 * r + 1]);
-        st2(o + 6, sm * Jq[4 * r + 2], sm * Jq[4 * r + 3]);
+        V[8 * r + 0] = -sm * (fv[r] + (r == 0 ? Pg0 : 0.0));
+        V[8 * r + 1] = Jvv[3 * r]; V[8 * r + 2] = Jvv[3 * r + 1]; V[8 * r + 3] = Jvv[3 * r + 2];
+        V[8 * r + 4] = sm * Jq[4 * r]; V[8 * r + 5] = sm * Jq[4 * r + 1];
+        V[8 * r + 6] = sm * Jq[4 * r + 2]; V[8 * r + 7] = sm * Jq[4 * r + 3];
     }
     // ---- direct (control / sigma) columns: G[col][row], rows m, v0..2, w0..2
     const double nu = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
@@ -334,6 +334,14 @@ __device__ __forceinline__ void produce_core(const scvx_probinfo& P, bool aero_r
     G[14] = gm * u2; G[15] = sm * c02; G[16] = sm * c12; G[17] = sm * c22;
     G[18] = sigma * (jBi[0] * rT[1] - jBi[3] * rT[0]); G[19] = sigma * (jBi[1] * rT[1] - jBi[4] * rT[0]); G[20] = sigma * (jBi[2] * rT[1] - jBi[5] * rT[0]);
     G[21] = fm; G[22] = fv[0]; G[23] = fv[1]; G[24] = fv[2]; G[25] = fw[0]; G[26] = fw[1]; G[27] = fw[2];
+    // ---- the slot must be free from here on
+    if (slot_free != nullptr) mbar_wait(slot_free, slot_parity);
+    st2(out + J_WW + 0, Jw[0], Jw[1]); st2(out + J_WW + 2, Jw[2], Jw[3]); st2(out + J_WW + 4, Jw[4], Jw[5]);
+    st2(out + J_WW + 6, Jw[6], Jw[7]); st2(out + J_WW + 8, Jw[8], hs * w0);
+    st2(out + J_HW + 1, hs * w1, hs * w2);
+    st2(out + J_HQ + 0, hs * q0, hs * q1); st2(out + J_HQ + 2, hs * q2, hs * q3);
+#pragma unroll
+    for (int k = 0; k < 24; k += 2) st2(out + J_V + k, V[k], V[k + 1]);
 #pragma unroll
     for (int k = 0; k < 28; k += 2) st2(out + J_G + k, G[k], G[k + 1]);
     st2(out + J_FRQ + 0, v[0], v[1]); st2(out + J_FRQ + 2, v[2], fq[0]);
@@ -343,7 +351,8 @@ __device__ __forceinline__ void produce_core(const scvx_probinfo& P, bool aero_r
 
 // STAGED path: the aero force Jacobians were recorded by the value kernel (record entries 25..42).
 __device__ __noinline__ void produce_stage(const scvx_probinfo& P, bool aero_rec, double sigma,
-                                           const double* __restrict__ rec, double* __restrict__ out) {
+                                           const double* __restrict__ rec, double* __restrict__ out,
+                                           uint64_t* slot_free = nullptr, uint32_t slot_parity = 0) {
     produce_core(P, aero_rec, sigma, rec, out,
                  [&](const double*, double, double, double, double Fv[3][3], double Fb[3][3]) {
 #pragma unroll
@@ -353,7 +362,7 @@ __device__ __noinline__ void produce_stage(const scvx_probinfo& P, bool aero_rec
                              Fv[r][c] = rec[(25 + 3 * r + c) * GROUP];
                              Fb[r][c] = rec[(34 + 3 * r + c) * GROUP];
                          }
-                 });
+                 }, slot_free, slot_parity);
 }
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
