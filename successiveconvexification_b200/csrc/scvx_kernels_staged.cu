@@ -528,6 +528,19 @@ __global__ void __launch_bounds__(256, 1) tangent_step_kernel(StagedArgs a) {
         }
 #pragma unroll
         for (int r = 0; r < 3; ++r) FA.Sr[r] = FB.Sr[r] = 0.0;
+        // this lane's interval and the two input values its columns multiply in z = endpoint - D * inp: loaded now,
+        // so the epilogue has no dependent global loads
+        const int t = g * GROUP + warp * 4 + sub;
+        const bool live = t < a.count;
+        const int wi = a.first + (live ? t : a.count - 1);
+        const int bi = wi / ni, ii = wi - bi * ni;
+        auto inp_of = [&](int c) -> double {
+            if (c < 0) return 0.0;
+            if (c < 14) return __ldg(bt.X + ((size_t)bi * bt.n_nodes + ii) * 14 + c);
+            if (c < 20) return __ldg(bt.U + ((size_t)bi * bt.n_nodes + ii) * 3 + (c - 14));
+            return __ldg(bt.sigma + bi);
+        };
+        const double xcA = inp_of(colA), xcB = inp_of(colB);
 
         double pca = 0.0;
 #pragma unroll 1
@@ -564,28 +577,15 @@ __global__ void __launch_bounds__(256, 1) tangent_step_kernel(StagedArgs a) {
             pca += pcs;
         }
 
-        // ---- epilogue: write D columns and z for interval (g*32 + warp*4 + sub)
-        const int t = g * GROUP + warp * 4 + sub;
-        const bool live = t < a.count;
-        const int wi = a.first + (live ? t : a.count - 1);
-        const int b = wi / ni, i = wi - b * ni;
+        // ---- epilogue: write D columns; z -= D[:, heavy] * inp with one fire-and-forget reduction per row
         double* blk = bt.out_blocks + (size_t)wi * SCVX_BLOCK_DOUBLES;
-        const double* xin = bt.X + ((size_t)b * bt.n_nodes + i) * 14;
-        const double* uin = bt.U + ((size_t)b * bt.n_nodes + i) * 3;
-        auto inp_of = [&](int c) -> double {
-            if (c < 0) return 0.0;
-            if (c < 14) return xin[c];
-            if (c < 20) return uin[c - 14];
-            return bt.sigma[b];
-        };
         double zp[14];
 #pragma unroll
         for (int r = 0; r < 14; ++r) zp[r] = 0.0;
-        auto emit_full = [&](const FullCol& F, int c) {
+        auto emit_full = [&](const FullCol& F, int c, double xc) {
             if (c < 0) return;
             const double col[14] = { F.S[0], F.Sr[0], F.Sr[1], F.Sr[2], F.S[1], F.S[2], F.S[3], F.S[4], F.S[5], F.S[6], F.S[7],
                                      F.S[8], F.S[9], F.S[10] };
-            const double xc = inp_of(c);
             double* o = blk + 14 * (1 + c);
 #pragma unroll
             for (int r = 0; r < 14; r += 2) {
@@ -593,8 +593,8 @@ __global__ void __launch_bounds__(256, 1) tangent_step_kernel(StagedArgs a) {
                 zp[r] = fma(col[r], xc, zp[r]); zp[r + 1] = fma(col[r + 1], xc, zp[r + 1]);
             }
         };
-        emit_full(FA, colA);
-        emit_full(FB, colB);
+        emit_full(FA, colA, xcA);
+        emit_full(FB, colB, xcB);
 #pragma unroll
         for (int r = 0; r < 14; ++r) {
             double v = zp[r];
@@ -604,12 +604,10 @@ __global__ void __launch_bounds__(256, 1) tangent_step_kernel(StagedArgs a) {
             zp[r] = v;
         }
         if (live && l8 == 7) {
+            // the z column holds the partial z of light_columns_kernel; exactly one addend per entry -> deterministic
             double* o = blk + 14 * 22;
 #pragma unroll
-            for (int r = 0; r < 14; r += 2) {
-                const double2 e = *reinterpret_cast<const double2*>(o + r);        // partial z (light_columns_kernel)
-                *reinterpret_cast<double2*>(o + r) = make_double2(e.x - zp[r], e.y - zp[r + 1]);
-            }
+            for (int r = 0; r < 14; ++r) atomicAdd(o + r, -zp[r]);
         }
     }
 }
