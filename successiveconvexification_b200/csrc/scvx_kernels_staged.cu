@@ -500,8 +500,8 @@ __global__ void __launch_bounds__(256, 1) tangent_step_kernel(StagedArgs a) {
         const double sigma = __ldg(bt.sigma + b);
         const int half = n & 1, use = n >> 1;
         mbar_wait(&sm.recfull[half][kq], (uint32_t)(use & 1));      // this warp is the only waiter of recfull[half][kq]
-        produce_stage(P, a.rec_n == REC_AERO, sigma, sm.recbuf[kq] + lane, &sm.ring[half * 4 + kq][lane][0],
-                      use > 0 ? &sm.empty_step[half] : nullptr, (uint32_t)((use - 1) & 1));
+        produce_stage_inl(P, a.rec_n == REC_AERO, sigma, sm.recbuf[kq] + lane, &sm.ring[half * 4 + kq][lane][0],
+                          use > 0 ? &sm.empty_step[half] : nullptr, (uint32_t)((use - 1) & 1));
         mbar_arrive(&sm.full_step[half]);
         __syncwarp();                                    // every lane has finished reading recbuf[kq]
         if (lane == 0 && n + 1 < total_steps) issue_record(n + 1);
@@ -514,8 +514,6 @@ __global__ void __launch_bounds__(256, 1) tangent_step_kernel(StagedArgs a) {
     }
 
     FullCol FA, FB;
-    double park[28];
-    volatile double* vp = park;
     int n = 0;                                           // global consumer step
     for (int it = 0; it < my_groups; ++it) {
         const int g = blockIdx.x + it * gridDim.x;
@@ -548,18 +546,11 @@ __global__ void __launch_bounds__(256, 1) tangent_step_kernel(StagedArgs a) {
             // ---- producer duty: the warps of the other half produce step n+1 (Y == S and A == 0 here, so only
             //      S and the r-row sums have to survive the call)
             if ((warp >> 2) == ((n + 1) & 1) && n + 1 < total_steps) {
-#pragma unroll
-                for (int r = 0; r < 11; ++r) { vp[r] = FA.S[r]; vp[11 + r] = FB.S[r]; }
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { vp[22 + r] = FA.Sr[r]; vp[25 + r] = FB.Sr[r]; }
                 produce(n + 1);
+                // the stage tangent and the accumulator are dead across the producer (Y == S, A == 0 at a step
+                // boundary): re-materialise them instead of keeping 88 registers alive
 #pragma unroll
-                for (int r = 0; r < 11; ++r) {
-                    FA.S[r] = vp[r]; FB.S[r] = vp[11 + r];
-                    FA.Y[r] = FA.S[r]; FB.Y[r] = FB.S[r]; FA.A[r] = 0.0; FB.A[r] = 0.0;
-                }
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { FA.Sr[r] = vp[22 + r]; FB.Sr[r] = vp[25 + r]; }
+                for (int r = 0; r < 11; ++r) { FA.Y[r] = FA.S[r]; FB.Y[r] = FB.S[r]; FA.A[r] = 0.0; FB.A[r] = 0.0; }
             }
             // ---- consume the four stages of step n
             const int half = n & 1;

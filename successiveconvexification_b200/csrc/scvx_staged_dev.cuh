@@ -365,6 +365,22 @@ __device__ __noinline__ void produce_stage(const scvx_probinfo& P, bool aero_rec
                  }, slot_free, slot_parity);
 }
 
+// inlined twin: for call sites where little tangent state is live (step boundaries: only S and the r-row sums)
+__device__ __forceinline__ void produce_stage_inl(const scvx_probinfo& P, bool aero_rec, double sigma,
+                                                  const double* __restrict__ rec, double* __restrict__ out,
+                                                  uint64_t* slot_free, uint32_t slot_parity) {
+    produce_core(P, aero_rec, sigma, rec, out,
+                 [&](const double*, double, double, double, double Fv[3][3], double Fb[3][3]) {
+#pragma unroll
+                     for (int r = 0; r < 3; ++r)
+#pragma unroll
+                         for (int c = 0; c < 3; ++c) {
+                             Fv[r][c] = rec[(25 + 3 * r + c) * GROUP];
+                             Fb[r][c] = rec[(34 + 3 * r + c) * GROUP];
+                         }
+                 }, slot_free, slot_parity);
+}
+
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 
 // one full tangent column: rows m, v(3), q(4), w(3) carried as (S, acc, Y); r rows as a pure quadrature
