@@ -144,7 +144,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--traj-per-gpu", type=int, default=TRAJ_PER_GPU)
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto (= staged-step), 1 dualwarp, 2 staged (per-stage hand-over), 3 staged-step")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto (= staged), 1 dualwarp, 2 staged")
     ap.add_argument("--mode", type=int, default=0, help="0 LITERAL (parity contract), 1 TEXTBOOK")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

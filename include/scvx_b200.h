@@ -46,7 +46,7 @@ enum { SCVX_MODE_LITERAL = 0, SCVX_MODE_TEXTBOOK = 1 };
 /* tables of AtmosphericData (drag_itrp, lift_itrp, trq_itrp; aerodynamics.jl:19-21) */
 enum { SCVX_TABLE_DRAG = 0, SCVX_TABLE_LIFT = 1, SCVX_TABLE_TORQUE = 2 };
 /* kernel selection: AUTO picks the fastest validated path */
-enum { SCVX_KERNEL_AUTO = 0, SCVX_KERNEL_DUALWARP = 1, SCVX_KERNEL_STAGED = 2, SCVX_KERNEL_STAGED_STEP = 3 };
+enum { SCVX_KERNEL_AUTO = 0, SCVX_KERNEL_DUALWARP = 1, SCVX_KERNEL_STAGED = 2 };
 
 /* Mirror of ProbInfo (master.jl:73-83) + AtmosphericData scalars (master.jl:14-15) + Tmin
  * (master.jl:21, used by the thrust-lower-bound rows rocketland.jl:199-200).  3x3 column-major. */

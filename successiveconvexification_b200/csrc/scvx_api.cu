@@ -114,7 +114,7 @@ int check_ready(scvx_ctx* c, int B) {
 int launch_linearize(scvx_ctx* c, Dev& d, const ScvxBatch& bt, cudaStream_t s) {
     const ScvxTables tb = tables_of(d);
     int k = c->kernel;
-    if (k == SCVX_KERNEL_AUTO) k = SCVX_KERNEL_STAGED_STEP;
+    if (k == SCVX_KERNEL_AUTO) k = SCVX_KERNEL_STAGED;
     if (k == SCVX_KERNEL_DUALWARP) {
         CK(scvx_launch_dualwarp(bt, tb, s));
         c->launches += 1;
@@ -140,7 +140,7 @@ int launch_linearize(scvx_ctx* c, Dev& d, const ScvxBatch& bt, cudaStream_t s) {
     }
     d.scratch_user = s;
     int n = 0;
-    CK(scvx_launch_staged(bt, tb, c->any_aero, d.scratch, chunk, d.sm_count, s, &n, k == SCVX_KERNEL_STAGED_STEP ? 1 : 0));
+    CK(scvx_launch_staged(bt, tb, c->any_aero, d.scratch, chunk, d.sm_count, s, &n));
     c->launches += n;
     return 0;
 }
@@ -433,7 +433,7 @@ int scvx_set_stream(scvx_ctx* c, void* stream) {
 
 int scvx_set_kernel(scvx_ctx* c, int which) {
     if (!c) return fail(SCVX_ERR_ARG, "null context");
-    if (which < SCVX_KERNEL_AUTO || which > SCVX_KERNEL_STAGED_STEP) return fail(SCVX_ERR_ARG, "unknown kernel id %d", which);
+    if (which < SCVX_KERNEL_AUTO || which > SCVX_KERNEL_STAGED) return fail(SCVX_ERR_ARG, "unknown kernel id %d", which);
     c->kernel = which;
     return 0;
 }

@@ -15,5 +15,5 @@ cudaError_t scvx_launch_fp64_peak(double* d_out, int blocks, int iters, cudaStre
 size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals);
 int scvx_staged_chunk_intervals(int sm_count);
 cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, void* scratch,
-                               int chunk_intervals, int sm_count, cudaStream_t s, int* launches, int variant);
+                               int chunk_intervals, int sm_count, cudaStream_t s, int* launches);
 

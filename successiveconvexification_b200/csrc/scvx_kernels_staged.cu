@@ -1,26 +1,26 @@
-// scvx_kernels_staged.cu — the STAGED linearise-and-discretise path (sm_100a, FP64).
+// scvx_kernels_staged.cu — the STAGED linearise-and-discretise path (sm_100a, FP64): the default.
 //
 // The exact forward-mode Jacobian of the reference's rk4 (dynamics.jl:112-134, 311-313) is the tangent
 // recursion  K_s = J_x(Y_s) * Yt_s + J_u(Y_s) * U_s + e_sigma f(Y_s)  over the 4*npts stages.
-// The value trajectory does not depend on the tangents, so the work is split in two kernels:
+// The value trajectory does not depend on the tangents, so the work is split in three kernels, each in the shape in
+// which it parallelises:
 //
-//  A  stage_value_kernel : one THREAD per interval.  Integrates the 14-state value with rk4, writes the
-//     endpoint (block column 0), lin_err, the thrust-lower-bound rows, and a 25-double "stage record"
-//     (stage state m,v,q,w; stage control u; unscaled rhs f) per stage, laid out
-//     [group of 32 intervals][stage][entry][32 lanes] so that one stage of one group is one contiguous
-//     6400-byte slab.
+//  A   stage_value_kernel   : one THREAD per interval.  Integrates the 14-state value with rk4 and evaluates the aero
+//      force together with its Jacobians dF/dv, dF/db (b = C(q) e1).  Writes the endpoint (block column 0), lin_err,
+//      the thrust-lower-bound rows and a 43-double "stage record" per stage (stage state m,v,q,w; stage control u;
+//      unscaled rhs f; dF/dv; dF/db), laid out [group of 32 intervals][stage][entry][32 lanes] so that one stage of
+//      one group is one contiguous 11 KB slab (= one TMA bulk copy).
 //
-//  B  tangent_kernel : persistent, one 256-thread CTA per SM, 32 intervals in flight per CTA.
-//     * Tangent propagation ("consumer" role): 8 lanes per interval, every lane owns two full tangent
-//       columns (rows m,v,q,w + the r rows as pure quadrature) and one light column (inputs m, v), all in
-//       registers.  Structure used: nothing depends on r; m, q, w rows of the m/v columns vanish.
-//     * Jacobian production ("producer" role): the 8 warps take turns (stage T -> warp T mod 8); the producing
-//       warp works with lane = interval (no redundancy), pulls its stage record with one TMA bulk copy
-//       (cp.async.bulk -> mbarrier), forms the sigma-scaled Jacobian blocks (78 doubles per interval) and
-//       stores them into a shared-memory ring; consumers read them back as broadcast 128-bit loads.
-//     * Ring slots are handed over with mbarriers (full/empty), so a warp that is busy producing does not
-//       stall the others until they are a whole ring ahead.
-//     Outputs [A|B-|B+|Sigma|z] go straight from registers to the 14x23 block with 16-byte stores.
+//  A2  light_columns_kernel : one THREAD per interval.  The four light tangent columns d/d(m, v) (only their v and r
+//      rows are non-trivial), the constant position columns and the partial z.
+//
+//  B   tangent_kernel       : persistent, one 256-thread CTA per SM, 32 intervals per pass.  The 14 heavy tangent
+//      columns: 8 lanes per interval, two full columns per lane, tangent state (S, accumulator, stage tangent, r-row
+//      quadrature = 144 registers) in registers.  The sigma-scaled Jacobian blocks (78 doubles per interval and
+//      stage) are produced by rotating warps with lane = interval (no redundancy) from TMA-staged stage records into
+//      a shared-memory ring and read back by the 8 lanes of an interval as broadcast 128-bit loads.  Ring slots are
+//      handed over with mbarriers once per rk4 step.  [A|B-|B+|Sigma] go from registers to the 14x23 block with
+//      16-byte stores; z is reduced over the 8 lanes and accumulated in place.
 #include "scvx_staged_dev.cuh"
 #include "scvx_kernels.h"
 
@@ -234,211 +234,16 @@ __global__ void __launch_bounds__(128, 3) light_columns_kernel(StagedArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Kernel B
-// ------------------------------------------------------------------------------------------------
-struct __align__(16) TangentSmem {
-    double ring[RING][GROUP][NJ];            // Jacobian records
-    double recbuf[NWARP][REC_MAX * GROUP];   // per-warp stage-record staging (TMA destination)
-    uint64_t full[RING];
-    uint64_t empty[RING];
-    uint64_t recfull[NWARP];
-};
-
-
-__global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TangentSmem& sm = *reinterpret_cast<TangentSmem*>(smem_raw);
-    const ScvxBatch& bt = a.bt;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int l8 = lane & 7;                   // column-group lane within the interval
-    const int sub = lane >> 3;                 // interval within the warp (0..3)
-    const int ni = bt.n_nodes - 1;
-    const int nst = 4 * bt.npts;
-    const double h = bt.dt / (double)bt.npts;
-    const double pcs = 1.0 / (double)bt.npts;
-    const double sstep = (bt.mode == SCVX_MODE_LITERAL) ? 1.0 : h;
-    const double h6 = h * (1.0 / 6.0);
-
-    if (tid == 0) {
-        for (int r = 0; r < RING; ++r) { mbar_init(&sm.full[r], 32); mbar_init(&sm.empty[r], NWARP); }
-        for (int wq = 0; wq < NWARP; ++wq) mbar_init(&sm.recfull[wq], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    // groups handled by this CTA: g = blockIdx.x, blockIdx.x + gridDim.x, ...
-    const int my_groups = (a.n_groups > (int)blockIdx.x) ? (a.n_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int total_stages = my_groups * nst;               // global stage counter T = it * nst + s
-
-    // ---- static per-lane column configuration
-    // full slots: lanes 0..2: (u-_j, u+_j); lane 3: (sigma, -); lane 4: (w0,w1); 5: (w2,q0); 6: (q1,q2); 7: (q3,-)
-    int colA = -1, colB = -1, gcol = 3;
-    if (l8 < 3) { colA = 14 + l8; colB = 17 + l8; gcol = l8; }
-    else if (l8 == 3) colA = 20;
-    else if (l8 == 4) { colA = 11; colB = 12; }
-    else if (l8 == 5) { colA = 13; colB = 7; }
-    else if (l8 == 6) { colA = 8; colB = 9; }
-    else colA = 10;
-    // direct-term coefficients, re-derived from l8 where used (keeps them out of long-lived registers):
-    //   alpha_A = 1-pc (u- columns) | 1 (sigma column) | 0 ;  alpha_B = pc (u+ columns) | 0 ;
-    //   dsigma_A = 1 for the sigma column
-
-    // producer bookkeeping: this warp produces global stages T with T % NWARP == warp
-    int nextP = warp;                                // next global stage this warp has to produce
-    int p_it = 0, p_s = warp;                        // ... as (group pass, stage) ; nst >= 4
-    while (p_s >= nst) { p_s -= nst; ++p_it; }
-    uint32_t rec_phase = 0;
-    auto issue_record = [&](int it, int s) {         // lane 0 only: TMA the stage record of (pass it, stage s)
-        const int g = blockIdx.x + it * gridDim.x;
-        const uint32_t bytes = (uint32_t)a.rec_n * GROUP * 8;
-        const double* src = a.rec + ((size_t)g * nst + s) * ((size_t)a.rec_n * GROUP);
-        mbar_expect_tx(&sm.recfull[warp], bytes);
-        bulk_g2s(sm.recbuf[warp], src, bytes, &sm.recfull[warp]);
-    };
-    if (lane == 0 && nextP < total_stages) issue_record(p_it, p_s);
-
-    auto produce = [&]() {                           // produce global stage nextP = (p_it, p_s), then advance
-        const int g = blockIdx.x + p_it * gridDim.x;
-        int t = g * GROUP + lane; if (t >= a.count) t = a.count - 1;
-        const int b = (a.first + t) / ni;
-        const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
-        const double sigma = bt.sigma[b];
-        const int slot = nextP % RING;
-        const int use = nextP / RING;
-        mbar_wait(&sm.recfull[warp], rec_phase); rec_phase ^= 1;
-        if (use > 0) mbar_wait(&sm.empty[slot], (uint32_t)((use - 1) & 1));
-        produce_stage(P, a.rec_n == REC_AERO, sigma, sm.recbuf[warp] + lane, &sm.ring[slot][lane][0]);
-        mbar_arrive(&sm.full[slot]);
-        nextP += NWARP; p_s += NWARP;
-        while (p_s >= nst) { p_s -= nst; ++p_it; }
-        __syncwarp();
-        if (lane == 0 && nextP < total_stages) { fence_proxy_async(); issue_record(p_it, p_s); }
-    };
-
-    // prologue: stages 0..LOOKAHEAD-1
-    for (int k = 0; k < LOOKAHEAD; ++k)
-        if (nextP == k && nextP < total_stages) produce();
-
-    FullCol FA, FB;
-    double park[72];
-    volatile double* vp = park;
-    int T = 0;
-    int c_slot = 0;
-    uint32_t c_phase = 0;
-    for (int it = 0; it < my_groups; ++it) {
-        const int g = blockIdx.x + it * gridDim.x;
-        // ---- initial tangent: S = [I | 0]
-#pragma unroll
-        for (int r = 0; r < 11; ++r) {
-            // local row order of a full column: 0 m, 1..3 v, 4..7 q, 8..10 w  (inp column of local row r >= 4 is r + 3)
-            FA.S[r] = (r >= 4 && colA == r + 3) ? 1.0 : 0.0;
-            FB.S[r] = (r >= 4 && colB == r + 3) ? 1.0 : 0.0;
-            FA.A[r] = 0.0; FB.A[r] = 0.0;
-            FA.Y[r] = FA.S[r]; FB.Y[r] = FB.S[r];
-        }
-#pragma unroll
-        for (int r = 0; r < 3; ++r) FA.Sr[r] = FB.Sr[r] = 0.0;
-
-        double pca = 0.0;
-#pragma unroll 1
-        for (int s = 0; s < nst; ++s, ++T) {
-            if (nextP == T + LOOKAHEAD && nextP < total_stages) {
-                // manual live-range split: park the tangent state in local memory across the producer call so
-                // that it never competes with the producer for registers inside the hot loop
-#pragma unroll
-                for (int r = 0; r < 11; ++r) {
-                    vp[r] = FA.S[r]; vp[11 + r] = FA.A[r]; vp[22 + r] = FA.Y[r];
-                    vp[36 + r] = FB.S[r]; vp[47 + r] = FB.A[r]; vp[58 + r] = FB.Y[r];
-                }
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { vp[33 + r] = FA.Sr[r]; vp[69 + r] = FB.Sr[r]; }
-                produce();
-#pragma unroll
-                for (int r = 0; r < 11; ++r) {
-                    FA.S[r] = vp[r]; FA.A[r] = vp[11 + r]; FA.Y[r] = vp[22 + r];
-                    FB.S[r] = vp[36 + r]; FB.A[r] = vp[47 + r]; FB.Y[r] = vp[58 + r];
-                }
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { FA.Sr[r] = vp[33 + r]; FB.Sr[r] = vp[69 + r]; }
-            }
-            const int st = s & 3;
-            const int slot = c_slot;
-            mbar_wait(&sm.full[slot], c_phase);
-            if (++c_slot == RING) { c_slot = 0; c_phase ^= 1; }
-            const double* J = &sm.ring[slot][warp * 4 + sub][0];
-            if (st == 3) {
-                consume_stage8<true>(FA, FB, J, gcol, l8, pca + pcs, 1.0, 0.0, h6, &sm.empty[slot], lane);
-                pca += pcs;
-            } else {
-                const double pc = (st == 0) ? pca : pca + 0.5 * pcs;
-                consume_stage8<false>(FA, FB, J, gcol, l8, pc, st == 0 ? 1.0 : 2.0, st == 2 ? sstep : 0.5 * sstep, h6,
-                                      &sm.empty[slot], lane);
-            }
-        }
-
-        // ---- epilogue: write D columns and z for interval (g*32 + warp*4 + sub)
-        const int t = g * GROUP + warp * 4 + sub;
-        const bool live = t < a.count;
-        const int wi = a.first + (live ? t : a.count - 1);
-        const int b = (int)(wi / ni), i = (int)(wi % ni);
-        double* blk = bt.out_blocks + (size_t)wi * SCVX_BLOCK_DOUBLES;
-        const double* xin = bt.X + ((size_t)b * bt.n_nodes + i) * 14;
-        const double* uin = bt.U + ((size_t)b * bt.n_nodes + i) * 3;
-        auto inp_of = [&](int c) -> double {
-            if (c < 0) return 0.0;
-            if (c < 14) return xin[c];
-            if (c < 20) return uin[c - 14];
-            return bt.sigma[b];
-        };
-        double zp[14];
-#pragma unroll
-        for (int r = 0; r < 14; ++r) zp[r] = 0.0;
-        auto emit_full = [&](const FullCol& F, int c) {
-            if (c < 0) return;
-            // state row order: m, r(3), v(3), q(4), w(3)
-            const double col[14] = { F.S[0], F.Sr[0], F.Sr[1], F.Sr[2], F.S[1], F.S[2], F.S[3], F.S[4], F.S[5], F.S[6], F.S[7],
-                                     F.S[8], F.S[9], F.S[10] };
-            const double xc = inp_of(c);
-            double* o = blk + 14 * (1 + c);
-#pragma unroll
-            for (int r = 0; r < 14; r += 2) {
-                if (live) *reinterpret_cast<double2*>(o + r) = make_double2(col[r], col[r + 1]);
-                zp[r] = fma(col[r], xc, zp[r]); zp[r + 1] = fma(col[r + 1], xc, zp[r + 1]);
-            }
-        };
-        emit_full(FA, colA);
-        emit_full(FB, colB);
-        // z = (partial z of kernel A2) - D[:, heavy columns] * inp  (sum over the 8 lanes of this interval)
-#pragma unroll
-        for (int r = 0; r < 14; ++r) {
-            double v = zp[r];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            zp[r] = v;
-        }
-        if (live && l8 == 7) {
-            double* o = blk + 14 * 22;
-#pragma unroll
-            for (int r = 0; r < 14; r += 2) {
-                const double2 e = *reinterpret_cast<const double2*>(o + r);        // partial z written by kernel A2
-                *reinterpret_cast<double2*>(o + r) = make_double2(e.x - zp[r], e.y - zp[r + 1]);
-            }
-        }
-    }
-}
-
-
-
-// ------------------------------------------------------------------------------------------------
-// Kernel B, step-synchronised variant (default).  Same mapping as tangent_kernel (8 lanes per interval, two full
-// columns per lane, rotating lane = interval producer, TMA-fed stage records, mbarrier-guarded ring), but production
-// and hand-over happen once per rk4 STEP instead of once per stage:
+// Kernel B: tangent propagation of the 14 heavy columns.  8 lanes per interval, two full columns per lane, rotating
+// lane = interval Jacobian producer, TMA-fed stage records, mbarrier-guarded shared-memory ring.  Production and
+// hand-over happen once per rk4 STEP (a per-stage hand-over cost 17 % of the kernel in barrier waits and loop drain):
 //   * the ring holds two steps (2 x 4 stage slabs); at the start of consumer step m the four warps of the other half
 //     each produce one stage of step m+1 (one whole step of slack);
 //   * consumers wait ONE "full" barrier per step and release the four slabs with ONE "empty" arrive per step;
-//   * at a step boundary the stage tangent equals S and the accumulator is zero, so a producing warp parks 28 instead
-//     of 72 doubles around the producer call;
+//   * at a step boundary the stage tangent equals S and the accumulator is zero, so only 56 registers of tangent
+//     state are live across the (inlined) producer: no spilling, no parking;
+//   * the producer forms the whole 78-double record in registers and waits for the ring slot only right before its
+//     stores, overlapping its arithmetic with consumers that are still reading the slot;
 //   * four record buffers (one per stage of a step); the warp that has just read buffer k re-arms its TMA for the
 //     next step.
 // ------------------------------------------------------------------------------------------------
@@ -450,7 +255,7 @@ struct __align__(16) StepSmem {
     uint64_t recfull[2][4];                  // [half][stage]: one waiting warp per barrier (it observes every phase)
 };
 
-__global__ void __launch_bounds__(256, 1) tangent_step_kernel(StagedArgs a) {
+__global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StepSmem& sm = *reinterpret_cast<StepSmem*>(smem_raw);
     const ScvxBatch& bt = a.bt;
@@ -616,13 +421,11 @@ size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals) {
 int scvx_staged_chunk_intervals(int sm_count) { return sm_count * 768; }
 
 cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, void* scratch,
-                               int chunk_intervals, int sm_count, cudaStream_t s, int* launches, int variant) {
+                               int chunk_intervals, int sm_count, cudaStream_t s, int* launches) {
     const long total = (long)(bt.n_nodes - 1) * bt.B;
-    const size_t smem = (variant == 1) ? sizeof(StepSmem) : sizeof(TangentSmem);
+    const size_t smem = sizeof(StepSmem);
     {
-        cudaError_t e = (variant == 1)
-            ? cudaFuncSetAttribute(tangent_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-            : cudaFuncSetAttribute(tangent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tangent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     for (long first = 0; first < total; first += chunk_intervals) {
@@ -635,8 +438,7 @@ cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool a
         stage_value_kernel<<<(threads + 127) / 128, 128, 0, s>>>(a);
         light_columns_kernel<<<(a.count + 127) / 128, 128, 0, s>>>(a);
         const int grid = a.n_groups < sm_count ? a.n_groups : sm_count;
-        if (variant == 1) tangent_step_kernel<<<grid, 256, smem, s>>>(a);
-        else tangent_kernel<<<grid, 256, smem, s>>>(a);
+        tangent_kernel<<<grid, 256, smem, s>>>(a);
         if (launches) *launches += 3;
     }
     return cudaGetLastError();

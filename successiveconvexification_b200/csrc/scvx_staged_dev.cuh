@@ -1,6 +1,6 @@
-// scvx_staged_dev.cuh — device-side building blocks shared by the STAGED (scvx_kernels_staged.cu) and FUSED
-// (scvx_kernels_fused.cu) linearise-and-discretise paths: Jacobian-record layout, spline value+gradient, aero force
-// Jacobian, the per-stage Jacobian producer, mbarrier / TMA helpers and the two-column tangent stage.
+// scvx_staged_dev.cuh — device-side building blocks of the STAGED linearise-and-discretise path
+// (scvx_kernels_staged.cu): Jacobian-record layout, spline value+gradient, aero force Jacobian, the per-stage
+// Jacobian producer, mbarrier / TMA helpers and the two-column tangent stage.
 #pragma once
 #include "scvx_common.cuh"
 
@@ -11,14 +11,6 @@ constexpr int REC_EXO = 25;      // stage record entries: m, v(3), q(4), w(3), u
 constexpr int REC_AERO = 43;     // + dF_aero/dv (9, row-major) + dF_aero/db (9), b = C(q) e1
 constexpr int REC_MAX = REC_AERO;
 constexpr int NJ = 78;           // Jacobian record entries per interval per stage (2 x odd: conflict-free STS.128)
-#ifndef SCVX_RING
-#define SCVX_RING 6
-#endif
-#ifndef SCVX_LOOKAHEAD
-#define SCVX_LOOKAHEAD 3
-#endif
-constexpr int RING = SCVX_RING;  // ring slots
-constexpr int LOOKAHEAD = SCVX_LOOKAHEAD;   // producer runs this many stages ahead of the consumers (< RING)
 constexpr int GROUP = 32;        // intervals per CTA pass
 constexpr int NWARP = 8;
 
@@ -349,23 +341,8 @@ __device__ __forceinline__ void produce_core(const scvx_probinfo& P, bool aero_r
     st2(out + J_FRQ + 8, 0.0, 0.0);
 }
 
-// STAGED path: the aero force Jacobians were recorded by the value kernel (record entries 25..42).
-__device__ __noinline__ void produce_stage(const scvx_probinfo& P, bool aero_rec, double sigma,
-                                           const double* __restrict__ rec, double* __restrict__ out,
-                                           uint64_t* slot_free = nullptr, uint32_t slot_parity = 0) {
-    produce_core(P, aero_rec, sigma, rec, out,
-                 [&](const double*, double, double, double, double Fv[3][3], double Fb[3][3]) {
-#pragma unroll
-                     for (int r = 0; r < 3; ++r)
-#pragma unroll
-                         for (int c = 0; c < 3; ++c) {
-                             Fv[r][c] = rec[(25 + 3 * r + c) * GROUP];
-                             Fb[r][c] = rec[(34 + 3 * r + c) * GROUP];
-                         }
-                 }, slot_free, slot_parity);
-}
-
-// inlined twin: for call sites where little tangent state is live (step boundaries: only S and the r-row sums)
+// The aero force Jacobians were recorded by the value kernel (record entries 25..42).  Inlined: at its call site (a
+// step boundary) only S and the r-row sums of the tangent state are live.
 __device__ __forceinline__ void produce_stage_inl(const scvx_probinfo& P, bool aero_rec, double sigma,
                                                   const double* __restrict__ rec, double* __restrict__ out,
                                                   uint64_t* slot_free, uint32_t slot_parity) {

@@ -27,7 +27,7 @@ from .defns import (AERO_TABLE, ACC_WIDTH, AtmosphericData, CProbInfo, DescentPr
 
 MODE_LITERAL = 0      # reproduces dynamics.jl:126-128 (stage increments not scaled by the sub-step)
 MODE_TEXTBOOK = 1     # classical RK4
-KERNEL_AUTO, KERNEL_DUALWARP, KERNEL_STAGED, KERNEL_STAGED_STEP = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_DUALWARP, KERNEL_STAGED = 0, 1, 2
 TABLE_DRAG, TABLE_LIFT, TABLE_TORQUE = 0, 1, 2
 
 state_idx = slice(0, 14)          # dynamics.jl:136  stateC = 1:14

@@ -10,7 +10,7 @@ from conftest import GOLDEN, PARITY_TOL, assert_parity, parity_report
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [1, 2, 3]       # SCVX_KERNEL_DUALWARP, SCVX_KERNEL_STAGED, SCVX_KERNEL_STAGED_STEP
+KERNELS = [1, 2]          # SCVX_KERNEL_DUALWARP, SCVX_KERNEL_STAGED
 
 
 @pytest.fixture(scope="module")
