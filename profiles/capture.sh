@@ -6,7 +6,7 @@ C="python bench.py --steps 2 --warmup 3 --traj-per-gpu 8192 --no-e2e --no-cpu"
 O=gpurun_out
 $C > $O/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 23 -c 24 --csv --log-file $O/r1_launches.csv $C > $O/ncu_launches.log 2>&1
-for k in tangent_kernel stage_value_kernel light_columns_kernel; do
+for k in tangent_kernel stage_value_kernel; do
   $C > $O/plain.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -o $O/r1_$k $C > $O/ncu_$k.log 2>&1
 done

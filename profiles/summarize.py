@@ -6,7 +6,7 @@ shutil.copy(os.path.join(G, "r1_launches.csv"), os.path.join(P, "r1_launches.csv
 for src, dst in (("r1_bench.json", "r1_bench_1gpu.json"), ("r1_bench_reference.json", "r1_bench_reference.json")):
     txt = open(os.path.join(G, src)).read()
     open(os.path.join(P, dst), "w").write([l for l in txt.splitlines() if l.startswith("{")][-1] + "\n")
-for k in ("tangent_kernel", "stage_value_kernel", "light_columns_kernel"):
+for k in ("tangent_kernel", "stage_value_kernel"):
     out = subprocess.run([sys.executable, os.path.join(P, "ncu_summary.py"), os.path.join(G, f"r1_{k}.ncu-rep")],
                          capture_output=True, text=True).stdout
     open(os.path.join(P, f"r1_{k}.txt"), "w").write(out)

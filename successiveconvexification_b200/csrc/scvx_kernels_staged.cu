@@ -2,17 +2,15 @@
 //
 // The exact forward-mode Jacobian of the reference's rk4 (dynamics.jl:112-134, 311-313) is the tangent
 // recursion  K_s = J_x(Y_s) * Yt_s + J_u(Y_s) * U_s + e_sigma f(Y_s)  over the 4*npts stages.
-// The value trajectory does not depend on the tangents, so the work is split in three kernels, each in the shape in
+// The value trajectory does not depend on the tangents, so the work is split in two kernels, each in the shape in
 // which it parallelises:
 //
 //  A   stage_value_kernel   : one THREAD per interval.  Integrates the 14-state value with rk4 and evaluates the aero
 //      force together with its Jacobians dF/dv, dF/db (b = C(q) e1).  Writes the endpoint (block column 0), lin_err,
 //      the thrust-lower-bound rows and a 43-double "stage record" per stage (stage state m,v,q,w; stage control u;
 //      unscaled rhs f; dF/dv; dF/db), laid out [group of 32 intervals][stage][entry][32 lanes] so that one stage of
-//      one group is one contiguous 11 KB slab (= one TMA bulk copy).
-//
-//  A2  light_columns_kernel : one THREAD per interval.  The four light tangent columns d/d(m, v) (only their v and r
-//      rows are non-trivial), the constant position columns and the partial z.
+//      one group is one contiguous 11 KB slab (= one TMA bulk copy).  It also carries the four light tangent columns
+//      d/d(m, v) (state in shared memory), the constant position columns and the partial z.
 //
 //  B   tangent_kernel       : persistent, one 256-thread CTA per SM, 32 intervals per pass.  The 14 heavy tangent
 //      columns: 8 lanes per interval, two full columns per lane, tangent state (S, accumulator, stage tangent, r-row
@@ -29,7 +27,14 @@ namespace {
 #ifndef SCVX_A_MINBLOCKS
 #define SCVX_A_MINBLOCKS 2
 #endif
+// The kernel also propagates the four light tangent columns d/d(m, v0, v1, v2) (only their v and r rows are non-trivial:
+// K_v = Jvv Y_v (+ Jvm for the mass column), r rows a quadrature of the v rows).  Their 48 doubles of state live in
+// shared memory, lane-private [entry][thread] (conflict-free), because the value chain already uses every register;
+// the Jacobian blocks they need (dF/dv, f_v, m) are at hand here, so no separate pass re-reads the stage records
+// (a separate one-thread-per-interval kernel was latency bound on those reads: 0.13 ms per chunk vs +0.03 ms here).
+constexpr size_t LIGHT_SMEM_BYTES = 48 * 128 * sizeof(double);
 __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(StagedArgs a) {
+    extern __shared__ double light_smem[];            // [48][128] doubles
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n_groups * GROUP) return;
     const ScvxBatch& bt = a.bt;
@@ -52,6 +57,19 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
     const double h = bt.dt / (double)bt.npts;
     const double pcs = 1.0 / (double)bt.npts;
     const double s = (bt.mode == SCVX_MODE_LITERAL) ? 1.0 : h;
+    // light-column state: L[(c*12 + kind*3 + r)*128 + tid], kind 0 = S, 1 = acc, 2 = Y, 3 = r-row sum
+    double* L = light_smem + threadIdx.x;
+    {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double s0 = (c == r + 1) ? 1.0 : 0.0;
+                L[(c * 12 + 0 + r) * 128] = s0; L[(c * 12 + 3 + r) * 128] = 0.0;
+                L[(c * 12 + 6 + r) * 128] = s0; L[(c * 12 + 9 + r) * 128] = 0.0;
+            }
+    }
+    const double g0 = __ldg(&P.g0);
     double pca = 0.0;
     for (int it = 0; it < bt.npts; ++it) {
         double acc[14], y[14];
@@ -85,6 +103,35 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
             for (int r = 0; r < 10; ++r) rp[(15 + r) * GROUP] = f[4 + r];
             const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
             const double cy = (st == 2) ? s : 0.5 * s;
+            {
+                const double smv = sigma / y[0];
+                const double csg = h * (1.0 / 6.0) * wgt * sigma;
+                double Jvv[3][3], Jvm[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    Jvm[r] = -smv * (f[4 + r] + (r == 0 ? g0 : 0.0));
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) Jvv[r][c] = smv * Fv[r][c];
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    double* Lc = L + c * 12 * 128;
+                    const double y0 = Lc[6 * 128], y1 = Lc[7 * 128], y2 = Lc[8 * 128];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const double yr = (r == 0) ? y0 : (r == 1 ? y1 : y2);
+                        Lc[(9 + r) * 128] = fma(csg, yr, Lc[(9 + r) * 128]);
+                        const double K = fma(Jvv[r][0], y0, fma(Jvv[r][1], y1, fma(Jvv[r][2], y2, c == 0 ? Jvm[r] : 0.0)));
+                        if (st != 3) {
+                            Lc[(3 + r) * 128] = fma(wgt, K, Lc[(3 + r) * 128]);
+                            Lc[(6 + r) * 128] = fma(cy, K, Lc[r * 128]);
+                        } else {
+                            const double sn = fma(h * (1.0 / 6.0), Lc[(3 + r) * 128] + K, Lc[r * 128]);
+                            Lc[r * 128] = sn; Lc[(6 + r) * 128] = sn; Lc[(3 + r) * 128] = 0.0;
+                        }
+                    }
+                }
+            }
 #pragma unroll
             for (int r = 0; r < 14; ++r) {
                 const double k = f[r] * sigma;
@@ -100,6 +147,40 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
     double* blk = bt.out_blocks + (size_t)w * SCVX_BLOCK_DOUBLES;
 #pragma unroll
     for (int r = 0; r < 14; r += 2) *reinterpret_cast<double2*>(blk + r) = make_double2(x[r], x[r + 1]);
+    {
+        // columns d/d(m, r, v) of the block and the partial z = endpoint - D[:, m r v] * inp[m r v]
+        double z[7];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) z[r] = x[r];
+        z[0] -= xin[0];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {               // inp 0 (m), 1..3 (r), 4..6 (v)
+            double col[14];
+#pragma unroll
+            for (int r = 0; r < 14; ++r) col[r] = 0.0;
+            if (c == 0 || c >= 4) {
+                const double* Lc = L + (c == 0 ? 0 : c - 3) * 12 * 128;
+                const double xc = xin[c];
+                if (c == 0) col[0] = 1.0;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    col[1 + r] = Lc[(9 + r) * 128]; col[4 + r] = Lc[r * 128];
+                    z[1 + r] = fma(-col[1 + r], xc, z[1 + r]); z[4 + r] = fma(-col[4 + r], xc, z[4 + r]);
+                }
+            } else {
+                col[c] = 1.0;                        // nothing depends on position: D[:, r_j] = e_{r_j}
+                z[c] -= xin[c];
+            }
+            double* o = blk + 14 * (1 + c);
+#pragma unroll
+            for (int r = 0; r < 14; r += 2) *reinterpret_cast<double2*>(o + r) = make_double2(col[r], col[r + 1]);
+        }
+        double* zo = blk + 14 * 22;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) zo[r] = z[r];
+#pragma unroll
+        for (int r = 7; r < 14; ++r) zo[r] = x[r];
+    }
     if (bt.out_lin_err) {
         double* e = bt.out_lin_err + (size_t)w * 14;
 #pragma unroll
@@ -115,122 +196,6 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
             *reinterpret_cast<double2*>(o + 2) = make_double2(-(u[2] / nu), __ldg(&P.Tmin) - nu);
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Kernel A2: the four "light" tangent columns d/d(m, v0, v1, v2) — one THREAD per interval.
-// Only the v and r rows of these columns are non-trivial: K_v = Jvv Y_v (+ Jvm for the mass
-// column), r rows are a quadrature of the v rows.  Reads m, f_v and dF/dv from the stage records, writes the
-// seven columns d/d(m, r, v) of the block and the partial z = endpoint - D[:, m r v] * inp[m r v].
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 3) light_columns_kernel(StagedArgs a) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.count) return;
-    const ScvxBatch& bt = a.bt;
-    const int ni = bt.n_nodes - 1;
-    const int w = a.first + t;
-    const int b = w / ni, i = w % ni;
-    const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
-    const double sigma = __ldg(bt.sigma + b), g0 = __ldg(&P.g0);
-    const bool aero = (a.rec_n == REC_AERO);
-    const int nst = 4 * bt.npts;
-    const double* rec = a.rec + ((size_t)(t >> 5) * nst) * ((size_t)a.rec_n * GROUP) + (t & 31);
-    const double h = bt.dt / (double)bt.npts;
-    const double sstep = (bt.mode == SCVX_MODE_LITERAL) ? 1.0 : h;
-    const double h6 = h * (1.0 / 6.0);
-    double S[4][3], A[4][3], Y[4][3], Sr[4][3];
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int r = 0; r < 3; ++r) { S[c][r] = (c == r + 1) ? 1.0 : 0.0; Y[c][r] = S[c][r]; A[c][r] = 0.0; Sr[c][r] = 0.0; }
-    // software-pipelined record reads: the 13 values of stage s+1 are in flight while stage s is computed
-    const size_t rstride = (size_t)a.rec_n * GROUP;
-    double nx[13];
-    auto fetch = [&](int s) {
-        const double* rp = rec + (size_t)s * rstride;
-        nx[0] = __ldg(rp);
-#pragma unroll
-        for (int r = 0; r < 3; ++r) nx[1 + r] = __ldg(rp + (15 + r) * GROUP);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) nx[4 + k] = aero ? __ldg(rp + (25 + k) * GROUP) : 0.0;
-    };
-    // ... and the lines of stage s+PF are pulled into L2 by prefetch instructions (no register cost): the records
-    // were written by the value kernel a whole chunk ago and are in DRAM by now
-    constexpr int PF = 6;
-    auto prefetch_l2 = [&](int s) {
-        const double* rp = rec + (size_t)s * rstride;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
-#pragma unroll
-        for (int r = 0; r < 3; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (15 + r) * GROUP));
-        if (aero) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (25 + k) * GROUP));
-        }
-    };
-    for (int s = 0; s < PF && s < nst; ++s) prefetch_l2(s);
-    fetch(0);
-#pragma unroll 1
-    for (int s = 0; s < nst; ++s) {
-        const int st = s & 3;
-        double cu[13];
-#pragma unroll
-        for (int k = 0; k < 13; ++k) cu[k] = nx[k];
-        if (s + PF < nst) prefetch_l2(s + PF);
-        if (s + 1 < nst) fetch(s + 1);
-        const double sm = sigma / cu[0];
-        double Jvv[3][3], Jvm[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            Jvm[r] = -sm * (cu[1 + r] + (r == 0 ? g0 : 0.0));
-#pragma unroll
-            for (int c = 0; c < 3; ++c) Jvv[r][c] = sm * cu[4 + 3 * r + c];
-        }
-        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
-        const double cy = (st == 2) ? sstep : 0.5 * sstep;
-        const double csg = h6 * wgt * sigma;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            double K[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                Sr[c][r] = fma(csg, Y[c][r], Sr[c][r]);
-                K[r] = fma(Jvv[r][0], Y[c][0], fma(Jvv[r][1], Y[c][1], fma(Jvv[r][2], Y[c][2], c == 0 ? Jvm[r] : 0.0)));
-            }
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                if (st != 3) { A[c][r] = fma(wgt, K[r], A[c][r]); Y[c][r] = fma(cy, K[r], S[c][r]); }
-                else { S[c][r] = fma(h6, A[c][r] + K[r], S[c][r]); Y[c][r] = S[c][r]; A[c][r] = 0.0; }
-            }
-        }
-    }
-    double* blk = bt.out_blocks + (size_t)w * SCVX_BLOCK_DOUBLES;
-    const double* xin = bt.X + ((size_t)b * bt.n_nodes + i) * 14;
-    // columns: inp 0 (m), 1..3 (r), 4..6 (v)
-#pragma unroll
-    for (int c = 0; c < 7; ++c) {
-        double col[14];
-#pragma unroll
-        for (int r = 0; r < 14; ++r) col[r] = 0.0;
-        if (c == 0) { col[0] = 1.0; for (int r = 0; r < 3; ++r) { col[1 + r] = Sr[0][r]; col[4 + r] = S[0][r]; } }
-        else if (c < 4) col[c] = 1.0;
-        else { for (int r = 0; r < 3; ++r) { col[1 + r] = Sr[c - 3][r]; col[4 + r] = S[c - 3][r]; } }
-        double* o = blk + 14 * (1 + c);
-#pragma unroll
-        for (int r = 0; r < 14; r += 2) *reinterpret_cast<double2*>(o + r) = make_double2(col[r], col[r + 1]);
-    }
-    // partial z (kernel B subtracts the remaining 14 columns)
-    double z[14];
-#pragma unroll
-    for (int r = 0; r < 14; ++r) z[r] = blk[r];
-    z[0] -= xin[0];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        z[1 + r] -= Sr[0][r] * xin[0] + xin[1 + r] + Sr[1][r] * xin[4] + Sr[2][r] * xin[5] + Sr[3][r] * xin[6];
-        z[4 + r] -= S[0][r] * xin[0] + S[1][r] * xin[4] + S[2][r] * xin[5] + S[3][r] * xin[6];
-    }
-    double* o = blk + 14 * 22;
-#pragma unroll
-    for (int r = 0; r < 14; r += 2) *reinterpret_cast<double2*>(o + r) = make_double2(z[r], z[r + 1]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -400,7 +365,7 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
             zp[r] = v;
         }
         if (live && l8 == 7) {
-            // the z column holds the partial z of light_columns_kernel; exactly one addend per entry -> deterministic
+            // the z column holds the partial z written by stage_value_kernel; exactly one addend per entry -> deterministic
             double* o = blk + 14 * 22;
 #pragma unroll
             for (int r = 0; r < 14; ++r) atomicAdd(o + r, -zp[r]);
@@ -415,14 +380,17 @@ size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals) {
     return groups * (size_t)(4 * npts) * REC_MAX * GROUP * sizeof(double);
 }
 
-// chunk = whole waves of all three kernels: the value kernel keeps 2 x 128 threads per SM resident (255 registers),
-// the light-column kernel 3 x 128 (168 registers), the tangent kernel 32 intervals per pass: 768 intervals per SM =
-// 3 / 2 waves / 24 passes.
+// chunk = whole waves of both kernels: the value kernel keeps 2 x 128 threads per SM resident (255 registers), the
+// tangent kernel 32 intervals per pass: 768 intervals per SM = 3 waves / 24 passes.
 int scvx_staged_chunk_intervals(int sm_count) { return sm_count * 768; }
 
 cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, void* scratch,
                                int chunk_intervals, int sm_count, cudaStream_t s, int* launches) {
     const long total = (long)(bt.n_nodes - 1) * bt.B;
+    {
+        cudaError_t e = cudaFuncSetAttribute(stage_value_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIGHT_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+    }
     const size_t smem = sizeof(StepSmem);
     {
         cudaError_t e = cudaFuncSetAttribute(tangent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -435,11 +403,10 @@ cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool a
         a.count = (int)((total - first < chunk_intervals) ? (total - first) : chunk_intervals);
         a.n_groups = (a.count + GROUP - 1) / GROUP;
         const int threads = a.n_groups * GROUP;
-        stage_value_kernel<<<(threads + 127) / 128, 128, 0, s>>>(a);
-        light_columns_kernel<<<(a.count + 127) / 128, 128, 0, s>>>(a);
+        stage_value_kernel<<<(threads + 127) / 128, 128, LIGHT_SMEM_BYTES, s>>>(a);
         const int grid = a.n_groups < sm_count ? a.n_groups : sm_count;
         tangent_kernel<<<grid, 256, smem, s>>>(a);
-        if (launches) *launches += 3;
+        if (launches) *launches += 2;
     }
     return cudaGetLastError();
 }
