@@ -403,10 +403,10 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
             const double2 c01 = ld2(J + J_V + 8 * row), c23 = ld2(J + J_V + 8 * row + 2);
             const double2 qa = ld2(J + J_V + 8 * row + 4), qb = ld2(J + J_V + 8 * row + 6);
             const double gg = Gc[1 + row];
-            kA[row] = fma(c01.x, FA.Y[0], fma(c01.y, FA.Y[1], fma(c23.x, FA.Y[2], fma(c23.y, FA.Y[3], alA * gg)))) +
-                      fma(qa.x, FA.Y[4], fma(qa.y, FA.Y[5], fma(qb.x, FA.Y[6], qb.y * FA.Y[7])));
-            kB[row] = fma(c01.x, FB.Y[0], fma(c01.y, FB.Y[1], fma(c23.x, FB.Y[2], fma(c23.y, FB.Y[3], alB * gg)))) +
-                      fma(qa.x, FB.Y[4], fma(qa.y, FB.Y[5], fma(qb.x, FB.Y[6], qb.y * FB.Y[7])));
+            kA[row] = fma(c01.x, FA.Y[0], fma(c01.y, FA.Y[1], fma(c23.x, FA.Y[2], fma(c23.y, FA.Y[3],
+                      fma(qa.x, FA.Y[4], fma(qa.y, FA.Y[5], fma(qb.x, FA.Y[6], fma(qb.y, FA.Y[7], alA * gg))))))));
+            kB[row] = fma(c01.x, FB.Y[0], fma(c01.y, FB.Y[1], fma(c23.x, FB.Y[2], fma(c23.y, FB.Y[3],
+                      fma(qa.x, FB.Y[4], fma(qa.y, FB.Y[5], fma(qb.x, FB.Y[6], fma(qb.y, FB.Y[7], alB * gg))))))));
         }
 #pragma unroll
         for (int r = 0; r < 3; ++r) { upd(FA, 1 + r, kA[r]); upd(FB, 1 + r, kB[r]); }
@@ -426,10 +426,10 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
         const double fq3 = J[J_FRQ + 6];
         double kA[4], kB[4];
 #define QROWS(F, K, ds)                                                                                                                     \
-        K[0] = fma(-hw0, F.Y[5], fma(-hw1, F.Y[6], fma(-hw2, F.Y[7], ds * fq0))) + fma(-hq1, F.Y[8], fma(-hq2, F.Y[9], -hq3 * F.Y[10]));     \
-        K[1] = fma(hw0, F.Y[4], fma(hw2, F.Y[6], fma(-hw1, F.Y[7], ds * fq12.x))) + fma(hq0, F.Y[8], fma(hq2, F.Y[10], -hq3 * F.Y[9]));      \
-        K[2] = fma(hw1, F.Y[4], fma(-hw2, F.Y[5], fma(hw0, F.Y[7], ds * fq12.y))) + fma(hq0, F.Y[9], fma(-hq1, F.Y[10], hq3 * F.Y[8]));      \
-        K[3] = fma(hw2, F.Y[4], fma(hw1, F.Y[5], fma(-hw0, F.Y[6], ds * fq3))) + fma(hq0, F.Y[10], fma(hq1, F.Y[9], -hq2 * F.Y[8]));
+        K[0] = fma(-hw0, F.Y[5], fma(-hw1, F.Y[6], fma(-hw2, F.Y[7], fma(-hq1, F.Y[8], fma(-hq2, F.Y[9], fma(-hq3, F.Y[10], ds * fq0))))));   \
+        K[1] = fma(hw0, F.Y[4], fma(hw2, F.Y[6], fma(-hw1, F.Y[7], fma(hq0, F.Y[8], fma(hq2, F.Y[10], fma(-hq3, F.Y[9], ds * fq12.x))))));    \
+        K[2] = fma(hw1, F.Y[4], fma(-hw2, F.Y[5], fma(hw0, F.Y[7], fma(hq0, F.Y[9], fma(-hq1, F.Y[10], fma(hq3, F.Y[8], ds * fq12.y))))));    \
+        K[3] = fma(hw2, F.Y[4], fma(hw1, F.Y[5], fma(-hw0, F.Y[6], fma(hq0, F.Y[10], fma(hq1, F.Y[9], fma(-hq2, F.Y[8], ds * fq3))))));
         QROWS(FA, kA, dsA)
         QROWS(FB, kB, 0.0)
 #undef QROWS
