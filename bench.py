@@ -115,6 +115,25 @@ class ClockSampler:
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPU cores NVML reports as local to GPU `index` (one process per GPU: keeps the pinned
+    staging buffers and the D2H traffic on the GPU's own NUMA node).  Best effort; returns a note for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(ClockSampler._physical_index(index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"bound to {len(cpus)} cores local to GPU {index}"
+    except Exception as e:          # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+    return "not bound"
+
+
 def cpu_reference_run(prob, steps, warmup, traj_per_thread):
     """The reference's CPU implementation of the path (oracle port), all host threads, bounded sample per step."""
     from oracle import oracle
@@ -191,6 +210,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_note = bind_to_gpu_numa(local_rank)     # before any pinned allocation: host buffers land next to the GPU
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
@@ -282,7 +302,8 @@ def main():
         e2e = {"value": total_intervals * e2e_steps / float(el.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(hX.nbytes + hU.nbytes + hS.nbytes),
                "d2h_bytes_per_step": int(hOut.nbytes + hErr.nbytes + hTlb.nbytes), "steps": e2e_steps,
-               "note": "pinned host buffers through scvx_linearize_batch; chunked H2D/kernel/D2H pipeline; PCIe-bound"}
+               "note": "pinned host buffers through scvx_linearize_batch; chunked H2D/kernel/D2H pipeline; PCIe-bound; "
+                       + numa_note}
         del hOut, hErr, hTlb
 
     if rank != 0:
