@@ -112,6 +112,16 @@ int scvx_predict_batch(scvx_ctx* ctx, const double* X, const double* U, const do
 int scvx_defect_cost_batch(scvx_ctx* ctx, const double* X, const double* lin_err, int n_nodes, int B, double wNu,
                            double* out_defect, double* out_cost);
 
+/* Batched initial guess: `linear_points` of the reference (initial_solve.jl:113-129) for B
+ * dispersed initial conditions.  Per trajectory b and node k = 0..K: mass, position and velocity on a straight line from
+ * (mwet_b, rIi_b, vIi_b) to (mdry, rIf, vIf); attitude = rotation_between([1,0,0], -v_k) (Rotations.jl, scalar-first
+ * quaternion); zero angular rate; control = [m_k * g, 0, 0].
+ *   rIi, vIi 3 x B;  mwet B (NULL: mwet_shared for every trajectory);  rIf, vIf 3 (host pointers, always)
+ *   X 14 x (K+1) x B, U 3 x (K+1) x B.  rIi/vIi/mwet/X/U are all host or all device pointers. */
+int scvx_linear_points_batch(scvx_ctx* ctx, const double* rIi, const double* vIi, const double* mwet, double mwet_shared,
+                             double mdry, const double* rIf, const double* vIf, double g, int K, int B,
+                             double* X, double* U);
+
 /* Stream used for device-pointer calls on the first device (a cudaStream_t; NULL = library stream). */
 int scvx_set_stream(scvx_ctx* ctx, void* cuda_stream);
 /* Kernel selection (SCVX_KERNEL_*). */

@@ -137,6 +137,23 @@ function defect_cost_batch(ctx::Context, X::Array{Float64,3}, lin_err::Array{Flo
     return defect, cost
 end
 
+# Batched initial guess: FirstRound.linear_points (reference initial_solve.jl:113-129) for B dispersed initial conditions.
+# rIi, vIi: 3 x B; mwet: per-trajectory wet masses or nothing.
+function linear_points_batch(ctx::Context, prob::DescentProblem, rIi::Matrix{Float64}, vIi::Matrix{Float64};
+                             mwet::Union{Nothing,Vector{Float64}}=nothing)
+    B, K = size(rIi, 2), prob.K
+    X = Array{Float64,3}(undef, 14, K + 1, B); U = Array{Float64,3}(undef, 3, K + 1, B)
+    rIf = Float64.(prob.rIf); vIf = Float64.(prob.vIf)
+    GC.@preserve rIi vIi mwet rIf vIf X U begin
+        check(ccall((:scvx_linear_points_batch, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble},
+                     Cdouble, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}),
+                    ctx.handle, rIi, vIi, mwet === nothing ? Ptr{Cdouble}(C_NULL) : pointer(mwet), prob.mwet, prob.mdry,
+                    rIf, vIf, prob.g, K, B, X, U))
+    end
+    return X, U
+end
+
 # IntegratorCache(prob, info) replacement (reference dynamics.jl:258-260): context + parameters + tables.
 # `aero_samples = (drag, lift, torque, aoa_range, mach_range)` are the matrices / ranges of aerodynamics.jl:17-21.
 function make_cache(prob::DescentProblem, info::ProbInfo; device_ids::Vector{Int}=[0], aero_samples=nothing)

@@ -38,6 +38,9 @@ SIGNATURES = {
                                           ctypes.c_void_p]),
     "scvx_defect_cost_batch": (ctypes.c_int, [_ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
+    "scvx_linear_points_batch": (ctypes.c_int, [_ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
+                                                ctypes.c_double, _dp, _dp, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_void_p, ctypes.c_void_p]),
     "scvx_set_stream": (ctypes.c_int, [_ctx_p, ctypes.c_void_p]),
     "scvx_set_kernel": (ctypes.c_int, [_ctx_p, ctypes.c_int]),
     "scvx_synchronize": (ctypes.c_int, [_ctx_p]),

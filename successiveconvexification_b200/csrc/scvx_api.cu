@@ -424,6 +424,41 @@ int scvx_defect_cost_batch(scvx_ctx* c, const double* X, const double* lin_err, 
     return 0;
 }
 
+int scvx_linear_points_batch(scvx_ctx* c, const double* rIi, const double* vIi, const double* mwet, double mwet_shared,
+                             double mdry, const double* rIf, const double* vIf, double g, int K, int B, double* X,
+                             double* U) {
+    if (!c) return fail(SCVX_ERR_ARG, "null context");
+    if (!rIi || !vIi || !rIf || !vIf || !X || !U) return fail(SCVX_ERR_ARG, "null array argument");
+    if (K < 1) return fail(SCVX_ERR_ARG, "K=%d must be >= 1", K);
+    if (B < 0) return fail(SCVX_ERR_ARG, "B=%d is negative", B);
+    if (B == 0) return 0;
+    const bool dev = is_device_ptr(rIi);
+    if (dev != is_device_ptr(vIi) || dev != is_device_ptr(X) || dev != is_device_ptr(U) || (mwet && dev != is_device_ptr(mwet)))
+        return fail(SCVX_ERR_ARG, "all array arguments must be either host or device pointers, not a mix");
+    Dev& d = c->devs[0];
+    CK(cudaSetDevice(d.id));
+    const size_t n = (size_t)(K + 1) * B;
+    if (dev) {
+        cudaStream_t s = c->have_user_stream ? c->user_stream : d.slot[0].stream;
+        CK(scvx_launch_linear_points(rIi, vIi, mwet, mwet_shared, mdry, rIf, vIf, g, K, B, X, U, s));
+        c->launches += 1;
+        return 0;
+    }
+    Slot& sl = d.slot[0];
+    CK(cudaStreamSynchronize(sl.stream));
+    if (grow(&sl.dX, &sl.capX, n * 14) || grow(&sl.dU, &sl.capU, n * 3) || grow(&sl.dS, &sl.capS, (size_t)7 * B)) return SCVX_ERR_NOMEM;
+    double *dr = sl.dS, *dv = sl.dS + (size_t)3 * B, *dm = sl.dS + (size_t)6 * B;
+    CK(cudaMemcpyAsync(dr, rIi, (size_t)3 * B * 8, cudaMemcpyHostToDevice, sl.stream));
+    CK(cudaMemcpyAsync(dv, vIi, (size_t)3 * B * 8, cudaMemcpyHostToDevice, sl.stream));
+    if (mwet) CK(cudaMemcpyAsync(dm, mwet, (size_t)B * 8, cudaMemcpyHostToDevice, sl.stream));
+    CK(scvx_launch_linear_points(dr, dv, mwet ? dm : nullptr, mwet_shared, mdry, rIf, vIf, g, K, B, sl.dX, sl.dU, sl.stream));
+    c->launches += 1;
+    CK(cudaMemcpyAsync(X, sl.dX, n * 14 * 8, cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaMemcpyAsync(U, sl.dU, n * 3 * 8, cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaStreamSynchronize(sl.stream));
+    return 0;
+}
+
 int scvx_set_stream(scvx_ctx* c, void* stream) {
     if (!c) return fail(SCVX_ERR_ARG, "null context");
     c->user_stream = (cudaStream_t)stream;

@@ -9,6 +9,9 @@ cudaError_t scvx_launch_prefilter(const double* d_samples, int n1, int n2, doubl
                                   const double* d_cp, cudaStream_t s);
 cudaError_t scvx_launch_defect_cost(const double* X, const double* lin_err, int n_nodes, int B, double wNu,
                                     double* out_defect, double* out_cost, cudaStream_t s);
+cudaError_t scvx_launch_linear_points(const double* rIi, const double* vIi, const double* mwet, double mwet_shared, double mdry,
+                                      const double* rIf, const double* vIf, double g, int K, int B, double* X, double* U,
+                                      cudaStream_t s);
 cudaError_t scvx_launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t s);
 
 // STAGED path (scvx_kernels_staged.cu): value kernel + persistent tangent kernel, chunked over a scratch buffer.

@@ -181,6 +181,39 @@ __global__ void __launch_bounds__(128) defect_cost_kernel(const double* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
+// Batched initial guess: linear_points (initial_solve.jl:113-129), one thread per (trajectory, node).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) linear_points_kernel(const double* __restrict__ rIi, const double* __restrict__ vIi,
+                                                            const double* __restrict__ mwet, double mwet_shared, double mdry,
+                                                            double rf0, double rf1, double rf2, double vf0, double vf1,
+                                                            double vf2, double g, int K, int B, double* __restrict__ X,
+                                                            double* __restrict__ U) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = K + 1;
+    if (t >= (long)n * B) return;
+    const int b = (int)(t / n), k = (int)(t - (long)b * n);
+    const double wa = (double)(K - k) / (double)K, wb = (double)k / (double)K;       // (K-k)/K and k/K, as the reference
+    const double mw = mwet ? mwet[b] : mwet_shared;
+    const double mk = wa * mw + wb * mdry;
+    const double rf[3] = { rf0, rf1, rf2 }, vf[3] = { vf0, vf1, vf2 };
+    double r[3], v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { r[c] = wa * rIi[(size_t)b * 3 + c] + wb * rf[c]; v[c] = wa * vIi[(size_t)b * 3 + c] + wb * vf[c]; }
+    // rotation_between(u = [1,0,0], w = -v): q = normalize([ |u||w| + u.w ; u x w ])
+    const double wv[3] = { -v[0], -v[1], -v[2] };
+    const double normprod = sqrt(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]);
+    double qw = normprod + wv[0];
+    double ax = 0.0, ay = -wv[2], az = wv[1];
+    if (fabs(qw) < 100.0 * 2.220446049250313e-16) { ax = 0.0; ay = 0.0; az = 1.0; }    // antiparallel: any axis perpendicular to u
+    const double qn = 1.0 / sqrt(qw * qw + ax * ax + ay * ay + az * az);
+    double* x = X + (size_t)t * 14;
+    x[0] = mk; x[1] = r[0]; x[2] = r[1]; x[3] = r[2]; x[4] = v[0]; x[5] = v[1]; x[6] = v[2];
+    x[7] = qw * qn; x[8] = ax * qn; x[9] = ay * qn; x[10] = az * qn; x[11] = 0.0; x[12] = 0.0; x[13] = 0.0;
+    double* u = U + (size_t)t * 3;
+    u[0] = mk * g; u[1] = 0.0; u[2] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
 cudaError_t scvx_launch_dualwarp(const ScvxBatch& bt, const ScvxTables& tb, cudaStream_t s) {
@@ -210,6 +243,16 @@ cudaError_t scvx_launch_defect_cost(const double* X, const double* lin_err, int 
     if (B <= 0) return cudaSuccess;
     const long threads = (long)B * 32;
     defect_cost_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(X, lin_err, n_nodes, B, wNu, out_defect, out_cost);
+    return cudaGetLastError();
+}
+
+cudaError_t scvx_launch_linear_points(const double* rIi, const double* vIi, const double* mwet, double mwet_shared, double mdry,
+                                      const double* rIf, const double* vIf, double g, int K, int B, double* X, double* U,
+                                      cudaStream_t s) {
+    const long threads = (long)(K + 1) * B;
+    if (threads <= 0) return cudaSuccess;
+    linear_points_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(rIi, vIi, mwet, mwet_shared, mdry, rIf[0], rIf[1],
+                                                                          rIf[2], vIf[0], vIf[1], vIf[2], g, K, B, X, U);
     return cudaGetLastError();
 }
 

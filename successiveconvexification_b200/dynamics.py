@@ -117,6 +117,12 @@ class DeviceContext:
         _lib.check(self._lib.scvx_defect_cost_batch(self._h, X, lin_err, n_nodes, B, float(wNu), out_defect,
                                                     out_cost or None))
 
+    def linear_points_ptr(self, rIi, vIi, mwet, mwet_shared, mdry, rIf, vIf, g, K, B, X, U):
+        rf = (ctypes.c_double * 3)(*[float(v) for v in rIf])
+        vf = (ctypes.c_double * 3)(*[float(v) for v in vIf])
+        _lib.check(self._lib.scvx_linear_points_batch(self._h, rIi, vIi, mwet or None, float(mwet_shared), float(mdry), rf, vf,
+                                                      float(g), int(K), int(B), X, U))
+
     def predict_ptr(self, X, U, sigma, base_dt, npts, mode, n_nodes, B, out):
         _lib.check(self._lib.scvx_predict_batch(self._h, X, U, sigma, base_dt, npts, mode, n_nodes, B, out))
 
@@ -200,6 +206,22 @@ def defect_cost(cache: IntegratorCache, X, lin_err, wNu: float):
     defect, cost = np.empty(B), np.empty(B)
     ctx.defect_cost_ptr(X.ctypes.data, lin_err.ctypes.data, n_nodes, B, wNu, defect.ctypes.data, cost.ctypes.data)
     return defect, cost
+
+
+def linear_points_batch(cache: IntegratorCache, problem: DescentProblem, rIi, vIi, mwet=None):
+    """Batched `linear_points` (initial_solve.jl:113-129) on the device for B dispersed initial conditions:
+    rIi, vIi (B, 3), optional per-trajectory mwet (B,).  -> X (B, K+1, 14), U (B, K+1, 3)."""
+    ctx = _ctx(cache)
+    rIi = np.ascontiguousarray(rIi, dtype=np.float64)
+    vIi = np.ascontiguousarray(vIi, dtype=np.float64)
+    B, K = rIi.shape[0], problem.K
+    if rIi.shape != (B, 3) or vIi.shape != (B, 3):
+        raise ValueError("expected rIi, vIi of shape (B, 3)")
+    mw = None if mwet is None else np.ascontiguousarray(mwet, dtype=np.float64)
+    X, U = np.empty((B, K + 1, 14)), np.empty((B, K + 1, 3))
+    ctx.linear_points_ptr(rIi.ctypes.data, vIi.ctypes.data, mw.ctypes.data if mw is not None else 0, problem.mwet,
+                          problem.mdry, problem.rIf, problem.vIf, problem.g, K, B, X.ctypes.data, U.ctypes.data)
+    return X, U
 
 
 def blocks_to_linres(blocks_one_traj: np.ndarray):

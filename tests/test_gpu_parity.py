@@ -211,6 +211,45 @@ def test_fused_defect_cost(dyn, cache_aero, prob_aero):
     assert dD.cpu().numpy() == pytest.approx(ref_d, rel=1e-12)
 
 
+def test_batched_initial_guess(dyn, cache_aero, prob_aero):
+    """linear_points (initial_solve.jl:113-129) for a batch of dispersed initial conditions."""
+    from successiveconvexification_b200 import workloads
+    from successiveconvexification_b200.first_round import linear_points
+    rng = np.random.default_rng(21)
+    B = 257
+    rIi = prob_aero.rIi[None] + rng.normal(0, 0.05, (B, 3))
+    vIi = prob_aero.vIi[None] + rng.normal(0, 0.02, (B, 3))
+    mwet = prob_aero.mwet * rng.uniform(0.9, 1.1, B)
+    X, U = dyn.linear_points_batch(cache_aero, prob_aero, rIi, vIi, mwet)
+    Xh, Uh = workloads.linear_points_batch(prob_aero, prob_aero.K, rIi, vIi, mwet)
+    assert np.abs(X - Xh).max() <= 1e-14 and np.abs(U - Uh).max() <= 1e-16
+    # the reference's scalar routine on one perturbed problem
+    p1 = prob_aero.replace(rIi=rIi[3], vIi=vIi[3], mwet=float(mwet[3]))
+    pts = linear_points(p1)
+    assert np.abs(X[3] - np.stack([p.state for p in pts])).max() <= 1e-14
+    assert np.abs(U[3] - np.stack([p.control for p in pts])).max() <= 1e-16
+    # shared wet mass + the unperturbed sample problem reproduces C2's nodes
+    X0, U0 = dyn.linear_points_batch(cache_aero, prob_aero, prob_aero.rIi[None], prob_aero.vIi[None])
+    Xs, Us, _, _ = workloads.sample_trajectory(prob_aero)
+    assert np.abs(X0 - Xs).max() <= 1e-15 and np.abs(U0 - Us).max() <= 1e-17
+
+
+def test_multi_device_context_shards_by_trajectory(dyn, prob_aero, cache_aero):
+    """One context over several GPUs (a single Julia process driving a whole node): host-pointer calls are sharded in
+    contiguous trajectory blocks; the result equals the single-device result bit for bit."""
+    from successiveconvexification_b200 import _lib, workloads
+    n_dev = _lib.load().scvx_device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least two CUDA devices")
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, 50, 1500, 55, sigma_range=(0.8, 1.5))
+    cache_aero.sim_prob.set_kernel(0)
+    one, err1, tlb1 = dyn.linearize_batch(cache_aero, X, U, sigma, 1 / 51)
+    multi = dyn.make_cache(prob_aero, device_ids=list(range(n_dev)))
+    many, errn, tlbn = dyn.linearize_batch(multi, X, U, sigma, 1 / 51)
+    assert np.array_equal(one, many) and np.array_equal(err1, errn) and np.array_equal(tlb1, tlbn)
+    assert np.array_equal(dyn.predict_batch(multi, X, U, sigma, 1 / 51), dyn.predict_batch(cache_aero, X, U, sigma, 1 / 51))
+
+
 def test_edge_cases_and_errors(dyn, cache_aero, prob_aero):
     from successiveconvexification_b200 import _lib, workloads
     X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, 1, 3, 8, sigma_range=(0.8, 1.5))     # n_nodes = 2
