@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -191,7 +192,8 @@ int run(scvx_ctx* c, bool predict, const double* X, const double* U, const doubl
     // Host pointers: contiguous trajectory blocks per device, chunked + double-buffered inside a device.
     const int nd = (int)c->devs.size();
     const size_t per_traj_out = predict ? (size_t)ni * 14 : (size_t)ni * SCVX_BLOCK_DOUBLES;
-    long chunk = (long)((size_t)(64u << 20) / (per_traj_out * sizeof(double)));   // ~64 MiB of output per chunk
+    static const long chunk_mb = getenv("SCVX_HOST_CHUNK_MB") ? atol(getenv("SCVX_HOST_CHUNK_MB")) : 256;
+    long chunk = (long)(((size_t)chunk_mb << 20) / (per_traj_out * sizeof(double)));   // output per pipeline chunk (D2H saturates this pool's PCIe at ~43 GB/s from 128 MiB up, profiles/e2e_sweep.py)
     chunk = std::max(1L, chunk);
     for (int di = 0; di < nd; ++di) {
         Dev& d = c->devs[di];
