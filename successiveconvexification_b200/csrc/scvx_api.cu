@@ -195,13 +195,20 @@ int run(scvx_ctx* c, bool predict, const double* X, const double* U, const doubl
     static const long chunk_mb = getenv("SCVX_HOST_CHUNK_MB") ? atol(getenv("SCVX_HOST_CHUNK_MB")) : 256;
     long chunk = (long)(((size_t)chunk_mb << 20) / (per_traj_out * sizeof(double)));   // output per pipeline chunk (D2H saturates this pool's PCIe at ~43 GB/s from 128 MiB up, profiles/e2e_sweep.py)
     chunk = std::max(1L, chunk);
+    // chunk index outermost, devices innermost: every device gets its c-th chunk enqueued before any device gets its
+    // (c+1)-th, so the slot-reuse waits of one device never hold back the others (all devices run concurrently)
+    long max_chunks = 0;
     for (int di = 0; di < nd; ++di) {
-        Dev& d = c->devs[di];
         const long b0 = (long)B * di / nd, b1 = (long)B * (di + 1) / nd;
-        if (b1 <= b0) continue;
-        CK(cudaSetDevice(d.id));
-        int ci = 0;
-        for (long cb = b0; cb < b1; cb += chunk, ++ci) {
+        max_chunks = std::max(max_chunks, (b1 - b0 + chunk - 1) / chunk);
+    }
+    for (long ci = 0; ci < max_chunks; ++ci) {
+        for (int di = 0; di < nd; ++di) {
+            Dev& d = c->devs[di];
+            const long b0 = (long)B * di / nd, b1 = (long)B * (di + 1) / nd;
+            const long cb = b0 + ci * chunk;
+            if (cb >= b1) continue;
+            CK(cudaSetDevice(d.id));
             const int nb = (int)std::min(chunk, b1 - cb);
             Slot& sl = d.slot[ci & 1];
             CK(cudaStreamSynchronize(sl.stream));       // previous user of this slot has drained its D2H
