@@ -9,8 +9,9 @@
 //      force together with its Jacobians dF/dv, dF/db (b = C(q) e1).  Writes the endpoint (block column 0), lin_err,
 //      the thrust-lower-bound rows and a 43-double "stage record" per stage (stage state m,v,q,w; stage control u;
 //      unscaled rhs f; dF/dv; dF/db), laid out [group of 32 intervals][stage][entry][32 lanes] so that one stage of
-//      one group is one contiguous 11 KB slab (= one TMA bulk copy).  It also carries the four light tangent columns
-//      d/d(m, v) (state in shared memory), the constant position columns and the partial z.
+//      one group is one contiguous 11 KB slab (= one TMA bulk copy).  It also carries two of the four light tangent
+//      columns (d/dv1, d/dv2; state in shared memory), the constant position columns and the partial z; the other two
+//      (d/dm, d/dv0) ride in the two otherwise idle column slots of the tangent kernel.
 //
 //  B   tangent_kernel       : persistent, one 256-thread CTA per SM, 32 intervals per pass.  The 14 heavy tangent
 //      columns: 8 lanes per interval, two full columns per lane, tangent state (S, accumulator, stage tangent, r-row
@@ -27,14 +28,14 @@ namespace {
 #ifndef SCVX_A_MINBLOCKS
 #define SCVX_A_MINBLOCKS 2
 #endif
-// The kernel also propagates the four light tangent columns d/d(m, v0, v1, v2) (only their v and r rows are non-trivial:
-// K_v = Jvv Y_v (+ Jvm for the mass column), r rows a quadrature of the v rows).  Their 48 doubles of state live in
-// shared memory, lane-private [entry][thread] (conflict-free), because the value chain already uses every register;
+// The kernel also propagates two of the four light tangent columns d/d(m, v0, v1, v2) — d/dv1 and d/dv2 (only their v
+// and r rows are non-trivial: K_v = Jvv Y_v, r rows a quadrature of the v rows; d/dm and d/dv0 ride in the two idle
+// slots of the tangent kernel).  Their 24 doubles of state live in shared memory, lane-private [entry][thread] (conflict-free), because the value chain already uses every register;
 // the Jacobian blocks they need (dF/dv, f_v, m) are at hand here, so no separate pass re-reads the stage records
 // (a separate one-thread-per-interval kernel was latency bound on those reads: 0.13 ms per chunk vs +0.03 ms here).
-constexpr size_t LIGHT_SMEM_BYTES = 48 * 128 * sizeof(double);
+constexpr size_t LIGHT_SMEM_BYTES = 24 * 128 * sizeof(double);
 __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(StagedArgs a) {
-    extern __shared__ double light_smem[];            // [48][128] doubles
+    extern __shared__ double light_smem[];            // [24][128] doubles
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n_groups * GROUP) return;
     const ScvxBatch& bt = a.bt;
@@ -57,19 +58,18 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
     const double h = bt.dt / (double)bt.npts;
     const double pcs = 1.0 / (double)bt.npts;
     const double s = (bt.mode == SCVX_MODE_LITERAL) ? 1.0 : h;
-    // light-column state: L[(c*12 + kind*3 + r)*128 + tid], kind 0 = S, 1 = acc, 2 = Y, 3 = r-row sum
+    // light-column state (columns d/dv1, d/dv2): L[(c*12 + kind*3 + r)*128 + tid], kind 0 = S, 1 = acc, 2 = Y, 3 = r-row sum
     double* L = light_smem + threadIdx.x;
     {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const double s0 = (c == r + 1) ? 1.0 : 0.0;
+                const double s0 = (c + 1 == r) ? 1.0 : 0.0;
                 L[(c * 12 + 0 + r) * 128] = s0; L[(c * 12 + 3 + r) * 128] = 0.0;
                 L[(c * 12 + 6 + r) * 128] = s0; L[(c * 12 + 9 + r) * 128] = 0.0;
             }
     }
-    const double g0 = __ldg(&P.g0);
     double pca = 0.0;
     for (int it = 0; it < bt.npts; ++it) {
         double acc[14], y[14];
@@ -106,22 +106,20 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
             {
                 const double smv = sigma / y[0];
                 const double csg = h * (1.0 / 6.0) * wgt * sigma;
-                double Jvv[3][3], Jvm[3];
+                double Jvv[3][3];
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    Jvm[r] = -smv * (f[4 + r] + (r == 0 ? g0 : 0.0));
+                for (int r = 0; r < 3; ++r)
 #pragma unroll
                     for (int c = 0; c < 3; ++c) Jvv[r][c] = smv * Fv[r][c];
-                }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     double* Lc = L + c * 12 * 128;
                     const double y0 = Lc[6 * 128], y1 = Lc[7 * 128], y2 = Lc[8 * 128];
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
                         const double yr = (r == 0) ? y0 : (r == 1 ? y1 : y2);
                         Lc[(9 + r) * 128] = fma(csg, yr, Lc[(9 + r) * 128]);
-                        const double K = fma(Jvv[r][0], y0, fma(Jvv[r][1], y1, fma(Jvv[r][2], y2, c == 0 ? Jvm[r] : 0.0)));
+                        const double K = fma(Jvv[r][0], y0, fma(Jvv[r][1], y1, Jvv[r][2] * y2));
                         if (st != 3) {
                             Lc[(3 + r) * 128] = fma(wgt, K, Lc[(3 + r) * 128]);
                             Lc[(6 + r) * 128] = fma(cy, K, Lc[r * 128]);
@@ -148,20 +146,20 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
 #pragma unroll
     for (int r = 0; r < 14; r += 2) *reinterpret_cast<double2*>(blk + r) = make_double2(x[r], x[r + 1]);
     {
-        // columns d/d(m, r, v) of the block and the partial z = endpoint - D[:, m r v] * inp[m r v]
+        // columns d/d(r, v1, v2) of the block and the partial z = endpoint - D[:, r v1 v2] * inp[r v1 v2]
+        // (the columns d/dm and d/dv0 ride in the two otherwise idle slots of the tangent kernel)
         double z[7];
 #pragma unroll
         for (int r = 0; r < 7; ++r) z[r] = x[r];
-        z[0] -= xin[0];
 #pragma unroll
-        for (int c = 0; c < 7; ++c) {               // inp 0 (m), 1..3 (r), 4..6 (v)
+        for (int c = 1; c < 7; ++c) {               // inp 1..3 (r), 5..6 (v1, v2)
+            if (c == 4) continue;
             double col[14];
 #pragma unroll
             for (int r = 0; r < 14; ++r) col[r] = 0.0;
-            if (c == 0 || c >= 4) {
-                const double* Lc = L + (c == 0 ? 0 : c - 3) * 12 * 128;
+            if (c >= 5) {
+                const double* Lc = L + (c - 5) * 12 * 128;
                 const double xc = xin[c];
-                if (c == 0) col[0] = 1.0;
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     col[1 + r] = Lc[(9 + r) * 128]; col[4 + r] = Lc[r * 128];
@@ -245,11 +243,11 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
 
     int colA = -1, colB = -1, gcol = 3;
     if (l8 < 3) { colA = 14 + l8; colB = 17 + l8; gcol = l8; }
-    else if (l8 == 3) colA = 20;
+    else if (l8 == 3) { colA = 20; colB = 0; }          // sigma column | light column d/dm
     else if (l8 == 4) { colA = 11; colB = 12; }
     else if (l8 == 5) { colA = 13; colB = 7; }
     else if (l8 == 6) { colA = 8; colB = 9; }
-    else colA = 10;
+    else { colA = 10; colB = 4; }                        // q3 column | light column d/dv0
 
     const int kq = warp & 3;                            // stage (within a step) this warp produces
     auto issue_record = [&](int n) {                    // one lane: TMA the record of (global step n, stage kq)
@@ -289,8 +287,9 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
         const int g = blockIdx.x + it * gridDim.x;
 #pragma unroll
         for (int r = 0; r < 11; ++r) {
-            FA.S[r] = (r >= 4 && colA == r + 3) ? 1.0 : 0.0;       // local rows: 0 m, 1..3 v, 4..7 q, 8..10 w
-            FB.S[r] = (r >= 4 && colB == r + 3) ? 1.0 : 0.0;
+            // identity part of S(0) = [I | 0]; local rows 0 m, 1..3 v, 4..7 q, 8..10 w <-> inp columns 0, 4..6, 7..10, 11..13
+            FA.S[r] = (colA == r + 3 && r >= 1) ? 1.0 : 0.0;
+            FB.S[r] = ((colB == r + 3 && r >= 1) || (colB == 0 && r == 0)) ? 1.0 : 0.0;
             FA.A[r] = 0.0; FB.A[r] = 0.0;
             FA.Y[r] = FA.S[r]; FB.Y[r] = FB.S[r];
         }
