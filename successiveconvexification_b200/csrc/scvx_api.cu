@@ -125,6 +125,8 @@ int launch_linearize(scvx_ctx* c, Dev& d, const ScvxBatch& bt, cudaStream_t s) {
     // pipeline stream must have consumed it before it is overwritten.
     const long total = (long)(bt.n_nodes - 1) * bt.B;
     int chunk = scvx_staged_chunk_intervals(d.sm_count);
+    // keep the stage-record scratch below ~4 GiB for long integrations (npts >> 10): whole tangent passes per SM
+    while (chunk > d.sm_count * 32 && scvx_staged_scratch_bytes(bt.npts, chunk) > ((size_t)4 << 30)) chunk -= d.sm_count * 32;
     if (total < chunk) chunk = (int)((total + 31) / 32 * 32);
     const size_t need = scvx_staged_scratch_bytes(bt.npts, chunk);
     if (need > d.scratch_cap) {
@@ -164,6 +166,8 @@ int run(scvx_ctx* c, bool predict, const double* X, const double* U, const doubl
     if (mode != SCVX_MODE_LITERAL && mode != SCVX_MODE_TEXTBOOK) return fail(SCVX_ERR_ARG, "unknown mode %d", mode);
     if (!(dt > 0.0)) return fail(SCVX_ERR_ARG, "base_dt must be positive");
     if (B == 0) return 0;
+    if ((long)(n_nodes - 1) * (long)B >= (1L << 31) - 64)
+        return fail(SCVX_ERR_ARG, "(n_nodes-1)*B = %ld intervals exceed the 2^31 limit of one call", (long)(n_nodes - 1) * (long)B);
     if (int rc = check_ready(c, B)) return rc;
     const int ni = n_nodes - 1;
     const int nP = (int)c->hP.size();

@@ -250,6 +250,20 @@ def test_multi_device_context_shards_by_trajectory(dyn, prob_aero, cache_aero):
     assert np.array_equal(dyn.predict_batch(multi, X, U, sigma, 1 / 51), dyn.predict_batch(cache_aero, X, U, sigma, 1 / 51))
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("npts", [1, 3, 16])
+def test_other_substep_counts(dyn, cache_aero, prob_aero, oracle_tables, kernel, npts):
+    """`npts` is a run-time knob of rk4 (dynamics.jl:112, default 10)."""
+    from successiveconvexification_b200 import workloads
+    cache_aero.sim_prob.set_kernel(kernel)
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, 7, 9, 123, sigma_range=(0.8, 1.5))
+    for mode in (0, 1):
+        blocks, err, _ = dyn.linearize_batch(cache_aero, X, U, sigma, 1 / 8, npts, mode)
+        ref, rerr, _, _ = _oracle().linearize_batch(P, oracle_tables, X, U, sigma, 1 / 8, npts, mode)
+        assert_parity(blocks, ref)
+        assert np.abs(err - rerr).max() <= 1e-12 * max(1.0, np.abs(rerr).max())
+
+
 def test_edge_cases_and_errors(dyn, cache_aero, prob_aero):
     from successiveconvexification_b200 import _lib, workloads
     X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, 1, 3, 8, sigma_range=(0.8, 1.5))     # n_nodes = 2
