@@ -122,6 +122,25 @@ int scvx_linear_points_batch(scvx_ctx* ctx, const double* rIi, const double* vIi
                              double mdry, const double* rIf, const double* vIf, double g, int K, int B,
                              double* X, double* U);
 
+/* Fixed-pattern sparse SOCP rows.  The reference refreshes the K dynamics equality blocks
+ * (rocketland.jl:117-133, 251-258) and the K+1 linearised thrust-lower-bound rows (rocketland.jl:194-201, 260-265)
+ * with K*21 + 3(K+1) MOI.modify calls per iteration; their sparsity never changes.  These entry points give that
+ * sub-matrix in compressed-sparse-column form for a direct conic-solver interface (ECOS-style A, b / G, h):
+ *   rows     14n + i (dynamics row i of interval n, Zeros cone), then 14K + n (thrust lower bound of node n, Nonpositives)
+ *   columns  dxv[j,n] -> 14n + j;  duv[j,n] -> 14(K+1) + 3n + j;  dsig -> 17(K+1);  nuv[j,n] -> 17(K+1) + 1 + 14n + j
+ *            (the reference's variable creation order, rocketland.jl:73-76: local column j = its variable 17(K+1) + j)
+ *   values   A_n, B-_n, B+_n, Sigma_n (all 14 x 21 entries, structural zeros kept as eachcol() emits them), +1 on
+ *            nuv[:,n+1], -1 on dxv[:,n+1], H_n = -u_n/|u_n| on duv[:,n];  constants  rhs = [lin_err ; Tmin - |u_n|]
+ * with K = n_nodes - 1, n_rows = 15K + 1, n_cols = 31(K+1) + 1, nnz = 325K + 3. */
+int scvx_socp_dims(int n_nodes, int* n_rows, int* n_cols, int* nnz);
+/* Pattern (host arrays, no device work): colptr n_cols + 1, rowind nnz; rows ascend inside a column. */
+int scvx_socp_pattern(int n_nodes, int32_t* colptr, int32_t* rowind);
+/* Values for B trajectories from the outputs of scvx_linearize_batch at the same inputs:
+ *   blocks 14 x 23 x K x B, lin_err 14 x K x B, tlb 4 x n_nodes x B  ->  out_vals nnz x B, out_rhs n_rows x B (may be NULL;
+ *   lin_err may be NULL then).  All host or all device pointers (device: enqueued on the context's stream). */
+int scvx_socp_values_batch(scvx_ctx* ctx, const double* blocks, const double* lin_err, const double* tlb, int n_nodes, int B,
+                           double* out_vals, double* out_rhs);
+
 /* Stream used for device-pointer calls on the first device (a cudaStream_t; NULL = library stream). */
 int scvx_set_stream(scvx_ctx* ctx, void* cuda_stream);
 /* Kernel selection (SCVX_KERNEL_*). */

@@ -154,6 +154,30 @@ function linear_points_batch(ctx::Context, prob::DescentProblem, rIi::Matrix{Flo
     return X, U
 end
 
+# Fixed-pattern sparse form of the trajectory-dependent SOCP rows (reference rocketland.jl:117-133, 194-201, 251-265):
+# CSC pattern (1-based for SparseMatrixCSC) and, per trajectory, the value array + constants.  Local column j is the
+# reference's variable 17(K+1) + j (dxv, duv, dsig, nuv are created consecutively, rocketland.jl:73-76).
+function socp_pattern(n_nodes::Integer)
+    nr = Ref{Cint}(0); nc = Ref{Cint}(0); nz = Ref{Cint}(0)
+    check(ccall((:scvx_socp_dims, LIB), Cint, (Cint, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), n_nodes, nr, nc, nz))
+    colptr = Vector{Int32}(undef, nc[] + 1); rowind = Vector{Int32}(undef, nz[])
+    check(ccall((:scvx_socp_pattern, LIB), Cint, (Cint, Ptr{Int32}, Ptr{Int32}), n_nodes, colptr, rowind))
+    return Int(nr[]), Int(nc[]), colptr .+ Int32(1), rowind .+ Int32(1)
+end
+
+function socp_values_batch(ctx::Context, blocks::Array{Float64,4}, lin_err::Array{Float64,3}, tlb::Array{Float64,3})
+    n_nodes, B = size(tlb, 2), size(tlb, 3)
+    nr = Ref{Cint}(0); nc = Ref{Cint}(0); nz = Ref{Cint}(0)
+    check(ccall((:scvx_socp_dims, LIB), Cint, (Cint, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), n_nodes, nr, nc, nz))
+    vals = Matrix{Float64}(undef, nz[], B); rhs = Matrix{Float64}(undef, nr[], B)
+    GC.@preserve blocks lin_err tlb vals rhs begin
+        check(ccall((:scvx_socp_values_batch, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}),
+                    ctx.handle, blocks, lin_err, tlb, n_nodes, B, vals, rhs))
+    end
+    return vals, rhs
+end
+
 # IntegratorCache(prob, info) replacement (reference dynamics.jl:258-260): context + parameters + tables.
 # `aero_samples = (drag, lift, torque, aoa_range, mach_range)` are the matrices / ranges of aerodynamics.jl:17-21.
 function make_cache(prob::DescentProblem, info::ProbInfo; device_ids::Vector{Int}=[0], aero_samples=nothing)

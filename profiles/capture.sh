@@ -2,7 +2,7 @@
 # Round-1 profile capture (run under gpurun on one B200).  Follows /opt/skills/guides/B200_PROFILING.md:
 # every ncu run is preceded by the same command exiting 0 without ncu; numbers printed under ncu are never bench values.
 set -u
-C="python bench.py --steps 2 --warmup 3 --traj-per-gpu 8192 --no-e2e --no-cpu"
+C="python bench.py --steps 2 --warmup 3 --traj-per-gpu 8192 --no-e2e --no-cpu --no-assembly"
 O=gpurun_out
 $C > $O/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 23 -c 24 --csv --log-file $O/r1_launches.csv $C > $O/ncu_launches.log 2>&1

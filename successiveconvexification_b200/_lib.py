@@ -41,6 +41,11 @@ SIGNATURES = {
     "scvx_linear_points_batch": (ctypes.c_int, [_ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
                                                 ctypes.c_double, _dp, _dp, ctypes.c_double, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_void_p, ctypes.c_void_p]),
+    "scvx_socp_dims": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                      ctypes.POINTER(ctypes.c_int)]),
+    "scvx_socp_pattern": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    "scvx_socp_values_batch": (ctypes.c_int, [_ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "scvx_set_stream": (ctypes.c_int, [_ctx_p, ctypes.c_void_p]),
     "scvx_set_kernel": (ctypes.c_int, [_ctx_p, ctypes.c_int]),
     "scvx_synchronize": (ctypes.c_int, [_ctx_p]),

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libscvx_b200.so")
-SOURCES = ["scvx_api.cu", "scvx_kernels_basic.cu", "scvx_kernels_staged.cu"]
+SOURCES = ["scvx_api.cu", "scvx_kernels_basic.cu", "scvx_kernels_staged.cu", "scvx_kernels_socp.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--fmad=true", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 

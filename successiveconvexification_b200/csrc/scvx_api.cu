@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "scvx_kernels.h"
+#include "scvx_socp_pattern.h"
 
 namespace {
 
@@ -469,6 +470,74 @@ int scvx_linear_points_batch(scvx_ctx* c, const double* rIi, const double* vIi, 
     CK(cudaMemcpyAsync(X, sl.dX, n * 14 * 8, cudaMemcpyDeviceToHost, sl.stream));
     CK(cudaMemcpyAsync(U, sl.dU, n * 3 * 8, cudaMemcpyDeviceToHost, sl.stream));
     CK(cudaStreamSynchronize(sl.stream));
+    return 0;
+}
+
+int scvx_socp_dims(int n_nodes, int* n_rows, int* n_cols, int* nnz) {
+    if (n_nodes < 2) return fail(SCVX_ERR_ARG, "n_nodes=%d: at least two nodes are required", n_nodes);
+    if (n_nodes > 6000000) return fail(SCVX_ERR_ARG, "n_nodes=%d: value indices would exceed 32 bits", n_nodes);
+    const int K = n_nodes - 1;
+    if (n_rows) *n_rows = socp_rows(K);
+    if (n_cols) *n_cols = socp_cols(K);
+    if (nnz) *nnz = socp_nnz(K);
+    return 0;
+}
+
+int scvx_socp_pattern(int n_nodes, int32_t* colptr, int32_t* rowind) {
+    if (!colptr || !rowind) return fail(SCVX_ERR_ARG, "colptr and rowind must be non-null");
+    if (int rc = scvx_socp_dims(n_nodes, nullptr, nullptr, nullptr)) return rc;
+    const int K = n_nodes - 1, nnz = socp_nnz(K), nc = socp_cols(K);
+    for (int j = 0; j <= nc; ++j) colptr[j] = 0;
+    for (int p = 0; p < nnz; ++p) {
+        const SocpEntry e = socp_decode(p, K);
+        rowind[p] = e.row;
+        colptr[e.col + 1] += 1;
+    }
+    for (int j = 0; j < nc; ++j) colptr[j + 1] += colptr[j];
+    return 0;
+}
+
+int scvx_socp_values_batch(scvx_ctx* c, const double* blocks, const double* lin_err, const double* tlb, int n_nodes, int B,
+                           double* out_vals, double* out_rhs) {
+    if (!c) return fail(SCVX_ERR_ARG, "null context");
+    if (!blocks || !tlb || !out_vals) return fail(SCVX_ERR_ARG, "blocks, tlb and out_vals must be non-null");
+    if (out_rhs && !lin_err) return fail(SCVX_ERR_ARG, "out_rhs needs lin_err");
+    if (int rc = scvx_socp_dims(n_nodes, nullptr, nullptr, nullptr)) return rc;
+    if (B < 0) return fail(SCVX_ERR_ARG, "B=%d is negative", B);
+    if (B == 0) return 0;
+    const bool dev = is_device_ptr(blocks);
+    if (dev != is_device_ptr(tlb) || dev != is_device_ptr(out_vals) || (lin_err && dev != is_device_ptr(lin_err)) ||
+        (out_rhs && dev != is_device_ptr(out_rhs)))
+        return fail(SCVX_ERR_ARG, "all array arguments must be either host or device pointers, not a mix");
+    const int K = n_nodes - 1;
+    const size_t nnz = socp_nnz(K), nr = socp_rows(K), nblk = (size_t)K * SCVX_BLOCK_DOUBLES, nerr = (size_t)14 * K, ntlb = (size_t)4 * n_nodes;
+    Dev& d = c->devs[0];
+    CK(cudaSetDevice(d.id));
+    if (dev) {
+        cudaStream_t s = c->have_user_stream ? c->user_stream : d.slot[0].stream;
+        CK(scvx_launch_socp_values(blocks, lin_err, tlb, n_nodes, B, out_vals, out_rhs, s));
+        c->launches += 1;
+        return 0;
+    }
+    // host pointers: trajectory chunks through the two pipeline slots of the first device
+    long chunk = std::max(1L, (long)(((size_t)128 << 20) / (nblk * sizeof(double))));
+    for (long cb = 0, ci = 0; cb < B; cb += chunk, ++ci) {
+        const int nb = (int)std::min(chunk, (long)B - cb);
+        Slot& sl = d.slot[ci & 1];
+        CK(cudaStreamSynchronize(sl.stream));
+        if (grow(&sl.dOut, &sl.capOut, nb * nblk) || grow(&sl.dTlb, &sl.capTlb, nb * ntlb) || grow(&sl.dEnd, &sl.capEnd, nb * nnz) ||
+            (out_rhs && (grow(&sl.dErr, &sl.capErr, nb * nerr) || grow(&sl.dX, &sl.capX, nb * nr))))
+            return SCVX_ERR_NOMEM;
+        CK(cudaMemcpyAsync(sl.dOut, blocks + cb * nblk, nb * nblk * 8, cudaMemcpyHostToDevice, sl.stream));
+        CK(cudaMemcpyAsync(sl.dTlb, tlb + cb * ntlb, nb * ntlb * 8, cudaMemcpyHostToDevice, sl.stream));
+        if (out_rhs) CK(cudaMemcpyAsync(sl.dErr, lin_err + cb * nerr, nb * nerr * 8, cudaMemcpyHostToDevice, sl.stream));
+        CK(scvx_launch_socp_values(sl.dOut, out_rhs ? sl.dErr : nullptr, sl.dTlb, n_nodes, nb, sl.dEnd, out_rhs ? sl.dX : nullptr, sl.stream));
+        c->launches += 1;
+        CK(cudaMemcpyAsync(out_vals + cb * nnz, sl.dEnd, nb * nnz * 8, cudaMemcpyDeviceToHost, sl.stream));
+        if (out_rhs) CK(cudaMemcpyAsync(out_rhs + cb * nr, sl.dX, nb * nr * 8, cudaMemcpyDeviceToHost, sl.stream));
+    }
+    CK(cudaStreamSynchronize(d.slot[0].stream));
+    CK(cudaStreamSynchronize(d.slot[1].stream));
     return 0;
 }
 

@@ -12,6 +12,8 @@ cudaError_t scvx_launch_defect_cost(const double* X, const double* lin_err, int 
 cudaError_t scvx_launch_linear_points(const double* rIi, const double* vIi, const double* mwet, double mwet_shared, double mdry,
                                       const double* rIf, const double* vIf, double g, int K, int B, double* X, double* U,
                                       cudaStream_t s);
+cudaError_t scvx_launch_socp_values(const double* blocks, const double* lin_err, const double* tlb, int n_nodes, int B,
+                                    double* vals, double* rhs, cudaStream_t s);
 cudaError_t scvx_launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t s);
 
 // STAGED path (scvx_kernels_staged.cu): value kernel + persistent tangent kernel, chunked over a scratch buffer.

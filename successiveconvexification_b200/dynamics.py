@@ -123,6 +123,10 @@ class DeviceContext:
         _lib.check(self._lib.scvx_linear_points_batch(self._h, rIi, vIi, mwet or None, float(mwet_shared), float(mdry), rf, vf,
                                                       float(g), int(K), int(B), X, U))
 
+    def socp_values_ptr(self, blocks, lin_err, tlb, n_nodes, B, out_vals, out_rhs=0):
+        _lib.check(self._lib.scvx_socp_values_batch(self._h, blocks, lin_err or None, tlb, n_nodes, B, out_vals,
+                                                    out_rhs or None))
+
     def predict_ptr(self, X, U, sigma, base_dt, npts, mode, n_nodes, B, out):
         _lib.check(self._lib.scvx_predict_batch(self._h, X, U, sigma, base_dt, npts, mode, n_nodes, B, out))
 

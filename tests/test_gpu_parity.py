@@ -211,6 +211,42 @@ def test_fused_defect_cost(dyn, cache_aero, prob_aero):
     assert dD.cpu().numpy() == pytest.approx(ref_d, rel=1e-12)
 
 
+@pytest.mark.parametrize("K,B", [(1, 3), (2, 5), (50, 37), (100, 700)])
+def test_sparse_socp_rows_vs_reference_assembly(dyn, cache_aero, prob_aero, K, B):
+    """fixed-pattern CSC values of the dynamics + thrust-lower-bound rows, bit-exact against the
+    reference-style triplet assembly (rocketland.jl:117-133, 194-201, 251-265)."""
+    import torch
+    from oracle import socp_assembly
+    from successiveconvexification_b200 import rocketland, workloads
+    cache_aero.sim_prob.set_kernel(0)
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, K, B, 400 + K, sigma_range=(0.8, 1.5))
+    blocks, err, tlb = dyn.linearize_batch(cache_aero, X, U, sigma, 1 / (K + 1))
+    vals, rhs = rocketland.socp_values_batch(cache_aero, blocks, err, tlb)            # host pointers (chunked staging)
+    nr, nc, colptr, rowind = rocketland.socp_pattern(K + 1)
+    first = socp_assembly.variable_index(K)["dxv"][0, 0]
+    for b in sorted(set([0, B // 2, B - 1])):
+        D = blocks[b, :, 1:22, :].transpose(0, 2, 1)                                  # (K, 14, 21) = LinRes.derivative
+        M, const = socp_assembly.assemble_dense(D, blocks[b, :, 0, :], X[b], U[b], float(np.atleast_1d(P["Tmin"])[0]))
+        dense = np.zeros((nr, nc))
+        for j in range(nc):
+            dense[rowind[colptr[j]:colptr[j + 1]], j] = vals[b, colptr[j]:colptr[j + 1]]
+        assert np.array_equal(dense[:14 * K], M[:14 * K, first:])                      # a pure gather: bit-exact
+        assert np.abs(dense[14 * K:] - M[14 * K:, first:]).max() <= 1e-15              # H_n: device sqrt/div vs numpy
+        cu = rocketland.variable_columns(K)["duv"]
+        assert np.array_equal(dense[14 * K + np.arange(K + 1)[None, :], cu], tlb[b, :, :3].T)
+        assert np.array_equal(rhs[b, :14 * K], const[:14 * K])
+        assert np.abs(rhs[b, 14 * K:] - const[14 * K:]).max() <= 1e-17               # h_n: device sqrt vs numpy sqrt
+    # device-pointer form on torch's stream gives the same bytes
+    dB, dE, dT = (torch.from_numpy(a).cuda() for a in (blocks, err, tlb))
+    dV = torch.empty(vals.shape, dtype=torch.float64, device="cuda")
+    dR = torch.empty(rhs.shape, dtype=torch.float64, device="cuda")
+    ctx = cache_aero.sim_prob
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.socp_values_ptr(dB.data_ptr(), dE.data_ptr(), dT.data_ptr(), K + 1, B, dV.data_ptr(), dR.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(dV.cpu().numpy(), vals) and np.array_equal(dR.cpu().numpy(), rhs)
+
+
 def test_batched_initial_guess(dyn, cache_aero, prob_aero):
     """linear_points (initial_solve.jl:113-129) for a batch of dispersed initial conditions."""
     from successiveconvexification_b200 import workloads

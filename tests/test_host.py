@@ -91,3 +91,42 @@ def test_linres_views():
     r = LinRes(np.zeros(14), D)
     assert r.A.shape == (14, 14) and r.Bm.shape == (14, 3) and r.Bp.shape == (14, 3) and r.Sigma.shape == (14,)
     assert LinPoint(range(14), [1, 2, 3]).state.dtype == np.float64
+
+
+# ---- fixed-pattern sparse SOCP rows: the pattern is host-only code of the library --------------
+@pytest.mark.parametrize("K", [1, 2, 3, 50])
+def test_socp_pattern_matches_reference_assembly(K):
+    """CSC pattern from the library == nonzero pattern of the reference-style triplet assembly (rocketland.jl:117-133,
+    194-201) with a fully dense derivative."""
+    from oracle import socp_assembly
+    from successiveconvexification_b200 import rocketland
+    nr, nc, colptr, rowind = rocketland.socp_pattern(K + 1)
+    assert (nr, nc, len(rowind)) == (15 * K + 1, 31 * (K + 1) + 1, 325 * K + 3) == rocketland.socp_dims(K + 1)
+    assert colptr[0] == 0 and colptr[-1] == len(rowind) and np.all(np.diff(colptr) >= 0)
+    for j in range(nc):
+        r = rowind[colptr[j]:colptr[j + 1]]
+        assert np.all(np.diff(r) > 0), "rows must ascend strictly inside a column"
+    rng = np.random.default_rng(K)
+    D = rng.uniform(0.5, 1.5, (K, 14, 21))
+    M, _ = socp_assembly.assemble_dense(D, rng.normal(size=(K, 14)), rng.normal(size=(K + 1, 14)),
+                                        rng.uniform(0.5, 1.5, (K + 1, 3)), 0.1)
+    v = socp_assembly.variable_index(K)
+    first = v["dxv"][0, 0]
+    assert first == 17 * (K + 1)
+    assert not M[:, :first].any(), "xv / uv do not appear in these rows"
+    local = M[:, first:]
+    assert local.shape[1] == nc
+    pat = np.zeros_like(local, dtype=bool)
+    for j in range(nc):
+        pat[rowind[colptr[j]:colptr[j + 1]], j] = True
+    assert np.array_equal(pat, local != 0)
+    cols = rocketland.variable_columns(K)
+    for name in ("dxv", "duv", "nuv"):
+        assert np.array_equal(cols[name] + first, v[name])
+    assert cols["dsig"] + first == v["dsig"]
+
+
+def test_socp_entry_points_reject_bad_arguments():
+    from successiveconvexification_b200 import rocketland, _lib
+    with pytest.raises(_lib.ScvxError):
+        rocketland.socp_dims(1)
