@@ -60,6 +60,15 @@ typedef struct scvx_probinfo {
     int32_t _pad;
 } scvx_probinfo;
 
+/* The dimensional DescentProblem fields (master.jl:17-71) that normalize_problem (sample_problems.jl:5-23), ProbInfo
+ * (master.jl:73-83) and linear_points (initial_solve.jl:113-129) consume; shared by a dispersion batch. */
+typedef struct scvx_dim_problem {
+    double g, mdry, mwet, Tmin, Tmax, alpha, sos, tf_guess;
+    double jB[9], rTB[3], rFB[3], rIf[3];
+    int32_t aero_kind;
+    int32_t K;
+} scvx_dim_problem;
+
 /* Number of visible CUDA devices (0 if none / no driver). */
 int scvx_device_count(void);
 /* Thread-local message of the last failing call on this thread. */
@@ -121,6 +130,18 @@ int scvx_defect_cost_batch(scvx_ctx* ctx, const double* X, const double* lin_err
 int scvx_linear_points_batch(scvx_ctx* ctx, const double* rIi, const double* vIi, const double* mwet, double mwet_shared,
                              double mdry, const double* rIf, const double* vIf, double g, int K, int B,
                              double* X, double* U);
+
+/* Per-trajectory problem set-up for Monte-Carlo dispersions of a DIMENSIONAL problem, one launch:
+ *   normalize_problem (sample_problems.jl:5-23) with Ul_b = max(rIi_b), Ut = tf_guess, Um = mwet_b (vIf := vIi as there),
+ *   ProbInfo of the normalised problem (master.jl:73-83: a, g0, sos, jB, inv(jB), rTB, rFB; aero scalars of
+ *   rescale_aerodata, aerodynamics.jl:30-36) and its linear_points initial guess (initial_solve.jl:113-129).
+ * In : rIi, vIi 3 x B, mwet B (NULL: base->mwet) — dimensional.
+ * Out: X 14 x (K+1) x B, U 3 x (K+1) x B, sigma B (= tf_guess / Ut), scales 3 x B = [Ul, Ut, Um] (may be NULL),
+ *      out_params B records (may be NULL).  install != 0 makes the records the context's per-trajectory parameters, as if
+ *      scvx_set_params(ctx, records, B) had been called (no host round trip).  All arrays host or all device pointers. */
+int scvx_dispersed_setup_batch(scvx_ctx* ctx, const scvx_dim_problem* base, const double* rIi, const double* vIi,
+                               const double* mwet, int B, double* X, double* U, double* sigma, double* scales,
+                               scvx_probinfo* out_params, int install);
 
 /* Fixed-pattern sparse SOCP rows.  The reference refreshes the K dynamics equality blocks
  * (rocketland.jl:117-133, 251-258) and the K+1 linearised thrust-lower-bound rows (rocketland.jl:194-201, 260-265)

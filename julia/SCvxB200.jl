@@ -154,6 +154,33 @@ function linear_points_batch(ctx::Context, prob::DescentProblem, rIi::Matrix{Flo
     return X, U
 end
 
+# Dispersion set-up on the device (SURVEY §8f-3): per-trajectory normalize_problem (sample_problems.jl:5-23), ProbInfo
+# (master.jl:73-83) and linear_points (initial_solve.jl:113-129) for B dispersed DIMENSIONAL initial conditions.
+struct CDimProblem
+    g::Cdouble; mdry::Cdouble; mwet::Cdouble; Tmin::Cdouble; Tmax::Cdouble; alpha::Cdouble; sos::Cdouble; tf_guess::Cdouble
+    jB::NTuple{9,Cdouble}; rTB::NTuple{3,Cdouble}; rFB::NTuple{3,Cdouble}; rIf::NTuple{3,Cdouble}
+    aero_kind::Int32; K::Int32
+end
+CDimProblem(p::DescentProblem) = CDimProblem(p.g, p.mdry, p.mwet, p.Tmin, p.Tmax, p.alpha, p.sos, p.tf_guess,
+    Tuple(Float64.(vec(Matrix(p.jB)))), Tuple(Float64.(p.rTB)), Tuple(Float64.(p.rFB)), Tuple(Float64.(p.rIf)),
+    Int32(p.aero isa AtmosphericData ? 1 : 0), Int32(p.K))
+
+function dispersed_setup!(ctx::Context, prob::DescentProblem, rIi::Matrix{Float64}, vIi::Matrix{Float64};
+                          mwet::Union{Nothing,Vector{Float64}}=nothing, install::Bool=true)
+    B, K = size(rIi, 2), prob.K
+    X = Array{Float64,3}(undef, 14, K + 1, B); U = Array{Float64,3}(undef, 3, K + 1, B)
+    sigma = Vector{Float64}(undef, B); scales = Matrix{Float64}(undef, 3, B)
+    base = Ref(CDimProblem(prob))
+    GC.@preserve rIi vIi mwet X U sigma scales base begin
+        check(ccall((:scvx_dispersed_setup_batch, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{CDimProblem}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble},
+                     Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cvoid}, Cint),
+                    ctx.handle, base, rIi, vIi, mwet === nothing ? Ptr{Cdouble}(C_NULL) : pointer(mwet), B, X, U, sigma, scales,
+                    C_NULL, install ? 1 : 0))
+    end
+    return X, U, sigma, scales
+end
+
 # Fixed-pattern sparse form of the trajectory-dependent SOCP rows (reference rocketland.jl:117-133, 194-201, 251-265):
 # CSC pattern (1-based for SparseMatrixCSC) and, per trajectory, the value array + constants.  Local column j is the
 # reference's variable 17(K+1) + j (dxv, duv, dsig, nuv are created consecutively, rocketland.jl:73-76).

@@ -18,6 +18,8 @@
 #include "scvx_kernels.h"
 #include "scvx_socp_pattern.h"
 
+static_assert(sizeof(scvx_probinfo) == 248 && sizeof(scvx_dim_problem) == 216, "ABI record sizes are part of the contract");
+
 namespace {
 
 thread_local std::string g_err;
@@ -470,6 +472,91 @@ int scvx_linear_points_batch(scvx_ctx* c, const double* rIi, const double* vIi, 
     CK(cudaMemcpyAsync(X, sl.dX, n * 14 * 8, cudaMemcpyDeviceToHost, sl.stream));
     CK(cudaMemcpyAsync(U, sl.dU, n * 3 * 8, cudaMemcpyDeviceToHost, sl.stream));
     CK(cudaStreamSynchronize(sl.stream));
+    return 0;
+}
+
+int scvx_dispersed_setup_batch(scvx_ctx* c, const scvx_dim_problem* base, const double* rIi, const double* vIi,
+                               const double* mwet, int B, double* X, double* U, double* sigma, double* scales,
+                               scvx_probinfo* out_params, int install) {
+    if (!c || !base) return fail(SCVX_ERR_ARG, "null context or base problem");
+    if (!rIi || !vIi || !X || !U || !sigma) return fail(SCVX_ERR_ARG, "null array argument");
+    if (base->K < 1) return fail(SCVX_ERR_ARG, "K=%d must be >= 1", base->K);
+    if (base->aero_kind != SCVX_AERO_EXO && base->aero_kind != SCVX_AERO_TABLE) return fail(SCVX_ERR_ARG, "unknown aero_kind %d", base->aero_kind);
+    if (!(base->tf_guess > 0.0)) return fail(SCVX_ERR_ARG, "tf_guess must be positive");
+    if (B < 0) return fail(SCVX_ERR_ARG, "B=%d is negative", B);
+    if (B == 0) return 0;
+    const bool dev = is_device_ptr(rIi);
+    if (dev != is_device_ptr(vIi) || dev != is_device_ptr(X) || dev != is_device_ptr(U) || dev != is_device_ptr(sigma) ||
+        (mwet && dev != is_device_ptr(mwet)) || (scales && dev != is_device_ptr(scales)) ||
+        (out_params && dev != is_device_ptr(out_params)))
+        return fail(SCVX_ERR_ARG, "all array arguments must be either host or device pointers, not a mix");
+    Dev& d = c->devs[0];
+    CK(cudaSetDevice(d.id));
+    const size_t n = (size_t)(base->K + 1) * B;
+    cudaStream_t s = (dev && c->have_user_stream) ? c->user_stream : d.slot[0].stream;
+    scvx_probinfo* dP = nullptr;
+    if (install) {
+        // the records are written straight into the context's parameter array
+        CK(cudaStreamSynchronize(d.slot[0].stream));
+        CK(cudaStreamSynchronize(d.slot[1].stream));
+        if (d.nP < B) {
+            if (d.dP) cudaFree(d.dP);
+            d.dP = nullptr; d.nP = 0;
+            CK(cudaMalloc((void**)&d.dP, (size_t)B * sizeof(scvx_probinfo)));
+            d.nP = B;
+        }
+        dP = d.dP;
+    }
+    if (dev) {
+        CK(scvx_launch_dispersed_setup(*base, rIi, vIi, mwet, B, X, U, sigma, scales, dP, out_params, s));
+        c->launches += 1;
+    } else {
+        Slot& sl = d.slot[0];
+        CK(cudaStreamSynchronize(sl.stream));
+        if (grow(&sl.dX, &sl.capX, n * 14) || grow(&sl.dU, &sl.capU, n * 3) || grow(&sl.dS, &sl.capS, (size_t)11 * B)) return SCVX_ERR_NOMEM;
+        double *dr = sl.dS, *dv = sl.dS + (size_t)3 * B, *dm = sl.dS + (size_t)6 * B, *dsg = sl.dS + (size_t)7 * B, *dsc = sl.dS + (size_t)8 * B;
+        scvx_probinfo* dOutP = nullptr;
+        if (out_params && !dP) {
+            if (grow(&sl.dEnd, &sl.capEnd, ((size_t)B * sizeof(scvx_probinfo) + 7) / 8)) return SCVX_ERR_NOMEM;
+            dOutP = reinterpret_cast<scvx_probinfo*>(sl.dEnd);
+        }
+        CK(cudaMemcpyAsync(dr, rIi, (size_t)3 * B * 8, cudaMemcpyHostToDevice, sl.stream));
+        CK(cudaMemcpyAsync(dv, vIi, (size_t)3 * B * 8, cudaMemcpyHostToDevice, sl.stream));
+        if (mwet) CK(cudaMemcpyAsync(dm, mwet, (size_t)B * 8, cudaMemcpyHostToDevice, sl.stream));
+        CK(scvx_launch_dispersed_setup(*base, dr, dv, mwet ? dm : nullptr, B, sl.dX, sl.dU, dsg, dsc, dP, dOutP, sl.stream));
+        c->launches += 1;
+        CK(cudaMemcpyAsync(X, sl.dX, n * 14 * 8, cudaMemcpyDeviceToHost, sl.stream));
+        CK(cudaMemcpyAsync(U, sl.dU, n * 3 * 8, cudaMemcpyDeviceToHost, sl.stream));
+        CK(cudaMemcpyAsync(sigma, dsg, (size_t)B * 8, cudaMemcpyDeviceToHost, sl.stream));
+        if (scales) CK(cudaMemcpyAsync(scales, dsc, (size_t)3 * B * 8, cudaMemcpyDeviceToHost, sl.stream));
+        if (out_params)
+            CK(cudaMemcpyAsync(out_params, dP ? dP : dOutP, (size_t)B * sizeof(scvx_probinfo), cudaMemcpyDeviceToHost, sl.stream));
+        CK(cudaStreamSynchronize(sl.stream));
+    }
+    if (install) {
+        CK(cudaStreamSynchronize(s));       // a set-up call: later work on any stream sees the installed records
+        // other devices of the context receive a copy; the host mirror only carries what the argument checks read
+        // (count and aero kind) — the values live on the devices
+        for (size_t i = 1; i < c->devs.size(); ++i) {
+            Dev& o = c->devs[i];
+            CK(cudaSetDevice(o.id));
+            CK(cudaStreamSynchronize(o.slot[0].stream));
+            CK(cudaStreamSynchronize(o.slot[1].stream));
+            if (o.nP < B) {
+                if (o.dP) cudaFree(o.dP);
+                o.dP = nullptr; o.nP = 0;
+                CK(cudaMalloc((void**)&o.dP, (size_t)B * sizeof(scvx_probinfo)));
+                o.nP = B;
+            }
+            CK(cudaMemcpyPeer(o.dP, o.id, d.dP, d.id, (size_t)B * sizeof(scvx_probinfo)));
+        }
+        CK(cudaSetDevice(d.id));
+        scvx_probinfo tmpl;
+        memset(&tmpl, 0, sizeof(tmpl));
+        tmpl.aero_kind = base->aero_kind;
+        c->hP.assign((size_t)B, tmpl);
+        c->any_aero = base->aero_kind == SCVX_AERO_TABLE;
+    }
     return 0;
 }
 

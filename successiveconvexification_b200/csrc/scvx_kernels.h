@@ -14,6 +14,9 @@ cudaError_t scvx_launch_linear_points(const double* rIi, const double* vIi, cons
                                       cudaStream_t s);
 cudaError_t scvx_launch_socp_values(const double* blocks, const double* lin_err, const double* tlb, int n_nodes, int B,
                                     double* vals, double* rhs, cudaStream_t s);
+cudaError_t scvx_launch_dispersed_setup(const scvx_dim_problem& base, const double* rIi, const double* vIi, const double* mwet,
+                                        int B, double* X, double* U, double* sigma, double* scales, scvx_probinfo* P0,
+                                        scvx_probinfo* P1, cudaStream_t s);
 cudaError_t scvx_launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t s);
 
 // STAGED path (scvx_kernels_staged.cu): value kernel + persistent tangent kernel, chunked over a scratch buffer.

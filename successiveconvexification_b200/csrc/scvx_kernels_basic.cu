@@ -256,6 +256,121 @@ cudaError_t scvx_launch_linear_points(const double* rIi, const double* vIi, cons
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dispersion set-up: per-trajectory normalize_problem (sample_problems.jl:5-23) + ProbInfo (master.jl:73-83) +
+// linear_points (initial_solve.jl:113-129), one thread per (trajectory, node).  Every scaling is written as the
+// reference writes it (multiply by a reciprocal where it broadcasts `*`, divide where it divides) so the results match
+// a host evaluation of those lines to the last bit wherever IEEE arithmetic is deterministic.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void inverse3x3_lu(const double A[9], double Ai[9]) {
+    // LU with partial pivoting, then three unit right-hand sides (what `inv` does); column-major
+    double a[3][3];
+    int piv[3] = { 0, 1, 2 };
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a[r][c] = A[r + 3 * c];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int p = k;
+#pragma unroll
+        for (int r = k + 1; r < 3; ++r) if (fabs(a[r][k]) > fabs(a[p][k])) p = r;
+        if (p != k) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { const double t = a[k][c]; a[k][c] = a[p][c]; a[p][c] = t; }
+            const int t = piv[k]; piv[k] = piv[p]; piv[p] = t;
+        }
+#pragma unroll
+        for (int r = k + 1; r < 3; ++r) {
+            a[r][k] /= a[k][k];
+#pragma unroll
+            for (int c = k + 1; c < 3; ++c) a[r][c] -= a[r][k] * a[k][c];
+        }
+    }
+#pragma unroll
+    for (int col = 0; col < 3; ++col) {
+        double y[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) y[r] = (piv[r] == col) ? 1.0 : 0.0;
+        y[1] -= a[1][0] * y[0];
+        y[2] -= a[2][0] * y[0] + a[2][1] * y[1];
+        y[2] = y[2] / a[2][2];
+        y[1] = (y[1] - a[1][2] * y[2]) / a[1][1];
+        y[0] = (y[0] - a[0][1] * y[1] - a[0][2] * y[2]) / a[0][0];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) Ai[r + 3 * col] = y[r];
+    }
+}
+
+__global__ void __launch_bounds__(128) dispersed_setup_kernel(scvx_dim_problem base, const double* __restrict__ rIi,
+                                                              const double* __restrict__ vIi, const double* __restrict__ mwet,
+                                                              int B, double* __restrict__ X, double* __restrict__ U,
+                                                              double* __restrict__ sigma, double* __restrict__ scales,
+                                                              scvx_probinfo* __restrict__ P0, scvx_probinfo* __restrict__ P1) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int K = base.K, n = K + 1;
+    if (t >= (long)n * B) return;
+    const int b = (int)(t / n), k = (int)(t - (long)b * n);
+    const double ri[3] = { rIi[(size_t)b * 3], rIi[(size_t)b * 3 + 1], rIi[(size_t)b * 3 + 2] };
+    const double vi[3] = { vIi[(size_t)b * 3], vIi[(size_t)b * 3 + 1], vIi[(size_t)b * 3 + 2] };
+    const double Ul = fmax(fmax(ri[0], ri[1]), ri[2]);                   // sample_problems.jl:6
+    const double Ut = base.tf_guess;                                     // :7
+    const double Um = mwet ? mwet[b] : base.mwet;                        // :8
+    const double acc = Ul / (Ut * Ut);                                   // Ul/Ut^2
+    const double g = base.g / acc;                                       // :10
+    const double mdry = base.mdry / Um, mw = Um / Um;
+    const double il = 1.0 / Ul, ivel = 1.0 / (Ul / Ut);
+    // linear_points of the normalised problem (vIf is the normalised vIi, sample_problems.jl:15)
+    const double wa = (double)(K - k) / (double)K, wb = (double)k / (double)K;
+    const double mk = wa * mw + wb * mdry;
+    double r[3], v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        r[c] = wa * (ri[c] * il) + wb * (base.rIf[c] * il);
+        v[c] = wa * (vi[c] * ivel) + wb * (vi[c] * ivel);
+    }
+    const double wv[3] = { -v[0], -v[1], -v[2] };
+    const double normprod = sqrt(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]);
+    double qw = normprod + wv[0];
+    double ax = 0.0, ay = -wv[2], az = wv[1];
+    if (fabs(qw) < 100.0 * 2.220446049250313e-16) { ax = 0.0; ay = 0.0; az = 1.0; }
+    const double qn = 1.0 / sqrt(qw * qw + ax * ax + ay * ay + az * az);
+    double* x = X + (size_t)t * 14;
+    x[0] = mk; x[1] = r[0]; x[2] = r[1]; x[3] = r[2]; x[4] = v[0]; x[5] = v[1]; x[6] = v[2];
+    x[7] = qw * qn; x[8] = ax * qn; x[9] = ay * qn; x[10] = az * qn; x[11] = 0.0; x[12] = 0.0; x[13] = 0.0;
+    double* u = U + (size_t)t * 3;
+    u[0] = mk * g; u[1] = 0.0; u[2] = 0.0;
+    if (k != 0) return;
+    sigma[b] = base.tf_guess / Ut;                                       // :20
+    if (scales) { scales[(size_t)b * 3] = Ul; scales[(size_t)b * 3 + 1] = Ut; scales[(size_t)b * 3 + 2] = Um; }
+    if (!P0 && !P1) return;
+    scvx_probinfo p;
+    p.a = base.alpha / (Ut * Ut / Ul);                                   // :19
+    p.g0 = g;
+    p.sos = base.sos / (Ul / Ut);                                        // :22
+    const double ij = 1.0 / (Um * (Ul * Ul));                            // :13
+#pragma unroll
+    for (int e = 0; e < 9; ++e) p.jB[e] = base.jB[e] * ij;
+    inverse3x3_lu(p.jB, p.jBi);                                          // master.jl:82
+#pragma unroll
+    for (int e = 0; e < 3; ++e) { p.rTB[e] = base.rTB[e] * il; p.rFB[e] = base.rFB[e] * (1.0 / Ut); }   // :14, :17 (1/Ut as there)
+    p.force_scalar = 1.0 / (Ul * Um / (Ut * Ut));                        // aerodynamics.jl:31
+    p.length_scalar = 1.0 / Ul;
+    p.Tmin = base.Tmin / (Um * Ul / (Ut * Ut));                          // :11
+    p.aero_kind = base.aero_kind; p._pad = 0;
+    if (P0) P0[b] = p;
+    if (P1) P1[b] = p;
+}
+
+cudaError_t scvx_launch_dispersed_setup(const scvx_dim_problem& base, const double* rIi, const double* vIi, const double* mwet,
+                                        int B, double* X, double* U, double* sigma, double* scales, scvx_probinfo* P0,
+                                        scvx_probinfo* P1, cudaStream_t s) {
+    const long threads = (long)(base.K + 1) * B;
+    if (threads <= 0) return cudaSuccess;
+    dispersed_setup_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(base, rIi, vIi, mwet, B, X, U, sigma, scales, P0, P1);
+    return cudaGetLastError();
+}
+
 cudaError_t scvx_launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t s) {
     fp64_peak_kernel<<<blocks, 256, 0, s>>>(d_out, iters, 0.999999, 1e-9);
     return cudaGetLastError();

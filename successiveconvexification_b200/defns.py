@@ -138,6 +138,29 @@ class CProbInfo(ctypes.Structure):
     ]
 
 
+class CDimProblem(ctypes.Structure):
+    """`scvx_dim_problem` of include/scvx_b200.h: the dimensional DescentProblem fields the path consumes."""
+    _fields_ = [
+        ("g", ctypes.c_double), ("mdry", ctypes.c_double), ("mwet", ctypes.c_double), ("Tmin", ctypes.c_double),
+        ("Tmax", ctypes.c_double), ("alpha", ctypes.c_double), ("sos", ctypes.c_double), ("tf_guess", ctypes.c_double),
+        ("jB", ctypes.c_double * 9), ("rTB", ctypes.c_double * 3), ("rFB", ctypes.c_double * 3), ("rIf", ctypes.c_double * 3),
+        ("aero_kind", ctypes.c_int32), ("K", ctypes.c_int32),
+    ]
+
+    @classmethod
+    def from_problem(cls, dp: "DescentProblem") -> "CDimProblem":
+        c = cls()
+        for name in ("g", "mdry", "mwet", "Tmin", "Tmax", "alpha", "sos", "tf_guess"):
+            setattr(c, name, float(getattr(dp, name)))
+        c.jB = (ctypes.c_double * 9)(*np.asarray(dp.jB, dtype=np.float64).reshape(3, 3).T.ravel())   # column-major
+        c.rTB = (ctypes.c_double * 3)(*np.asarray(dp.rTB, dtype=np.float64))
+        c.rFB = (ctypes.c_double * 3)(*np.asarray(dp.rFB, dtype=np.float64))
+        c.rIf = (ctypes.c_double * 3)(*np.asarray(dp.rIf, dtype=np.float64))
+        c.aero_kind = AERO_TABLE if isinstance(dp.aero, AtmosphericData) else AERO_EXO
+        c.K = int(dp.K)
+        return c
+
+
 @dataclass
 class ProbInfo:
     """master.jl:73-83.  `ProbInfo(problem)` copies alpha→a, g→g0, sos, jB, inv(jB), rTB, rFB, aero

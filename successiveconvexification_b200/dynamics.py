@@ -123,6 +123,11 @@ class DeviceContext:
         _lib.check(self._lib.scvx_linear_points_batch(self._h, rIi, vIi, mwet or None, float(mwet_shared), float(mdry), rf, vf,
                                                       float(g), int(K), int(B), X, U))
 
+    def dispersed_setup_ptr(self, base, rIi, vIi, mwet, B, X, U, sigma, scales=0, out_params=0, install=True):
+        """`base`: a CDimProblem; the other arguments raw host or device addresses."""
+        _lib.check(self._lib.scvx_dispersed_setup_batch(self._h, ctypes.addressof(base), rIi, vIi, mwet or None, int(B), X, U,
+                                                        sigma, scales or None, out_params or None, 1 if install else 0))
+
     def socp_values_ptr(self, blocks, lin_err, tlb, n_nodes, B, out_vals, out_rhs=0):
         _lib.check(self._lib.scvx_socp_values_batch(self._h, blocks, lin_err or None, tlb, n_nodes, B, out_vals,
                                                     out_rhs or None))

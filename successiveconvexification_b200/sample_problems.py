@@ -63,3 +63,28 @@ def base_prob_aero(liftdrag) -> DescentProblem:
 def base_prob_aero_scaled(liftdrag) -> DescentProblem:
     """sample_problems.jl:32."""
     return normalize_problem(base_prob_aero(liftdrag))
+
+
+def dispersed_setup(cache, dim_problem: DescentProblem, rIi, vIi, mwet=None, install: bool = True):
+    """Monte-Carlo dispersions of a DIMENSIONAL problem, set up on the device in one launch: per
+    trajectory `normalize_problem` (sample_problems.jl:5-23, with Ul = max(rIi_b), Um = mwet_b), `ProbInfo` of the
+    normalised problem (master.jl:73-83) and its `linear_points` initial guess (initial_solve.jl:113-129).
+    rIi, vIi (B, 3) and mwet (B,) are dimensional.  With `install` the records become the cache's per-trajectory
+    parameters.  -> X (B, K+1, 14), U (B, K+1, 3), sigma (B,), scales (B, 3) = [Ul, Ut, Um], params (structured, B)."""
+    from .defns import CDimProblem
+    from .dynamics import _ctx
+    from .workloads import PROBINFO_DTYPE
+    ctx = _ctx(cache)
+    rIi = np.ascontiguousarray(rIi, dtype=np.float64)
+    vIi = np.ascontiguousarray(vIi, dtype=np.float64)
+    B, K = rIi.shape[0], dim_problem.K
+    if rIi.shape != (B, 3) or vIi.shape != (B, 3):
+        raise ValueError("expected rIi, vIi of shape (B, 3)")
+    mw = None if mwet is None else np.ascontiguousarray(mwet, dtype=np.float64)
+    X, U = np.empty((B, K + 1, 14)), np.empty((B, K + 1, 3))
+    sigma, scales = np.empty(B), np.empty((B, 3))
+    params = np.zeros(B, dtype=PROBINFO_DTYPE)
+    base = CDimProblem.from_problem(dim_problem)
+    ctx.dispersed_setup_ptr(base, rIi.ctypes.data, vIi.ctypes.data, mw.ctypes.data if mw is not None else 0, B,
+                            X.ctypes.data, U.ctypes.data, sigma.ctypes.data, scales.ctypes.data, params.ctypes.data, install)
+    return X, U, sigma, scales, params

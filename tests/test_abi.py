@@ -41,6 +41,8 @@ def test_probinfo_layout():
     lib = _lib.load()
     assert lib.scvx_sizeof_probinfo() == ctypes.sizeof(CProbInfo) == 248
     assert lib.scvx_version() >= 1000
+    from successiveconvexification_b200.defns import CDimProblem
+    assert ctypes.sizeof(CDimProblem) == 216          # static_assert in scvx_api.cu
 
 
 def test_julia_shim_binds_every_symbol():

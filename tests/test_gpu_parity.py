@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, PARITY_TOL, assert_parity, parity_report
+from conftest import AERO_NPZ, GOLDEN, PARITY_TOL, assert_parity, parity_report
 
 pytestmark = pytest.mark.gpu
 
@@ -245,6 +245,53 @@ def test_sparse_socp_rows_vs_reference_assembly(dyn, cache_aero, prob_aero, K, B
     ctx.socp_values_ptr(dB.data_ptr(), dE.data_ptr(), dT.data_ptr(), K + 1, B, dV.data_ptr(), dR.data_ptr())
     torch.cuda.synchronize()
     assert np.array_equal(dV.cpu().numpy(), vals) and np.array_equal(dR.cpu().numpy(), rhs)
+
+
+def test_dispersed_setup_on_device(dyn, oracle_tables):
+    """per-trajectory normalize_problem (sample_problems.jl:5-23) + ProbInfo (master.jl:73-83) +
+    linear_points (initial_solve.jl:113-129) in one launch, against the host mirror of those lines; the installed
+    records then drive a linearisation that matches one with host-built records."""
+    from successiveconvexification_b200 import sample_problems as sp
+    from successiveconvexification_b200.defns import ProbInfo
+    from successiveconvexification_b200.first_round import linear_points
+    dim = sp.base_prob_aero(AERO_NPZ).replace(K=12)                 # dimensional (sample_problems.jl:30-31)
+    cache = dyn.make_cache(sp.normalize_problem(dim))
+    rng = np.random.default_rng(8)
+    B = 130
+    rIi = dim.rIi[None] + rng.normal(0, 50.0, (B, 3))
+    rIi[5] = [400.0, 900.0, 1200.0]                                  # Ul comes from another component
+    vIi = dim.vIi[None] + rng.normal(0, 20.0, (B, 3))
+    mwet = dim.mwet * rng.uniform(0.9, 1.1, B)
+    X, U, sigma, scales, params = sp.dispersed_setup(cache, dim, rIi, vIi, mwet)
+    recs = []
+    for b in range(B):
+        pb = sp.normalize_problem(dim.replace(rIi=rIi[b], vIi=vIi[b], mwet=float(mwet[b])))
+        info = ProbInfo(pb)
+        recs.append(info)
+        assert np.array_equal(scales[b], [rIi[b].max(), dim.tf_guess, mwet[b]]) and sigma[b] == pb.tf_guess
+        pts = linear_points(pb)
+        assert np.abs(X[b] - np.stack([p.state for p in pts])).max() <= 1e-14
+        assert np.abs(U[b] - np.stack([p.control for p in pts])).max() <= 1e-16
+        got = params[b]
+        for name, ref in (("a", info.a), ("g0", info.g0), ("sos", info.sos), ("Tmin", info.Tmin),
+                          ("force_scalar", info.aero.force_scalar), ("length_scalar", info.aero.length_scalar)):
+            assert got[name] == pytest.approx(ref, rel=4e-16), name
+        assert np.allclose(got["jB"].reshape(3, 3).T, info.jB, rtol=4e-16, atol=0)
+        assert np.allclose(got["jBi"].reshape(3, 3).T, info.jBi, rtol=1e-15, atol=0)
+        assert np.allclose(got["rTB"], info.rTB, rtol=4e-16, atol=0) and np.allclose(got["rFB"], info.rFB, rtol=4e-16, atol=0)
+        assert got["aero_kind"] == 1
+    # the installed records are what the next call uses
+    blocks, err, tlb = dyn.linearize_batch(cache, X, U, sigma, 1 / 13, 10, 1)
+    ref, rerr, rtlb, _ = _oracle().linearize_batch(recs, oracle_tables, X, U, sigma, 1 / 13, 10, 1)
+    assert_parity(blocks, ref)
+    assert np.abs(tlb - rtlb).max() <= 1e-15
+    # a general (non-diagonal) inertia goes through the pivoted LU
+    jB = dim.jB + 1e4 * np.array([[0, 2.0, 1.0], [2.0, 0, 3.0], [1.0, 3.0, 0]])
+    dim2 = dim.replace(jB=jB)
+    _, _, _, _, p2 = sp.dispersed_setup(cache, dim2, rIi[:3], vIi[:3], mwet[:3], install=False)
+    for b in range(3):
+        info = ProbInfo(sp.normalize_problem(dim2.replace(rIi=rIi[b], vIi=vIi[b], mwet=float(mwet[b]))))
+        assert np.allclose(p2[b]["jBi"].reshape(3, 3).T, info.jBi, rtol=1e-13, atol=0)
 
 
 def test_batched_initial_guess(dyn, cache_aero, prob_aero):
