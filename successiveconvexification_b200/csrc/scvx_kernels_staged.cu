@@ -250,6 +250,9 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
     else { colA = 10; colB = 4; }                        // q3 column | light column d/dv0
 
     const int kq = warp & 3;                            // stage (within a step) this warp produces
+    // rk4 factor folded into the Jacobian blocks of that stage (consume_stage8): Y_{i+1} = S + c_i K_i, h/6 for the last
+    const double stage_scale = (kq == 3) ? h6 : (kq == 2 ? sstep : 0.5 * sstep);
+    const double kappa = (bt.mode == SCVX_MODE_LITERAL) ? h * (1.0 / 3.0) : (1.0 / 3.0);
     auto issue_record = [&](int n) {                    // one lane: TMA the record of (global step n, stage kq)
         const int it = n / npts, ls = n - it * npts;
         const int g = blockIdx.x + it * gridDim.x;
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
         const double sigma = __ldg(bt.sigma + b);
         const int half = n & 1, use = n >> 1;
         mbar_wait(&sm.recfull[half][kq], (uint32_t)(use & 1));      // this warp is the only waiter of recfull[half][kq]
-        produce_stage_inl(P, a.rec_n == REC_AERO, sigma, sm.recbuf[kq] + lane, &sm.ring[half * 4 + kq][lane][0],
+        produce_stage_inl(P, a.rec_n == REC_AERO, sigma, stage_scale, sm.recbuf[kq] + lane, &sm.ring[half * 4 + kq][lane][0],
                           use > 0 ? &sm.empty_step[half] : nullptr, (uint32_t)((use - 1) & 1));
         mbar_arrive(&sm.full_step[half]);
         __syncwarp();                                    // every lane has finished reading recbuf[kq]
@@ -328,10 +331,10 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
 #pragma unroll 1
             for (int k = 0; k < 3; ++k) {
                 const double pc = (k == 0) ? pca : pca + 0.5 * pcs;
-                consume_stage8<false>(FA, FB, J0 + k * (GROUP * NJ), gcol, l8, pc, k == 0 ? 1.0 : 2.0,
-                                      k == 2 ? sstep : 0.5 * sstep, h6, nullptr, lane);
+                consume_stage8<false>(FA, FB, J0 + k * (GROUP * NJ), gcol, l8, pc, k == 1 ? 2.0 : 1.0,
+                                      k == 0 ? h6 : 2.0 * h6, kappa, nullptr, lane);
             }
-            consume_stage8<true>(FA, FB, J0 + 3 * (GROUP * NJ), gcol, l8, pca + pcs, 1.0, 0.0, h6, nullptr, lane);
+            consume_stage8<true>(FA, FB, J0 + 3 * (GROUP * NJ), gcol, l8, pca + pcs, 1.0, h6, kappa, nullptr, lane);
             __syncwarp();
             mbar_arrive_lane0(&sm.empty_step[half], lane);           // the four slabs of this step are free again
             pca += pcs;

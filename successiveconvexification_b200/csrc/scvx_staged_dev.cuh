@@ -235,7 +235,7 @@ __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpre
 // whole record is formed in registers first and the wait sits right before the stores, so a producer that arrives
 // early overlaps its arithmetic with the consumers still reading the slot.
 template <class GetAero>
-__device__ __forceinline__ void produce_core(const scvx_probinfo& P, bool aero_rec, double sigma,
+__device__ __forceinline__ void produce_core(const scvx_probinfo& P, bool aero_rec, double sigma, double scale,
                                              const double* __restrict__ rec, double* __restrict__ out, GetAero get_aero,
                                              uint64_t* slot_free = nullptr, uint32_t slot_parity = 0) {
     // parameters first, as one batch of independent read-only loads (one latency, not one per use)
@@ -254,11 +254,14 @@ __device__ __forceinline__ void produce_core(const scvx_probinfo& P, bool aero_r
     const double fv[3] = { rec[15 * GROUP], rec[16 * GROUP], rec[17 * GROUP] };
     const double fq[4] = { rec[18 * GROUP], rec[19 * GROUP], rec[20 * GROUP], rec[21 * GROUP] };
     const double fw[3] = { rec[22 * GROUP], rec[23 * GROUP], rec[24 * GROUP] };
-    const double sm = sigma / m;
+    // every block that enters a stage increment carries sigma * scale (scale = the stage's rk4 factor, see
+    // consume_stage8); the quadrature entries (v, sigma) stay unscaled
+    const double ss = sigma * scale;
+    const double sm = ss / m;
 
     // ---- rotational block: Jww = -sigma * jBi * ([w]x jB - [jB w]x)
     double Jw[9];
-    const double hs = 0.5 * sigma;
+    const double hs = 0.5 * ss;
     {
         const double L0 = jB[0] * w0 + jB[3] * w1 + jB[6] * w2;
         const double L1 = jB[1] * w0 + jB[4] * w1 + jB[7] * w2;
@@ -275,7 +278,7 @@ __device__ __forceinline__ void produce_core(const scvx_probinfo& P, bool aero_r
         for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int c = 0; c < 3; ++c)
-                Jw[3 * r + c] = -sigma * (jBi[r] * M[0][c] + jBi[r + 3] * M[1][c] + jBi[r + 6] * M[2][c]);
+                Jw[3 * r + c] = -ss * (jBi[r] * M[0][c] + jBi[r + 3] * M[1][c] + jBi[r + 6] * M[2][c]);
     }
     // ---- translational block
     const double c00 = 1.0 - 2.0 * (q2 * q2 + q3 * q3), c01 = 2.0 * (q1 * q2 - q0 * q3), c02 = 2.0 * (q1 * q3 + q0 * q2);
@@ -316,16 +319,17 @@ __device__ __forceinline__ void produce_core(const scvx_probinfo& P, bool aero_r
     }
     // ---- direct (control / sigma) columns: G[col][row], rows m, v0..2, w0..2
     const double nu = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
-    const double gm = -sigma * Pa / nu;
+    const double gm = -ss * Pa / nu;
     // jBi * (rTB x e_j): rTB x e0 = (0, r2, -r1); x e1 = (-r2, 0, r0); x e2 = (r1, -r0, 0)
     double G[28];
     G[0] = gm * u0; G[1] = sm * c00; G[2] = sm * c10; G[3] = sm * c20;
-    G[4] = sigma * (jBi[3] * rT[2] - jBi[6] * rT[1]); G[5] = sigma * (jBi[4] * rT[2] - jBi[7] * rT[1]); G[6] = sigma * (jBi[5] * rT[2] - jBi[8] * rT[1]);
+    G[4] = ss * (jBi[3] * rT[2] - jBi[6] * rT[1]); G[5] = ss * (jBi[4] * rT[2] - jBi[7] * rT[1]); G[6] = ss * (jBi[5] * rT[2] - jBi[8] * rT[1]);
     G[7] = gm * u1; G[8] = sm * c01; G[9] = sm * c11; G[10] = sm * c21;
-    G[11] = sigma * (jBi[6] * rT[0] - jBi[0] * rT[2]); G[12] = sigma * (jBi[7] * rT[0] - jBi[1] * rT[2]); G[13] = sigma * (jBi[8] * rT[0] - jBi[2] * rT[2]);
+    G[11] = ss * (jBi[6] * rT[0] - jBi[0] * rT[2]); G[12] = ss * (jBi[7] * rT[0] - jBi[1] * rT[2]); G[13] = ss * (jBi[8] * rT[0] - jBi[2] * rT[2]);
     G[14] = gm * u2; G[15] = sm * c02; G[16] = sm * c12; G[17] = sm * c22;
-    G[18] = sigma * (jBi[0] * rT[1] - jBi[3] * rT[0]); G[19] = sigma * (jBi[1] * rT[1] - jBi[4] * rT[0]); G[20] = sigma * (jBi[2] * rT[1] - jBi[5] * rT[0]);
-    G[21] = fm; G[22] = fv[0]; G[23] = fv[1]; G[24] = fv[2]; G[25] = fw[0]; G[26] = fw[1]; G[27] = fw[2];
+    G[18] = ss * (jBi[0] * rT[1] - jBi[3] * rT[0]); G[19] = ss * (jBi[1] * rT[1] - jBi[4] * rT[0]); G[20] = ss * (jBi[2] * rT[1] - jBi[5] * rT[0]);
+    G[21] = scale * fm; G[22] = scale * fv[0]; G[23] = scale * fv[1]; G[24] = scale * fv[2];
+    G[25] = scale * fw[0]; G[26] = scale * fw[1]; G[27] = scale * fw[2];
     // ---- the slot must be free from here on
     if (slot_free != nullptr) mbar_wait(slot_free, slot_parity);
     st2(out + J_WW + 0, Jw[0], Jw[1]); st2(out + J_WW + 2, Jw[2], Jw[3]); st2(out + J_WW + 4, Jw[4], Jw[5]);
@@ -336,17 +340,17 @@ __device__ __forceinline__ void produce_core(const scvx_probinfo& P, bool aero_r
     for (int k = 0; k < 24; k += 2) st2(out + J_V + k, V[k], V[k + 1]);
 #pragma unroll
     for (int k = 0; k < 28; k += 2) st2(out + J_G + k, G[k], G[k + 1]);
-    st2(out + J_FRQ + 0, v[0], v[1]); st2(out + J_FRQ + 2, v[2], fq[0]);
-    st2(out + J_FRQ + 4, fq[1], fq[2]); st2(out + J_FRQ + 6, fq[3], sigma);
+    st2(out + J_FRQ + 0, v[0], v[1]); st2(out + J_FRQ + 2, v[2], scale * fq[0]);
+    st2(out + J_FRQ + 4, scale * fq[1], scale * fq[2]); st2(out + J_FRQ + 6, scale * fq[3], sigma);
     st2(out + J_FRQ + 8, 0.0, 0.0);
 }
 
 // The aero force Jacobians were recorded by the value kernel (record entries 25..42).  Inlined: at its call site (a
 // step boundary) only S and the r-row sums of the tangent state are live.
-__device__ __forceinline__ void produce_stage_inl(const scvx_probinfo& P, bool aero_rec, double sigma,
+__device__ __forceinline__ void produce_stage_inl(const scvx_probinfo& P, bool aero_rec, double sigma, double scale,
                                                   const double* __restrict__ rec, double* __restrict__ out,
                                                   uint64_t* slot_free, uint32_t slot_parity) {
-    produce_core(P, aero_rec, sigma, rec, out,
+    produce_core(P, aero_rec, sigma, scale, rec, out,
                  [&](const double*, double, double, double, double Fv[3][3], double Fb[3][3]) {
 #pragma unroll
                      for (int r = 0; r < 3; ++r)
@@ -370,24 +374,34 @@ struct FullCol {
 // there is no control flow inside the stage; two instantiations keep the hot loop inside the instruction cache).
 // Rows are processed in cascade order (r, v, m, q, w): a row block is overwritten only after every block that
 // reads its old stage value has been formed.
+//
+// Stage-tangent form of rk4.  The producer scales the Jacobian blocks of stage i by c_i (the factor of
+// Y_{i+1} = S + c_i K_i; h/6 for the final stage), so a row's chain of FMAs started FROM S yields the next stage
+// tangent directly (no separate K, no multiply to start the chain).  With T = Y_2 + 2 Y_3 + Y_4 and kappa = h/(3 s)
+// (s = 1 LITERAL, h TEXTBOOK):   S_new = S + kappa (T - 4 S) + (h/6) K_4,  the last term again a chain started from
+// the first two.  T - 4S cancels exactly for entries that never move, so constants of D stay exact.
+// 11 % fewer FP64 instructions per stage than forming K, acc += w K, Y = S + c K.
 template <bool LAST>
 __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const double* __restrict__ J, const int gcol,
-                                               const int l8, const double pc, const double wgt, const double cy,
-                                               const double h6, uint64_t* empty_bar, const int lane) {
+                                               const int l8, const double pc, const double tw, const double cr,
+                                               const double kappa, uint64_t* empty_bar, const int lane) {
     constexpr bool last = LAST;
     const double alA = (l8 < 3) ? 1.0 - pc : (l8 == 3 ? 1.0 : 0.0), alB = (l8 < 3) ? pc : 0.0;
     const double dsA = (l8 == 3) ? 1.0 : 0.0;
     const double* Gc = J + J_G + 7 * gcol;
-    auto upd = [&](FullCol& F, const int idx, const double K) {
-        if constexpr (!last) { F.A[idx] = fma(wgt, K, F.A[idx]); F.Y[idx] = fma(cy, K, F.S[idx]); }
-        else { F.S[idx] = fma(h6, F.A[idx] + K, F.S[idx]); F.Y[idx] = F.S[idx]; F.A[idx] = 0.0; }
+    auto init = [&](const FullCol& F, const int idx) -> double {
+        if constexpr (!last) return F.S[idx];
+        else return fma(kappa, fma(-4.0, F.S[idx], F.A[idx]), F.S[idx]);
     };
-    // ---- r rows (pure quadrature): S_r += cr * (sigma * Y_v + dsigma * f_r)
+    auto fin = [&](FullCol& F, const int idx, const double yn) {
+        if constexpr (!last) { F.A[idx] = fma(tw, yn, F.A[idx]); F.Y[idx] = yn; }
+        else { F.S[idx] = yn; F.Y[idx] = yn; F.A[idx] = 0.0; }
+    };
+    // ---- r rows (pure quadrature): S_r += cr * (sigma * Y_v + dsigma * f_r),  cr = h/6 * rk4 weight
     {
         const double2 fr01 = ld2(J + J_FRQ);
         const double fr2 = J[J_FRQ + 2];
         const double sg = J[J_FRQ + 7];
-        const double cr = h6 * wgt;
         const double csg = cr * sg, cds = cr * dsA;
         FA.Sr[0] = fma(csg, FA.Y[1], fma(cds, fr01.x, FA.Sr[0]));
         FA.Sr[1] = fma(csg, FA.Y[2], fma(cds, fr01.y, FA.Sr[1]));
@@ -395,7 +409,7 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
 #pragma unroll
         for (int r = 0; r < 3; ++r) FB.Sr[r] = fma(csg, FB.Y[1 + r], FB.Sr[r]);
     }
-    // ---- v rows: K_v = Jvm Y_m + Jvv Y_v + Jvq Y_q + alpha * G_v
+    // ---- v rows: Jvm Y_m + Jvv Y_v + Jvq Y_q + alpha * G_v
     {
         double kA[3], kB[3];
 #pragma unroll
@@ -404,19 +418,20 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
             const double2 qa = ld2(J + J_V + 8 * row + 4), qb = ld2(J + J_V + 8 * row + 6);
             const double gg = Gc[1 + row];
             kA[row] = fma(c01.x, FA.Y[0], fma(c01.y, FA.Y[1], fma(c23.x, FA.Y[2], fma(c23.y, FA.Y[3],
-                      fma(qa.x, FA.Y[4], fma(qa.y, FA.Y[5], fma(qb.x, FA.Y[6], fma(qb.y, FA.Y[7], alA * gg))))))));
+                      fma(qa.x, FA.Y[4], fma(qa.y, FA.Y[5], fma(qb.x, FA.Y[6], fma(qb.y, FA.Y[7], fma(alA, gg, init(FA, 1 + row))))))))));
             kB[row] = fma(c01.x, FB.Y[0], fma(c01.y, FB.Y[1], fma(c23.x, FB.Y[2], fma(c23.y, FB.Y[3],
-                      fma(qa.x, FB.Y[4], fma(qa.y, FB.Y[5], fma(qb.x, FB.Y[6], fma(qb.y, FB.Y[7], alB * gg))))))));
+                      fma(qa.x, FB.Y[4], fma(qa.y, FB.Y[5], fma(qb.x, FB.Y[6], fma(qb.y, FB.Y[7], fma(alB, gg, init(FB, 1 + row))))))))));
         }
 #pragma unroll
-        for (int r = 0; r < 3; ++r) { upd(FA, 1 + r, kA[r]); upd(FB, 1 + r, kB[r]); }
+        for (int r = 0; r < 3; ++r) { fin(FA, 1 + r, kA[r]); fin(FB, 1 + r, kB[r]); }
     }
-    // ---- m row: K_m = alpha * G_m
+    // ---- m row: alpha * G_m
     {
         const double gmv = Gc[0];
-        upd(FA, 0, alA * gmv); upd(FB, 0, alB * gmv);
+        const double a0 = fma(alA, gmv, init(FA, 0)), b0 = fma(alB, gmv, init(FB, 0));
+        fin(FA, 0, a0); fin(FB, 0, b0);
     }
-    // ---- q rows: K_q = Omega(hw) Y_q + Omega(Y_w) hq + dsigma * f_q
+    // ---- q rows: Omega(hw) Y_q + Omega(Y_w) hq + dsigma * f_q   (only slot A can hold the sigma column)
     {
         const double hw0 = J[J_HW], hw1 = J[J_HW + 1], hw2 = J[J_HW + 2];
         const double2 hq01 = ld2(J + J_HQ), hq23 = ld2(J + J_HQ + 2);
@@ -425,29 +440,29 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
         const double2 fq12 = ld2(J + J_FRQ + 4);
         const double fq3 = J[J_FRQ + 6];
         double kA[4], kB[4];
-#define QROWS(F, K, ds)                                                                                                                     \
-        K[0] = fma(-hw0, F.Y[5], fma(-hw1, F.Y[6], fma(-hw2, F.Y[7], fma(-hq1, F.Y[8], fma(-hq2, F.Y[9], fma(-hq3, F.Y[10], ds * fq0))))));   \
-        K[1] = fma(hw0, F.Y[4], fma(hw2, F.Y[6], fma(-hw1, F.Y[7], fma(hq0, F.Y[8], fma(hq2, F.Y[10], fma(-hq3, F.Y[9], ds * fq12.x))))));    \
-        K[2] = fma(hw1, F.Y[4], fma(-hw2, F.Y[5], fma(hw0, F.Y[7], fma(hq0, F.Y[9], fma(-hq1, F.Y[10], fma(hq3, F.Y[8], ds * fq12.y))))));    \
-        K[3] = fma(hw2, F.Y[4], fma(hw1, F.Y[5], fma(-hw0, F.Y[6], fma(hq0, F.Y[10], fma(hq1, F.Y[9], fma(-hq2, F.Y[8], ds * fq3))))));
-        QROWS(FA, kA, dsA)
-        QROWS(FB, kB, 0.0)
+#define QROWS(F, K, i0, i1, i2, i3)                                                                                                  \
+        K[0] = fma(-hw0, F.Y[5], fma(-hw1, F.Y[6], fma(-hw2, F.Y[7], fma(-hq1, F.Y[8], fma(-hq2, F.Y[9], fma(-hq3, F.Y[10], i0))))));   \
+        K[1] = fma(hw0, F.Y[4], fma(hw2, F.Y[6], fma(-hw1, F.Y[7], fma(hq0, F.Y[8], fma(hq2, F.Y[10], fma(-hq3, F.Y[9], i1))))));       \
+        K[2] = fma(hw1, F.Y[4], fma(-hw2, F.Y[5], fma(hw0, F.Y[7], fma(hq0, F.Y[9], fma(-hq1, F.Y[10], fma(hq3, F.Y[8], i2))))));       \
+        K[3] = fma(hw2, F.Y[4], fma(hw1, F.Y[5], fma(-hw0, F.Y[6], fma(hq0, F.Y[10], fma(hq1, F.Y[9], fma(-hq2, F.Y[8], i3))))));
+        QROWS(FA, kA, fma(dsA, fq0, init(FA, 4)), fma(dsA, fq12.x, init(FA, 5)), fma(dsA, fq12.y, init(FA, 6)), fma(dsA, fq3, init(FA, 7)))
+        QROWS(FB, kB, init(FB, 4), init(FB, 5), init(FB, 6), init(FB, 7))
 #undef QROWS
 #pragma unroll
-        for (int r = 0; r < 4; ++r) { upd(FA, 4 + r, kA[r]); upd(FB, 4 + r, kB[r]); }
+        for (int r = 0; r < 4; ++r) { fin(FA, 4 + r, kA[r]); fin(FB, 4 + r, kB[r]); }
     }
-    // ---- w rows: K_w = Jww * Y_w + alpha * G_w
+    // ---- w rows: Jww * Y_w + alpha * G_w
     {
         const double2 j01 = ld2(J + J_WW), j23 = ld2(J + J_WW + 2), j45 = ld2(J + J_WW + 4), j67 = ld2(J + J_WW + 6);
         const double j8 = J[J_WW + 8];
         const double g0 = Gc[4], g1 = Gc[5], g2 = Gc[6];
         double kA[3], kB[3];
-        kA[0] = fma(j01.x, FA.Y[8], fma(j01.y, FA.Y[9], fma(j23.x, FA.Y[10], alA * g0)));
-        kA[1] = fma(j23.y, FA.Y[8], fma(j45.x, FA.Y[9], fma(j45.y, FA.Y[10], alA * g1)));
-        kA[2] = fma(j67.x, FA.Y[8], fma(j67.y, FA.Y[9], fma(j8, FA.Y[10], alA * g2)));
-        kB[0] = fma(j01.x, FB.Y[8], fma(j01.y, FB.Y[9], fma(j23.x, FB.Y[10], alB * g0)));
-        kB[1] = fma(j23.y, FB.Y[8], fma(j45.x, FB.Y[9], fma(j45.y, FB.Y[10], alB * g1)));
-        kB[2] = fma(j67.x, FB.Y[8], fma(j67.y, FB.Y[9], fma(j8, FB.Y[10], alB * g2)));
+        kA[0] = fma(j01.x, FA.Y[8], fma(j01.y, FA.Y[9], fma(j23.x, FA.Y[10], fma(alA, g0, init(FA, 8)))));
+        kA[1] = fma(j23.y, FA.Y[8], fma(j45.x, FA.Y[9], fma(j45.y, FA.Y[10], fma(alA, g1, init(FA, 9)))));
+        kA[2] = fma(j67.x, FA.Y[8], fma(j67.y, FA.Y[9], fma(j8, FA.Y[10], fma(alA, g2, init(FA, 10)))));
+        kB[0] = fma(j01.x, FB.Y[8], fma(j01.y, FB.Y[9], fma(j23.x, FB.Y[10], fma(alB, g0, init(FB, 8)))));
+        kB[1] = fma(j23.y, FB.Y[8], fma(j45.x, FB.Y[9], fma(j45.y, FB.Y[10], fma(alB, g1, init(FB, 9)))));
+        kB[2] = fma(j67.x, FB.Y[8], fma(j67.y, FB.Y[9], fma(j8, FB.Y[10], fma(alB, g2, init(FB, 10)))));
         // all reads of the ring slot are done: hand it back (per-stage hand-over only; the step-synchronised kernel
         // passes a null barrier and releases a whole step at once)
         if (empty_bar != nullptr) {
@@ -455,7 +470,7 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
             mbar_arrive_lane0(empty_bar, lane);
         }
 #pragma unroll
-        for (int r = 0; r < 3; ++r) { upd(FA, 8 + r, kA[r]); upd(FB, 8 + r, kB[r]); }
+        for (int r = 0; r < 3; ++r) { fin(FA, 8 + r, kA[r]); fin(FB, 8 + r, kB[r]); }
     }
 }
 
