@@ -331,6 +331,20 @@ def test_multi_device_context_shards_by_trajectory(dyn, prob_aero, cache_aero):
     many, errn, tlbn = dyn.linearize_batch(multi, X, U, sigma, 1 / 51)
     assert np.array_equal(one, many) and np.array_equal(err1, errn) and np.array_equal(tlb1, tlbn)
     assert np.array_equal(dyn.predict_batch(multi, X, U, sigma, 1 / 51), dyn.predict_batch(cache_aero, X, U, sigma, 1 / 51))
+    # per-trajectory records installed by the device-side dispersion set-up reach every device of the context
+    from successiveconvexification_b200 import sample_problems as sp
+    dim = sp.base_prob_aero(AERO_NPZ).replace(K=10)
+    rng = np.random.default_rng(3)
+    rIi = dim.rIi[None] + rng.normal(0, 50.0, (64, 3))
+    vIi = dim.vIi[None] + rng.normal(0, 20.0, (64, 3))
+    mwet = dim.mwet * rng.uniform(0.9, 1.1, 64)
+    single = dyn.make_cache(sp.normalize_problem(dim))
+    Xs, Us, ss, _, _ = sp.dispersed_setup(single, dim, rIi, vIi, mwet)
+    Xm, Um, sm_, _, _ = sp.dispersed_setup(multi, dim, rIi, vIi, mwet)
+    assert np.array_equal(Xs, Xm) and np.array_equal(Us, Um)
+    a = dyn.linearize_batch(single, Xs, Us, ss, 1 / 11)
+    b = dyn.linearize_batch(multi, Xm, Um, sm_, 1 / 11)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
