@@ -1,6 +1,6 @@
 // scvx_api.cu — context management and the C ABI declared in include/scvx_b200.h.
 //
-// A context owns, per device: the staged spline tables, the parameter records, two pipeline slots of
+// A context owns, per device: the staged spline tables, the parameter records, NSLOT pipeline slots of
 // staging buffers + streams (host-pointer calls are cut into trajectory chunks so that the H2D copy of
 // chunk c+1, the kernels of chunk c and the D2H copy of chunk c-1 overlap), and launch bookkeeping.
 // Trajectories are independent (reference dynamics.jl:324-332 reads only nodes i, i+1), so multi-device
@@ -38,6 +38,11 @@ int fail(int code, const char* fmt, ...) {
             return fail(SCVX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// Pipeline depth of the host-pointer path.  Three slots: when the D2H copy of chunk c ends, the copy of chunk c+1 is running
+// and chunk c+2 has already been computed, so the D2H engine never waits for a kernel (with two slots it idled for
+// the ~1.3 ms of H2D + kernels of every chunk: 43 instead of 54 GB/s on this pool's PCIe).
+constexpr int NSLOT = 3;
+
 struct Slot {
     cudaStream_t stream = nullptr;
     double *dX = nullptr, *dU = nullptr, *dS = nullptr, *dOut = nullptr, *dErr = nullptr, *dTlb = nullptr, *dEnd = nullptr;
@@ -46,7 +51,7 @@ struct Slot {
 
 struct Dev {
     int id = 0;
-    Slot slot[2];
+    Slot slot[NSLOT];
     double* coef[3] = { nullptr, nullptr, nullptr };
     int n1 = 0, n2 = 0;
     double x0 = 0, dx = 1, y0 = 0, dy = 1;
@@ -140,14 +145,14 @@ int launch_linearize(scvx_ctx* c, Dev& d, const ScvxBatch& bt, cudaStream_t s) {
         if (e != cudaSuccess) return fail(SCVX_ERR_NOMEM, "cudaMalloc(%zu B) for the stage-record scratch failed: %s", need, cudaGetErrorString(e));
         d.scratch_cap = need;
     }
-    if (d.scratch_user && d.scratch_user != s) {
-        CK(cudaEventRecord(d.ev_scratch, d.scratch_user));
-        CK(cudaStreamWaitEvent(s, d.ev_scratch, 0));
-    }
-    d.scratch_user = s;
+    // ev_scratch marks the end of the KERNELS of the previous user (recorded right behind them, below): waiting on an
+    // event recorded now on that stream would also wait for its D2H copy and serialise copy and compute
+    if (d.scratch_user && d.scratch_user != s) CK(cudaStreamWaitEvent(s, d.ev_scratch, 0));
     int n = 0;
     CK(scvx_launch_staged(bt, tb, c->any_aero, d.scratch, chunk, d.sm_count, s, &n));
     c->launches += n;
+    CK(cudaEventRecord(d.ev_scratch, s));
+    d.scratch_user = s;
     return 0;
 }
 
@@ -217,7 +222,7 @@ int run(scvx_ctx* c, bool predict, const double* X, const double* U, const doubl
             if (cb >= b1) continue;
             CK(cudaSetDevice(d.id));
             const int nb = (int)std::min(chunk, b1 - cb);
-            Slot& sl = d.slot[ci & 1];
+            Slot& sl = d.slot[ci % NSLOT];
             CK(cudaStreamSynchronize(sl.stream));       // previous user of this slot has drained its D2H
             if (grow(&sl.dX, &sl.capX, (size_t)nb * n_nodes * 14) || grow(&sl.dU, &sl.capU, (size_t)nb * n_nodes * 3) ||
                 grow(&sl.dS, &sl.capS, (size_t)nb))
@@ -252,8 +257,7 @@ int run(scvx_ctx* c, bool predict, const double* X, const double* U, const doubl
     for (int di = 0; di < nd; ++di) {
         Dev& d = c->devs[di];
         CK(cudaSetDevice(d.id));
-        CK(cudaStreamSynchronize(d.slot[0].stream));
-        CK(cudaStreamSynchronize(d.slot[1].stream));
+        for (int q = 0; q < NSLOT; ++q) CK(cudaStreamSynchronize(d.slot[q].stream));
     }
     c->timed = false;
     return 0;
@@ -289,7 +293,7 @@ int scvx_create(scvx_ctx** out, const int* device_ids, int n_dev) {
         Dev& d = c->devs[i];
         d.id = ids[i];
         cudaError_t e = cudaSetDevice(d.id);
-        for (int s = 0; s < 2 && e == cudaSuccess; ++s) e = cudaStreamCreateWithFlags(&d.slot[s].stream, cudaStreamNonBlocking);
+        for (int s = 0; s < NSLOT && e == cudaSuccess; ++s) e = cudaStreamCreateWithFlags(&d.slot[s].stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreate(&d.ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&d.ev1);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_scratch, cudaEventDisableTiming);
@@ -304,7 +308,7 @@ void scvx_destroy(scvx_ctx* c) {
     if (!c) return;
     for (Dev& d : c->devs) {
         cudaSetDevice(d.id);
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NSLOT; ++s) {
             Slot& sl = d.slot[s];
             if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
             double* bufs[] = { sl.dX, sl.dU, sl.dS, sl.dOut, sl.dErr, sl.dTlb, sl.dEnd };
@@ -330,8 +334,7 @@ int scvx_set_params(scvx_ctx* c, const scvx_probinfo* p, int n) {
     for (int i = 0; i < n; ++i) if (p[i].aero_kind == SCVX_AERO_TABLE) c->any_aero = true;
     for (Dev& d : c->devs) {
         CK(cudaSetDevice(d.id));
-        CK(cudaStreamSynchronize(d.slot[0].stream));
-        CK(cudaStreamSynchronize(d.slot[1].stream));
+        for (int q = 0; q < NSLOT; ++q) CK(cudaStreamSynchronize(d.slot[q].stream));
         if (d.nP < n) {
             if (d.dP) cudaFree(d.dP);
             d.dP = nullptr; d.nP = 0;
@@ -497,8 +500,7 @@ int scvx_dispersed_setup_batch(scvx_ctx* c, const scvx_dim_problem* base, const 
     scvx_probinfo* dP = nullptr;
     if (install) {
         // the records are written straight into the context's parameter array
-        CK(cudaStreamSynchronize(d.slot[0].stream));
-        CK(cudaStreamSynchronize(d.slot[1].stream));
+        for (int q = 0; q < NSLOT; ++q) CK(cudaStreamSynchronize(d.slot[q].stream));
         if (d.nP < B) {
             if (d.dP) cudaFree(d.dP);
             d.dP = nullptr; d.nP = 0;
@@ -540,8 +542,7 @@ int scvx_dispersed_setup_batch(scvx_ctx* c, const scvx_dim_problem* base, const 
         for (size_t i = 1; i < c->devs.size(); ++i) {
             Dev& o = c->devs[i];
             CK(cudaSetDevice(o.id));
-            CK(cudaStreamSynchronize(o.slot[0].stream));
-            CK(cudaStreamSynchronize(o.slot[1].stream));
+            for (int q = 0; q < NSLOT; ++q) CK(cudaStreamSynchronize(o.slot[q].stream));
             if (o.nP < B) {
                 if (o.dP) cudaFree(o.dP);
                 o.dP = nullptr; o.nP = 0;
@@ -610,7 +611,7 @@ int scvx_socp_values_batch(scvx_ctx* c, const double* blocks, const double* lin_
     long chunk = std::max(1L, (long)(((size_t)128 << 20) / (nblk * sizeof(double))));
     for (long cb = 0, ci = 0; cb < B; cb += chunk, ++ci) {
         const int nb = (int)std::min(chunk, (long)B - cb);
-        Slot& sl = d.slot[ci & 1];
+        Slot& sl = d.slot[ci % NSLOT];
         CK(cudaStreamSynchronize(sl.stream));
         if (grow(&sl.dOut, &sl.capOut, nb * nblk) || grow(&sl.dTlb, &sl.capTlb, nb * ntlb) || grow(&sl.dEnd, &sl.capEnd, nb * nnz) ||
             (out_rhs && (grow(&sl.dErr, &sl.capErr, nb * nerr) || grow(&sl.dX, &sl.capX, nb * nr))))
@@ -623,8 +624,7 @@ int scvx_socp_values_batch(scvx_ctx* c, const double* blocks, const double* lin_
         CK(cudaMemcpyAsync(out_vals + cb * nnz, sl.dEnd, nb * nnz * 8, cudaMemcpyDeviceToHost, sl.stream));
         if (out_rhs) CK(cudaMemcpyAsync(out_rhs + cb * nr, sl.dX, nb * nr * 8, cudaMemcpyDeviceToHost, sl.stream));
     }
-    CK(cudaStreamSynchronize(d.slot[0].stream));
-    CK(cudaStreamSynchronize(d.slot[1].stream));
+    for (int q = 0; q < NSLOT; ++q) CK(cudaStreamSynchronize(d.slot[q].stream));
     return 0;
 }
 
@@ -646,8 +646,7 @@ int scvx_synchronize(scvx_ctx* c) {
     if (!c) return fail(SCVX_ERR_ARG, "null context");
     for (Dev& d : c->devs) {
         CK(cudaSetDevice(d.id));
-        CK(cudaStreamSynchronize(d.slot[0].stream));
-        CK(cudaStreamSynchronize(d.slot[1].stream));
+        for (int q = 0; q < NSLOT; ++q) CK(cudaStreamSynchronize(d.slot[q].stream));
     }
     if (c->have_user_stream) { CK(cudaSetDevice(c->devs[0].id)); CK(cudaStreamSynchronize(c->user_stream)); }
     return 0;
