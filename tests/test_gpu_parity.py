@@ -361,6 +361,22 @@ def test_other_substep_counts(dyn, cache_aero, prob_aero, oracle_tables, kernel,
         assert np.abs(err - rerr).max() <= 1e-12 * max(1.0, np.abs(rerr).max())
 
 
+@pytest.mark.parametrize("npts", [1, 3, 5])
+def test_odd_substep_counts_over_several_passes(dyn, cache_aero, prob_aero, npts):
+    """Several 32-interval passes per CTA with an odd number of rk4 steps per pass: the step-parity bookkeeping of the
+    STAGED ring (two steps deep) must carry across passes.  Cross-checked on the device against the DUALWARP kernel."""
+    from successiveconvexification_b200 import workloads
+    X, U, sigma, _ = workloads.monte_carlo_batch(prob_aero, 50, 330, 17, sigma_range=(0.8, 1.5))      # 16 500 intervals
+    ctx = cache_aero.sim_prob
+    ctx.set_kernel(2)
+    a, ea, _ = dyn.linearize_batch(cache_aero, X, U, sigma, 1 / 51, npts, 0)
+    ctx.set_kernel(1)
+    b, eb, _ = dyn.linearize_batch(cache_aero, X, U, sigma, 1 / 51, npts, 0)
+    ctx.set_kernel(0)
+    assert_parity(a, b)
+    assert np.abs(ea - eb).max() <= 1e-12 * max(1.0, np.abs(eb).max())
+
+
 def test_edge_cases_and_errors(dyn, cache_aero, prob_aero):
     from successiveconvexification_b200 import _lib, workloads
     X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, 1, 3, 8, sigma_range=(0.8, 1.5))     # n_nodes = 2
