@@ -197,19 +197,28 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
 }
 
 // ------------------------------------------------------------------------------------------------
-// Kernel B: tangent propagation of the 14 heavy columns.  8 lanes per interval, two full columns per lane, rotating
-// lane = interval Jacobian producer, TMA-fed stage records, mbarrier-guarded shared-memory ring.  Production and
-// hand-over happen once per rk4 STEP (a per-stage hand-over cost 17 % of the kernel in barrier waits and loop drain):
-//   * the ring holds two steps (2 x 4 stage slabs); at the start of consumer step m the four warps of the other half
-//     each produce one stage of step m+1 (one whole step of slack);
-//   * consumers wait ONE "full" barrier per step and release the four slabs with ONE "empty" arrive per step;
-//   * at a step boundary the stage tangent equals S and the accumulator is zero, so only 56 registers of tangent
-//     state are live across the (inlined) producer: no spilling, no parking;
-//   * the producer forms the whole 78-double record in registers and waits for the ring slot only right before its
-//     stores, overlapping its arithmetic with consumers that are still reading the slot;
-//   * four record buffers (one per stage of a step); the warp that has just read buffer k re-arms its TMA for the
-//     next step.
+// Kernel B: tangent propagation of the 14 heavy columns (+ 2 light ones in the idle slots).  Warp-specialised,
+// persistent, one CTA of 12 warps per SM:
+//   * warps 0..7  CONSUMERS: 8 lanes per interval, two full columns per lane (4 intervals per warp, 32 per pass); they
+//     run nothing but the FP64 chains of consume_stage8 on register state;
+//   * warps 8..11 PRODUCERS: warp 8+k forms the Jacobian blocks of rk4 stage k of every step with lane = interval, from
+//     the stage record the value kernel wrote (one TMA bulk copy per record, mbarrier complete_tx; the next record is
+//     pulled into L2 a step ahead because the staging buffer is single);
+//   * registers are re-partitioned between the warpgroups with setmaxnreg (168 at launch -> 208 per consumer thread,
+//     88 per producer thread): the consumers keep their 156 registers of tangent state without spills while a third
+//     warp per scheduler fills the issue slots their FP64 dependency chains leave empty;
+//   * hand-over once per rk4 STEP through a shared-memory ring two steps deep (2 x 4 stage slabs): consumers wait ONE
+//     "full" barrier per step and release the four slabs with ONE "empty" arrive per step (a per-stage hand-over cost
+//     17 % of the kernel in barrier waits and loop drain); producers run as far ahead as the ring allows.
+// (Until the producers got their own warps the consumer warps took turns producing, inlined at step boundaries where
+//  only S is live; the consumers then spent 18 % of their issue slots on it: 9.8e7 -> 1.02e8 intervals/s.)
 // ------------------------------------------------------------------------------------------------
+constexpr int TANGENT_THREADS = (NWARP + 4) * 32;
+// setmaxnreg re-partition: 128 * PRODUCER_REGS + 256 * CONSUMER_REGS <= 384 * 168 (the launch-time allocation)
+constexpr int CONSUMER_REGS = 208;
+constexpr int PRODUCER_REGS = (384 * 168 - 256 * CONSUMER_REGS) / 128;
+static_assert(PRODUCER_REGS == 88, "register split");
+
 struct __align__(16) StepSmem {
     double ring[8][GROUP][NJ];               // [half * 4 + stage][interval][entry]
     double recbuf[4][REC_MAX * GROUP];       // stage records of the step being produced (TMA destination)
@@ -218,7 +227,7 @@ struct __align__(16) StepSmem {
     uint64_t recfull[2][4];                  // [half][stage]: one waiting warp per barrier (it observes every phase)
 };
 
-__global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
+__global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(StagedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StepSmem& sm = *reinterpret_cast<StepSmem*>(smem_raw);
     const ScvxBatch& bt = a.bt;
@@ -262,7 +271,15 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
         mbar_expect_tx(&sm.recfull[n & 1][kq], bytes);
         bulk_g2s(sm.recbuf[kq], src, bytes, &sm.recfull[n & 1][kq]);
     };
+    auto record_src = [&](int n) -> const double* {
+        const int it = n / npts, ls = n - it * npts;
+        const int g = blockIdx.x + it * gridDim.x;
+        return a.rec + ((size_t)g * nst + 4 * ls + kq) * ((size_t)a.rec_n * GROUP);
+    };
     auto produce = [&](int n) {                         // whole warp (lane = interval): stage kq of global step n
+        // the record buffer is single (shared memory is full), so the TMA of step n+1 can only be issued once this
+        // step's record has been read: pull it into L2 now, the copy then costs an L2 hit instead of a DRAM round trip
+        if (lane == 0 && n + 1 < total_steps) bulk_prefetch_l2(record_src(n + 1), (uint32_t)a.rec_n * GROUP * 8);
         const int it = n / npts;
         const int g = blockIdx.x + it * gridDim.x;
         int t = g * GROUP + lane; if (t >= a.count) t = a.count - 1;
@@ -271,18 +288,25 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
         const double sigma = __ldg(bt.sigma + b);
         const int half = n & 1, use = n >> 1;
         mbar_wait(&sm.recfull[half][kq], (uint32_t)(use & 1));      // this warp is the only waiter of recfull[half][kq]
-        produce_stage_inl(P, a.rec_n == REC_AERO, sigma, stage_scale, sm.recbuf[kq] + lane, &sm.ring[half * 4 + kq][lane][0],
-                          use > 0 ? &sm.empty_step[half] : nullptr, (uint32_t)((use - 1) & 1));
+        if (use > 0) mbar_wait(&sm.empty_step[half], (uint32_t)((use - 1) & 1));
+        produce_lean(P, a.rec_n == REC_AERO, sigma, stage_scale, sm.recbuf[kq] + lane, &sm.ring[half * 4 + kq][lane][0]);
         mbar_arrive(&sm.full_step[half]);
         __syncwarp();                                    // every lane has finished reading recbuf[kq]
         if (lane == 0 && n + 1 < total_steps) issue_record(n + 1);
     };
 
-    // prologue: warps 0..3 fetch and produce step 0 (and re-arm the record buffers for step 1)
-    if (warp < 4 && total_steps > 0) {
-        if (lane == 0) issue_record(0);
-        produce(0);
+    // dedicated producer warps: warp NWARP + kq forms stage kq of every step, as far ahead as the ring allows
+    if (warp >= NWARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+        if (total_steps > 0) {
+            if (lane == 0) issue_record(0);
+            __syncwarp();
+#pragma unroll 1
+            for (int n = 0; n < total_steps; ++n) produce(n);
+        }
+        return;
     }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
 
     FullCol FA, FB;
     int n = 0;                                           // global consumer step
@@ -315,15 +339,6 @@ __global__ void __launch_bounds__(256, 1) tangent_kernel(StagedArgs a) {
         double pca = 0.0;
 #pragma unroll 1
         for (int ls = 0; ls < npts; ++ls, ++n) {
-            // ---- producer duty: the warps of the other half produce step n+1 (Y == S and A == 0 here, so only
-            //      S and the r-row sums have to survive the call)
-            if ((warp >> 2) == ((n + 1) & 1) && n + 1 < total_steps) {
-                produce(n + 1);
-                // the stage tangent and the accumulator are dead across the producer (Y == S, A == 0 at a step
-                // boundary): re-materialise them instead of keeping 88 registers alive
-#pragma unroll
-                for (int r = 0; r < 11; ++r) { FA.Y[r] = FA.S[r]; FB.Y[r] = FB.S[r]; FA.A[r] = 0.0; FB.A[r] = 0.0; }
-            }
             // ---- consume the four stages of step n
             const int half = n & 1;
             mbar_wait(&sm.full_step[half], (uint32_t)((n >> 1) & 1));
@@ -407,7 +422,7 @@ cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool a
         const int threads = a.n_groups * GROUP;
         stage_value_kernel<<<(threads + 127) / 128, 128, LIGHT_SMEM_BYTES, s>>>(a);
         const int grid = a.n_groups < sm_count ? a.n_groups : sm_count;
-        tangent_kernel<<<grid, 256, smem, s>>>(a);
+        tangent_kernel<<<grid, TANGENT_THREADS, smem, s>>>(a);
         if (launches) *launches += 2;
     }
     return cudaGetLastError();

@@ -222,6 +222,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
@@ -229,137 +232,114 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 
-// rec: this lane's stage record (stride GROUP doubles between entries, in shared memory);
-// out: this lane's NJ-double Jacobian record in the ring.
-// `slot_free` (may be null): mbarrier that must have completed phase `slot_parity` before `out` may be written.  The
-// whole record is formed in registers first and the wait sits right before the stores, so a producer that arrives
-// early overlaps its arithmetic with the consumers still reading the slot.
-template <class GetAero>
-__device__ __forceinline__ void produce_core(const scvx_probinfo& P, bool aero_rec, double sigma, double scale,
-                                             const double* __restrict__ rec, double* __restrict__ out, GetAero get_aero,
-                                             uint64_t* slot_free = nullptr, uint32_t slot_parity = 0) {
-    // parameters first, as one batch of independent read-only loads (one latency, not one per use)
-    const double Pa = __ldg(&P.a), Pg0 = __ldg(&P.g0);
-    double jB[9], jBi[9], rT[3];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) { jB[k] = __ldg(&P.jB[k]); jBi[k] = __ldg(&P.jBi[k]); }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) rT[k] = __ldg(&P.rTB[k]);
-    const double m = rec[0];
-    const double v[3] = { rec[1 * GROUP], rec[2 * GROUP], rec[3 * GROUP] };
-    const double q0 = rec[4 * GROUP], q1 = rec[5 * GROUP], q2 = rec[6 * GROUP], q3 = rec[7 * GROUP];
-    const double w0 = rec[8 * GROUP], w1 = rec[9 * GROUP], w2 = rec[10 * GROUP];
-    const double u0 = rec[11 * GROUP], u1 = rec[12 * GROUP], u2 = rec[13 * GROUP];
-    const double fm = rec[14 * GROUP];
-    const double fv[3] = { rec[15 * GROUP], rec[16 * GROUP], rec[17 * GROUP] };
-    const double fq[4] = { rec[18 * GROUP], rec[19 * GROUP], rec[20 * GROUP], rec[21 * GROUP] };
-    const double fw[3] = { rec[22 * GROUP], rec[23 * GROUP], rec[24 * GROUP] };
-    // every block that enters a stage increment carries sigma * scale (scale = the stage's rk4 factor, see
-    // consume_stage8); the quadrature entries (v, sigma) stay unscaled
+// Register-lean producer for the dedicated producer warps of tangent_kernel (they run with 88 registers after the
+// setmaxnreg re-partition).  rec: this lane's stage record (stride GROUP doubles between entries, in shared memory);
+// out: this lane's NJ-double Jacobian record in the ring (the caller has waited for the slot).  The record is formed
+// and stored block by block, so only a few values are live at any time; every block that enters a stage increment
+// carries sigma * scale (scale = the stage's rk4 factor, see consume_stage8), the quadrature entries (v, sigma) do not.
+__device__ __forceinline__ void produce_lean(const scvx_probinfo& P, bool aero_rec, double sigma, double scale,
+                                             const double* __restrict__ rec, double* __restrict__ out) {
     const double ss = sigma * scale;
-    const double sm = ss / m;
-
-    // ---- rotational block: Jww = -sigma * jBi * ([w]x jB - [jB w]x)
-    double Jw[9];
     const double hs = 0.5 * ss;
+    const double sm = ss / rec[0];
+    // ---- quadrature entries, hw, hq
     {
-        const double L0 = jB[0] * w0 + jB[3] * w1 + jB[6] * w2;
-        const double L1 = jB[1] * w0 + jB[4] * w1 + jB[7] * w2;
-        const double L2 = jB[2] * w0 + jB[5] * w1 + jB[8] * w2;
-        double M[3][3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {          // column c of [w]x jB = w x jB[:,c]
-            const double a0 = jB[3 * c], a1 = jB[3 * c + 1], a2 = jB[3 * c + 2];
-            M[0][c] = w1 * a2 - w2 * a1; M[1][c] = w2 * a0 - w0 * a2; M[2][c] = w0 * a1 - w1 * a0;
-        }
-        // minus [L]x = [[0,-L2,L1],[L2,0,-L0],[-L1,L0,0]]
-        M[0][1] += L2; M[0][2] -= L1; M[1][0] -= L2; M[1][2] += L0; M[2][0] += L1; M[2][1] -= L0;
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                Jw[3 * r + c] = -ss * (jBi[r] * M[0][c] + jBi[r + 3] * M[1][c] + jBi[r + 6] * M[2][c]);
+        const double q0 = rec[4 * GROUP], q1 = rec[5 * GROUP], q2 = rec[6 * GROUP], q3 = rec[7 * GROUP];
+        st2(out + J_HQ + 0, hs * q0, hs * q1); st2(out + J_HQ + 2, hs * q2, hs * q3);
+        const double v0 = rec[1 * GROUP], v1 = rec[2 * GROUP], v2 = rec[3 * GROUP];
+        const double f0 = rec[18 * GROUP], f1 = rec[19 * GROUP], f2 = rec[20 * GROUP], f3 = rec[21 * GROUP];
+        st2(out + J_FRQ + 0, v0, v1); st2(out + J_FRQ + 2, v2, scale * f0);
+        st2(out + J_FRQ + 4, scale * f1, scale * f2); st2(out + J_FRQ + 6, scale * f3, sigma);
+        st2(out + J_FRQ + 8, 0.0, 0.0);
     }
-    // ---- translational block
-    const double c00 = 1.0 - 2.0 * (q2 * q2 + q3 * q3), c01 = 2.0 * (q1 * q2 - q0 * q3), c02 = 2.0 * (q1 * q3 + q0 * q2);
-    const double c10 = 2.0 * (q1 * q2 + q0 * q3), c11 = 1.0 - 2.0 * (q1 * q1 + q3 * q3), c12 = 2.0 * (q2 * q3 - q0 * q1);
-    const double c20 = 2.0 * (q1 * q3 - q0 * q2), c21 = 2.0 * (q2 * q3 + q0 * q1), c22 = 1.0 - 2.0 * (q1 * q1 + q2 * q2);
-    // d(C u)/dq, row-major 3x4
-    double Jq[12];
-    Jq[0] = 2.0 * (q2 * u2 - q3 * u1);             Jq[1] = 2.0 * (q2 * u1 + q3 * u2);
-    Jq[2] = 2.0 * (q1 * u1 + q0 * u2) - 4.0 * q2 * u0; Jq[3] = 2.0 * (q1 * u2 - q0 * u1) - 4.0 * q3 * u0;
-    Jq[4] = 2.0 * (q3 * u0 - q1 * u2);             Jq[5] = 2.0 * (q2 * u0 - q0 * u2) - 4.0 * q1 * u1;
-    Jq[6] = 2.0 * (q1 * u0 + q3 * u2);             Jq[7] = 2.0 * (q0 * u0 + q2 * u2) - 4.0 * q3 * u1;
-    Jq[8] = 2.0 * (q1 * u1 - q2 * u0);             Jq[9] = 2.0 * (q3 * u0 + q0 * u1) - 4.0 * q1 * u2;
-    Jq[10] = 2.0 * (q3 * u1 - q0 * u0) - 4.0 * q2 * u2; Jq[11] = 2.0 * (q1 * u0 + q2 * u1);
-    double Jvv[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
-    if (aero_rec) {
-        double Fv[3][3], Fb[3][3];
-        get_aero(v, c00, c10, c20, Fv, Fb);
-        // db/dq
-        const double B[3][4] = { { 0.0, 0.0, -4.0 * q2, -4.0 * q3 },
-                                 { 2.0 * q3, 2.0 * q2, 2.0 * q1, 2.0 * q0 },
-                                 { -2.0 * q2, 2.0 * q3, -2.0 * q0, 2.0 * q1 } };
+    // ---- rotational block: Jww = -ss * jBi * ([w]x jB - [jB w]x), and hw
+    {
+        const double w0 = rec[8 * GROUP], w1 = rec[9 * GROUP], w2 = rec[10 * GROUP];
+        double M[3][3];
+        {
+            double jB[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) jB[k] = __ldg(&P.jB[k]);
+            const double L0 = jB[0] * w0 + jB[3] * w1 + jB[6] * w2;
+            const double L1 = jB[1] * w0 + jB[4] * w1 + jB[7] * w2;
+            const double L2 = jB[2] * w0 + jB[5] * w1 + jB[8] * w2;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double a0 = jB[3 * c], a1 = jB[3 * c + 1], a2 = jB[3 * c + 2];
+                M[0][c] = w1 * a2 - w2 * a1; M[1][c] = w2 * a0 - w0 * a2; M[2][c] = w0 * a1 - w1 * a0;
+            }
+            M[0][1] += L2; M[0][2] -= L1; M[1][0] -= L2; M[1][2] += L0; M[2][0] += L1; M[2][1] -= L0;
+        }
+        double Jw[9];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
+            const double b0 = __ldg(&P.jBi[r]), b1 = __ldg(&P.jBi[r + 3]), b2 = __ldg(&P.jBi[r + 6]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) Jq[4 * r + c] += Fb[r][0] * B[0][c] + Fb[r][1] * B[1][c] + Fb[r][2] * B[2][c];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) Jvv[3 * r + c] = sm * Fv[r][c];
+            for (int c = 0; c < 3; ++c) Jw[3 * r + c] = -ss * (b0 * M[0][c] + b1 * M[1][c] + b2 * M[2][c]);
         }
+        st2(out + J_WW + 0, Jw[0], Jw[1]); st2(out + J_WW + 2, Jw[2], Jw[3]); st2(out + J_WW + 4, Jw[4], Jw[5]);
+        st2(out + J_WW + 6, Jw[6], Jw[7]); st2(out + J_WW + 8, Jw[8], hs * w0);
+        st2(out + J_HW + 1, hs * w1, hs * w2);
     }
-    // Jvm = -sigma * ((C u + F)/m) / m = -(sigma/m) * (f_v + g0 e1); one 8-double row per v component
-    double V[24];
+    // ---- v rows: [d/dm, d/dv (3), d/dq (4)] per row
+    {
+        const double q0 = rec[4 * GROUP], q1 = rec[5 * GROUP], q2 = rec[6 * GROUP], q3 = rec[7 * GROUP];
+        const double u0 = rec[11 * GROUP], u1 = rec[12 * GROUP], u2 = rec[13 * GROUP];
+        const double Pg0 = __ldg(&P.g0);
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        V[8 * r + 0] = -sm * (fv[r] + (r == 0 ? Pg0 : 0.0));
-        V[8 * r + 1] = Jvv[3 * r]; V[8 * r + 2] = Jvv[3 * r + 1]; V[8 * r + 3] = Jvv[3 * r + 2];
-        V[8 * r + 4] = sm * Jq[4 * r]; V[8 * r + 5] = sm * Jq[4 * r + 1];
-        V[8 * r + 6] = sm * Jq[4 * r + 2]; V[8 * r + 7] = sm * Jq[4 * r + 3];
+        for (int r = 0; r < 3; ++r) {
+            double j0, j1, j2, j3;
+            if (r == 0) {
+                j0 = 2.0 * (q2 * u2 - q3 * u1);             j1 = 2.0 * (q2 * u1 + q3 * u2);
+                j2 = 2.0 * (q1 * u1 + q0 * u2) - 4.0 * q2 * u0; j3 = 2.0 * (q1 * u2 - q0 * u1) - 4.0 * q3 * u0;
+            } else if (r == 1) {
+                j0 = 2.0 * (q3 * u0 - q1 * u2);             j1 = 2.0 * (q2 * u0 - q0 * u2) - 4.0 * q1 * u1;
+                j2 = 2.0 * (q1 * u0 + q3 * u2);             j3 = 2.0 * (q0 * u0 + q2 * u2) - 4.0 * q3 * u1;
+            } else {
+                j0 = 2.0 * (q1 * u1 - q2 * u0);             j1 = 2.0 * (q3 * u0 + q0 * u1) - 4.0 * q1 * u2;
+                j2 = 2.0 * (q3 * u1 - q0 * u0) - 4.0 * q2 * u2; j3 = 2.0 * (q1 * u0 + q2 * u1);
+            }
+            double vv0 = 0.0, vv1 = 0.0, vv2 = 0.0;
+            if (aero_rec) {
+                const double b0 = rec[(34 + 3 * r) * GROUP], b1 = rec[(35 + 3 * r) * GROUP], b2 = rec[(36 + 3 * r) * GROUP];
+                // db/dq rows: {0, 0, -4 q2, -4 q3}, {2 q3, 2 q2, 2 q1, 2 q0}, {-2 q2, 2 q3, -2 q0, 2 q1}
+                j0 += b0 * 0.0 + b1 * (2.0 * q3) + b2 * (-2.0 * q2);
+                j1 += b0 * 0.0 + b1 * (2.0 * q2) + b2 * (2.0 * q3);
+                j2 += b0 * (-4.0 * q2) + b1 * (2.0 * q1) + b2 * (-2.0 * q0);
+                j3 += b0 * (-4.0 * q3) + b1 * (2.0 * q0) + b2 * (2.0 * q1);
+                vv0 = sm * rec[(25 + 3 * r) * GROUP]; vv1 = sm * rec[(26 + 3 * r) * GROUP]; vv2 = sm * rec[(27 + 3 * r) * GROUP];
+            }
+            const double fvr = rec[(15 + r) * GROUP];
+            st2(out + J_V + 8 * r + 0, -sm * (fvr + (r == 0 ? Pg0 : 0.0)), vv0);
+            st2(out + J_V + 8 * r + 2, vv1, vv2);
+            st2(out + J_V + 8 * r + 4, sm * j0, sm * j1);
+            st2(out + J_V + 8 * r + 6, sm * j2, sm * j3);
+        }
+        // ---- direct (control / sigma) columns G[col][row], rows m, v0..2, w0..2 (7 per column)
+        const double c00 = 1.0 - 2.0 * (q2 * q2 + q3 * q3), c01 = 2.0 * (q1 * q2 - q0 * q3), c02 = 2.0 * (q1 * q3 + q0 * q2);
+        const double c10 = 2.0 * (q1 * q2 + q0 * q3), c11 = 1.0 - 2.0 * (q1 * q1 + q3 * q3), c12 = 2.0 * (q2 * q3 - q0 * q1);
+        const double c20 = 2.0 * (q1 * q3 - q0 * q2), c21 = 2.0 * (q2 * q3 + q0 * q1), c22 = 1.0 - 2.0 * (q1 * q1 + q2 * q2);
+        const double nu = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
+        const double gm = -ss * __ldg(&P.a) / nu;
+        const double r0 = __ldg(&P.rTB[0]), r1 = __ldg(&P.rTB[1]), r2 = __ldg(&P.rTB[2]);
+        double* G = out + J_G;
+        double bi[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) bi[k] = __ldg(&P.jBi[k]);
+        // jBi * (rTB x e_j): rTB x e0 = (0, r2, -r1); x e1 = (-r2, 0, r0); x e2 = (r1, -r0, 0)
+        st2(G + 0, gm * u0, sm * c00); st2(G + 2, sm * c10, sm * c20);
+        st2(G + 4, ss * (bi[3] * r2 - bi[6] * r1), ss * (bi[4] * r2 - bi[7] * r1));
+        st2(G + 6, ss * (bi[5] * r2 - bi[8] * r1), gm * u1);
+        st2(G + 8, sm * c01, sm * c11);
+        st2(G + 10, sm * c21, ss * (bi[6] * r0 - bi[0] * r2));
+        st2(G + 12, ss * (bi[7] * r0 - bi[1] * r2), ss * (bi[8] * r0 - bi[2] * r2));
+        st2(G + 14, gm * u2, sm * c02); st2(G + 16, sm * c12, sm * c22);
+        st2(G + 18, ss * (bi[0] * r1 - bi[3] * r0), ss * (bi[1] * r1 - bi[4] * r0));
+        st2(G + 20, ss * (bi[2] * r1 - bi[5] * r0), scale * rec[14 * GROUP]);
+        st2(G + 22, scale * rec[15 * GROUP], scale * rec[16 * GROUP]);
+        st2(G + 24, scale * rec[17 * GROUP], scale * rec[22 * GROUP]);
+        st2(G + 26, scale * rec[23 * GROUP], scale * rec[24 * GROUP]);
     }
-    // ---- direct (control / sigma) columns: G[col][row], rows m, v0..2, w0..2
-    const double nu = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
-    const double gm = -ss * Pa / nu;
-    // jBi * (rTB x e_j): rTB x e0 = (0, r2, -r1); x e1 = (-r2, 0, r0); x e2 = (r1, -r0, 0)
-    double G[28];
-    G[0] = gm * u0; G[1] = sm * c00; G[2] = sm * c10; G[3] = sm * c20;
-    G[4] = ss * (jBi[3] * rT[2] - jBi[6] * rT[1]); G[5] = ss * (jBi[4] * rT[2] - jBi[7] * rT[1]); G[6] = ss * (jBi[5] * rT[2] - jBi[8] * rT[1]);
-    G[7] = gm * u1; G[8] = sm * c01; G[9] = sm * c11; G[10] = sm * c21;
-    G[11] = ss * (jBi[6] * rT[0] - jBi[0] * rT[2]); G[12] = ss * (jBi[7] * rT[0] - jBi[1] * rT[2]); G[13] = ss * (jBi[8] * rT[0] - jBi[2] * rT[2]);
-    G[14] = gm * u2; G[15] = sm * c02; G[16] = sm * c12; G[17] = sm * c22;
-    G[18] = ss * (jBi[0] * rT[1] - jBi[3] * rT[0]); G[19] = ss * (jBi[1] * rT[1] - jBi[4] * rT[0]); G[20] = ss * (jBi[2] * rT[1] - jBi[5] * rT[0]);
-    G[21] = scale * fm; G[22] = scale * fv[0]; G[23] = scale * fv[1]; G[24] = scale * fv[2];
-    G[25] = scale * fw[0]; G[26] = scale * fw[1]; G[27] = scale * fw[2];
-    // ---- the slot must be free from here on
-    if (slot_free != nullptr) mbar_wait(slot_free, slot_parity);
-    st2(out + J_WW + 0, Jw[0], Jw[1]); st2(out + J_WW + 2, Jw[2], Jw[3]); st2(out + J_WW + 4, Jw[4], Jw[5]);
-    st2(out + J_WW + 6, Jw[6], Jw[7]); st2(out + J_WW + 8, Jw[8], hs * w0);
-    st2(out + J_HW + 1, hs * w1, hs * w2);
-    st2(out + J_HQ + 0, hs * q0, hs * q1); st2(out + J_HQ + 2, hs * q2, hs * q3);
-#pragma unroll
-    for (int k = 0; k < 24; k += 2) st2(out + J_V + k, V[k], V[k + 1]);
-#pragma unroll
-    for (int k = 0; k < 28; k += 2) st2(out + J_G + k, G[k], G[k + 1]);
-    st2(out + J_FRQ + 0, v[0], v[1]); st2(out + J_FRQ + 2, v[2], scale * fq[0]);
-    st2(out + J_FRQ + 4, scale * fq[1], scale * fq[2]); st2(out + J_FRQ + 6, scale * fq[3], sigma);
-    st2(out + J_FRQ + 8, 0.0, 0.0);
-}
-
-// The aero force Jacobians were recorded by the value kernel (record entries 25..42).  Inlined: at its call site (a
-// step boundary) only S and the r-row sums of the tangent state are live.
-__device__ __forceinline__ void produce_stage_inl(const scvx_probinfo& P, bool aero_rec, double sigma, double scale,
-                                                  const double* __restrict__ rec, double* __restrict__ out,
-                                                  uint64_t* slot_free, uint32_t slot_parity) {
-    produce_core(P, aero_rec, sigma, scale, rec, out,
-                 [&](const double*, double, double, double, double Fv[3][3], double Fb[3][3]) {
-#pragma unroll
-                     for (int r = 0; r < 3; ++r)
-#pragma unroll
-                         for (int c = 0; c < 3; ++c) {
-                             Fv[r][c] = rec[(25 + 3 * r + c) * GROUP];
-                             Fb[r][c] = rec[(34 + 3 * r + c) * GROUP];
-                         }
-                 }, slot_free, slot_parity);
 }
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
