@@ -13,13 +13,14 @@
 //      columns (d/dv1, d/dv2; state in shared memory), the constant position columns and the partial z; the other two
 //      (d/dm, d/dv0) ride in the two otherwise idle column slots of the tangent kernel.
 //
-//  B   tangent_kernel       : persistent, one 256-thread CTA per SM, 32 intervals per pass.  The 14 heavy tangent
-//      columns: 8 lanes per interval, two full columns per lane, tangent state (S, accumulator, stage tangent, r-row
-//      quadrature = 144 registers) in registers.  The sigma-scaled Jacobian blocks (78 doubles per interval and
-//      stage) are produced by rotating warps with lane = interval (no redundancy) from TMA-staged stage records into
-//      a shared-memory ring and read back by the 8 lanes of an interval as broadcast 128-bit loads.  Ring slots are
-//      handed over with mbarriers once per rk4 step.  [A|B-|B+|Sigma] go from registers to the 14x23 block with
-//      16-byte stores; z is reduced over the 8 lanes and accumulated in place.
+//  B   tangent_kernel       : persistent, warp-specialised, one 384-thread CTA per SM, 32 intervals per pass.  The 14
+//      heavy tangent columns (+ 2 light ones): 8 consumer warps, 8 lanes per interval, two full columns per lane,
+//      tangent state (S, stage sum T, stage tangent, r-row quadrature = 156 registers) in registers.  The
+//      sigma*c_i-scaled Jacobian blocks (78 doubles per interval and stage) are formed by 4 dedicated producer warps with
+//      lane = interval (no redundancy) from TMA-staged stage records into a shared-memory ring and read back by the 8
+//      lanes of an interval as broadcast 128-bit loads.  Ring slabs are handed over with mbarriers once per rk4 step;
+//      registers are re-partitioned between the roles with setmaxnreg.  [A|B-|B+|Sigma] go from registers to the
+//      14x23 block with 16-byte stores; z is reduced over the 8 lanes and accumulated in place.
 #include "scvx_staged_dev.cuh"
 #include "scvx_kernels.h"
 
@@ -30,7 +31,8 @@ namespace {
 #endif
 // The kernel also propagates two of the four light tangent columns d/d(m, v0, v1, v2) — d/dv1 and d/dv2 (only their v
 // and r rows are non-trivial: K_v = Jvv Y_v, r rows a quadrature of the v rows; d/dm and d/dv0 ride in the two idle
-// slots of the tangent kernel).  Their 24 doubles of state live in shared memory, lane-private [entry][thread] (conflict-free), because the value chain already uses every register;
+// slots of the tangent kernel).  Their 24 doubles of state live in shared memory, lane-private [entry][thread]
+// (conflict-free), because the value chain already uses every register;
 // the Jacobian blocks they need (dF/dv, f_v, m) are at hand here, so no separate pass re-reads the stage records
 // (a separate one-thread-per-interval kernel was latency bound on those reads: 0.13 ms per chunk vs +0.03 ms here).
 constexpr size_t LIGHT_SMEM_BYTES = 24 * 128 * sizeof(double);

@@ -15,13 +15,14 @@ constexpr int GROUP = 32;        // intervals per CTA pass
 constexpr int NWARP = 8;
 
 // Jacobian record layout (doubles)
+// (entries that enter a stage increment carry sigma * c_i, c_i = the stage's rk4 factor; see consume_stage8)
 constexpr int J_WW = 0;          // 9  sigma * d(wdot)/dw, row-major
 constexpr int J_HW = 9;          // 3  sigma*w/2
 constexpr int J_HQ = 12;         // 4  sigma*q/2
 constexpr int J_V = 16;          // 3 rows x 8: [d(vdot_r)/dm, d(vdot_r)/dv (3), d(vdot_r)/dq (4)], all times sigma
 constexpr int J_G = 40;          // 4 columns (u0,u1,u2,f) x 7 rows (m, v0..2, w0..2)
-constexpr int J_FRQ = 68;        // 7  f_r (= v) and f_q of the unscaled rhs (sigma column only)
-constexpr int J_SIG = 75;        // 1  sigma
+constexpr int J_FRQ = 68;        // 7  f_r (= v, unscaled) and c_i * f_q (sigma column only)
+constexpr int J_SIG = 75;        // 1  sigma (unscaled: the r-row quadrature uses it)
 
 struct StagedArgs {
     ScvxBatch bt;
