@@ -15,7 +15,7 @@ from successiveconvexification_b200 import workloads
 from successiveconvexification_b200.defns import ProbInfo
 from successiveconvexification_b200.first_round import linear_points
 
-from conftest import GOLDEN, assert_parity
+from conftest import GOLDEN, assert_parity, parity_report
 
 
 def _inp(prob, i, sigma=1.0):
@@ -124,6 +124,36 @@ def test_oracle_vs_complex_step_restatement(prob_aero, prob_exo, oracle_tables, 
         blk = oracle.linearize_interval(info, tb, inp, 1 / 51, 10, mode)
         ref = np.concatenate([e[None], D.T, z[None]])[None]             # (1, 23, 14)
         assert_parity(blk.T[None], ref)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_oracle_vs_50_digit_arithmetic(prob_aero, oracle_tables, mode):
+    """The FP64 oracle against the same map evaluated and differentiated at 50 digits (oracle/mp_restatement.py):
+    the residual is pure FP64 rounding of the oracle, and it sets the floor of the parity metric (conftest)."""
+    from oracle import mp_restatement as mpr
+    info = ProbInfo(prob_aero)
+    P = mpr.probinfo_mp(info)
+    tb = oracle_tables
+    T = dict(drag=tb.drag, lift=tb.lift, geom=tb.geom)
+    rng = np.random.default_rng(5)
+    inp = _inp(prob_aero, 17, sigma=1.0 if mode == 0 else 6.0)
+    inp[7:11] += rng.normal(0, 0.2, 4); inp[7:11] /= np.linalg.norm(inp[7:11])        # lift branch, spin, gimbal
+    inp[11:14] += rng.normal(0, 0.05, 3); inp[15:17] += rng.normal(0, 0.003, 2)
+    e, D = mpr.linearize_interval(P, T, inp, 1 / 51, 10, mode)
+    blk = oracle.linearize_interval(info, tb, inp, 1 / 51, 10, mode)                  # (14, 23) column = block column
+    e64 = np.array([float(v) for v in e])
+    D64 = np.array([[float(v) for v in row] for row in D])
+    assert np.abs(blk[:, 0] - e64).max() <= 4e-16 * np.abs(e64).max()
+    got = blk[:, 1:22]
+    # per part, relative to the part's largest entry: FP64 evaluation of the oracle is good to a few 1e-16 of that
+    for lo, hi in ((0, 14), (14, 17), (17, 20), (20, 21)):
+        part, ref = got[:, lo:hi], D64[:, lo:hi]
+        assert np.abs(part - ref).max() <= 2e-14 * np.abs(ref).max()
+    # and it passes the parity metric used for the GPU with a wide margin
+    z = e64 - D64 @ inp
+    ref_blk = np.concatenate([e64[None], D64.T, z[None]])[None]
+    rep = parity_report(blk.T[None], ref_blk)
+    assert max(rep.values()) <= 1e-11, rep
 
 
 def test_oracle_vs_finite_differences(prob_aero, oracle_tables):
