@@ -294,6 +294,27 @@ def test_dispersed_setup_on_device(dyn, oracle_tables):
         assert np.allclose(p2[b]["jBi"].reshape(3, 3).T, info.jBi, rtol=1e-13, atol=0)
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("mode,sig", [(0, 1.0), (1, 6.0)])
+def test_against_50_digit_arithmetic(dyn, cache_aero, prob_aero, oracle_tables, kernel, mode, sig):
+    """The CUDA path against the map evaluated and differentiated at 50 digits (oracle/mp_restatement.py): parity
+    evidence that does not go through the FP64 C++ oracle."""
+    from oracle import mp_restatement as mpr
+    from successiveconvexification_b200 import workloads
+    from successiveconvexification_b200.defns import ProbInfo
+    cache_aero.sim_prob.set_kernel(kernel)
+    X, U, sigma, _ = workloads.monte_carlo_batch(prob_aero, 2, 1, 91, sigma_range=(sig, sig))
+    blocks, _, _ = dyn.linearize_batch(cache_aero, X, U, sigma, 1 / 51, 10, mode)
+    cache_aero.sim_prob.set_kernel(0)
+    inp = np.concatenate([X[0, 0], U[0, 0], U[0, 1], sigma[:1]])
+    T = dict(drag=oracle_tables.drag, lift=oracle_tables.lift, geom=oracle_tables.geom)
+    e, D = mpr.linearize_interval(mpr.probinfo_mp(ProbInfo(prob_aero)), T, inp, 1 / 51, 10, mode)
+    e64 = np.array([float(v) for v in e])
+    D64 = np.array([[float(v) for v in row] for row in D])
+    ref = np.concatenate([e64[None], D64.T, (e64 - D64 @ inp)[None]])[None, None]
+    assert_parity(blocks[:, :1], ref)
+
+
 def test_batched_initial_guess(dyn, cache_aero, prob_aero):
     """linear_points (initial_solve.jl:113-129) for a batch of dispersed initial conditions."""
     from successiveconvexification_b200 import workloads
