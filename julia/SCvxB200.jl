@@ -245,3 +245,26 @@ function Dynamics.predict_state(initial_state, uk, up, sigma, dt, pinfo, cache::
     X[:, 1, 1] .= initial_state; U[:, 1, 1] .= uk; U[:, 2, 1] .= up
     return SCvxB200.predict_batch(ctx, X, U, [Float64(sigma)], Float64(dt))[:, 1, 1]
 end
+
+# Replace dynamics.jl:308-313 (same signatures): value and (y, J') of the discrete map of one interval on the device.
+function _scvx_one_interval(inp::Vector{Float64})
+    X = zeros(14, 2, 1); U = zeros(3, 2, 1)
+    X[:, 1, 1] .= inp[1:14]; U[:, 1, 1] .= inp[15:17]; U[:, 2, 1] .= inp[18:20]
+    return X, U, [inp[21]]
+end
+
+function Dynamics.simulate_zygote(inp::Vector{Float64}, dt::Float64, cache::IntegratorCache; npts=10)
+    ctx = _scvx_ctx(cache)
+    X, U, sig = _scvx_one_interval(inp)
+    old = ctx.npts; ctx.npts = npts
+    y = SCvxB200.predict_batch(ctx, X, U, sig, dt)[:, 1, 1]
+    ctx.npts = old
+    return y
+end
+
+function Dynamics.sensitivity_zygote(inp::Vector{Float64}, dt::Float64, cache::IntegratorCache)
+    ctx = _scvx_ctx(cache)
+    X, U, sig = _scvx_one_interval(inp)
+    blocks, _, _ = SCvxB200.linearize_batch(ctx, X, U, sig, dt; lin_err=false, tlb=false)
+    return blocks[:, 1, 1, 1], permutedims(blocks[:, 2:22, 1, 1])      # (y, J') with J' 21 x 14, as Zygote.forward_jacobian
+end
