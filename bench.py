@@ -12,8 +12,13 @@ One "step" = one pass of the hot path over that batch.  No data-path collective:
 
   value  : intervals/s, inputs and outputs resident in HBM, CUDA events on the launching stream, max over ranks
   e2e    : same metric through the C-ABI call with pinned HOST buffers (H2D + kernels + D2H inside the timed region)
-  roofline : binding resource is the FP64 FMA pipe; `peak` is measured in this run by the library's
-             DFMA microbenchmark (MEASURED_PEAKS.json holds no FP64 figure); the HBM view is given beside it
+  e2e    : same metric through the C-ABI call a Monte-Carlo host makes, scvx_linearize_batch_compact, with pinned HOST
+           buffers (H2D + kernels + pack + D2H inside the timed region); the dense-block call is timed beside it
+  parity : conditioning-aware check of a random sample of the TIMED outputs against the CPU oracle in FP64 and binary128
+  roofline : binding resource is the FP64 FMA pipe; `peak` is measured in this run by a DFMA
+             microbenchmark (libscvx_benchtools.so; MEASURED_PEAKS.json holds no FP64 figure), the fraction of the
+             nominal 37.2 TFLOP/s is given beside it, and so is the HBM view
+  extra  : (N=1) the other BASELINE configs: C2 single-trajectory call latency, C3 / C4 throughput + roofline
   cpu_baseline : the CPU oracle (C++ restatement of the reference's Julia path; Julia is not installed) on the
              box's host cores, bounded sample.  A reported baseline, not the target.
 `--impl reference` times that CPU implementation alone (rank 0 only) and prints the same JSON line.
@@ -42,6 +47,45 @@ UNIT = "intervals/s"
 # algorithmic work per interval (SURVEY.md §8d / BASELINE.md §3), aero-table variant, npts = 10
 FLOP_PER_INTERVAL_AERO = 10 * (4 * (300 + 600 + 2 * 21 * 60 + 2 * 6 * 21 + 28) + 4620)     # 194 200
 BYTES_PER_INTERVAL = 8 * (21 + 14 * 23) + 8 * (14 + 4)                                        # 2 888 incl. lin_err + tlb
+FP64_NOMINAL_TF = 148 * 64 * 2 * 1.965e9 * 1e-12                                              # 37.2
+PARITY_SAMPLE = 64              # trajectories of the timed outputs checked against the oracle (3 200 intervals)
+
+
+def fp64_peak_tf(device_index):
+    """DFMA issue-rate microbenchmark (measurement helper library, not part of the product ABI)."""
+    import ctypes
+    from successiveconvexification_b200 import _lib
+    tf = ctypes.c_double()
+    rc = _lib.load_benchtools().scvx_bench_fp64_peak(int(device_index), ctypes.byref(tf))
+    if rc != 0:
+        raise RuntimeError(f"scvx_bench_fp64_peak failed ({rc})")
+    return tf.value
+
+
+def parity_of_timed_outputs(prob, X, U, sigma, P, dOut, dt, mode, threads):
+    """Conditioning-aware parity of a random sample of the timed outputs (tests/conftest.py: 1e-10 against the binary128
+    evaluation wherever FP64 can hold it; within K_COND x the reference arithmetic's own distance elsewhere)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import conftest
+    from oracle import oracle
+    tb = oracle.OracleTables.from_aero(prob.aero)
+    B = X.shape[0]
+    pick = np.sort(np.random.default_rng(SEED).choice(B, min(PARITY_SAMPLE, B), replace=False))
+    got = dOut[torch.from_numpy(pick).to(dOut.device)].cpu().numpy()
+    Pp = P if P.shape[0] == 1 else P[pick]
+    ref64, s64 = oracle.linearize_batch_ex(Pp, tb, X[pick], U[pick], sigma[pick], dt, NPTS, mode, nthreads=threads, precision=0)
+    refq, sq = oracle.linearize_batch_ex(Pp, tb, X[pick], U[pick], sigma[pick], dt, NPTS, mode, nthreads=threads, precision=1)
+    rep = conftest.conditioned_parity(got, ref64, refq, s64, sq)
+    rep["trajectories_sampled"] = int(len(pick))
+    rep["tolerance"] = conftest.PARITY_TOL
+    rep["k_cond"] = conftest.K_COND
+    rep["pass"] = bool(rep["max_metric_well_conditioned"] <= conftest.PARITY_TOL and
+                       rep["max_err_over_kappa_eps_ill_conditioned"] <= conftest.K_COND)
+    rep["vs_fp64_oracle_max_metric"] = float(conftest.parity_metric_per_interval(got, ref64).max())
+    rep["note"] = ("sample of the TIMED device outputs vs the CPU oracle in FP64 and IEEE binary128; LITERAL rk4 at sigma up to 15 "
+                   "is ill-conditioned, so intervals are split by the measured kappa*eps of the reference arithmetic")
+    return rep
 
 
 class ClockSampler:
@@ -156,6 +200,69 @@ def cpu_reference_run(prob, steps, warmup, traj_per_thread):
     return value, threads, sample, total / len(times)
 
 
+def other_configs(prob, ctx, dev, args, fp64_peak):
+    """The other BASELINE configs on one GPU (parity-test cases; reported for completeness, not the headline):
+      C2  one trajectory x 50 intervals through the host-pointer ABI: call latency (median of 200) — the only number the
+          unmodified SCvx loop (rocketland.jl:318, one linearize_dynamics per iteration) would feel;
+      C3  aero K=100, 4096 trajectories;  C4  K=400, 16384 trajectories, per-trajectory parameter sweep:
+          device-resident throughput + FP64 roofline fraction."""
+    import torch
+    from successiveconvexification_b200 import dynamics, workloads
+    out = {}
+    # ---- C2
+    X, U, sigma, dt = workloads.sample_trajectory(prob)
+    hX, hU, hS = (torch.from_numpy(a).pin_memory() for a in (X, U, sigma))
+    hOut = torch.empty((1, 50, 23, 14), dtype=torch.float64).pin_memory()
+    lat = []
+    for it in range(220):
+        t0 = time.perf_counter()
+        ctx.linearize_ptr(hX.data_ptr(), hU.data_ptr(), hS.data_ptr(), dt, NPTS, args.mode, 51, 1, hOut.data_ptr())
+        if it >= 20:
+            lat.append(time.perf_counter() - t0)
+    lat = np.array(lat) * 1e6
+    out["c2"] = {"workload": "C2: sample trajectory, 1 x 50 intervals, host pointers, dense blocks", "calls": 200,
+                 "latency_us_median": float(np.median(lat)), "latency_us_p90": float(np.percentile(lat, 90)),
+                 "intervals_per_s": 50.0 / (float(np.median(lat)) * 1e-6)}
+    # ---- C3, C4 (device resident)
+    stream = torch.cuda.current_stream()
+    for name, K, B, seed, sweep in (("c3", 100, 4096, 1001, False), ("c4", 400, 16384, 1002, True)):
+        Xc, Uc, sc, Pc = workloads.monte_carlo_batch(prob, K, B, seed, sweep=sweep)
+        if sweep:
+            ptr, n, keep = workloads.as_c_params(Pc)
+            ctx.set_params_raw(ptr, n)
+        dX, dU, dS = (torch.from_numpy(a).to(dev) for a in (Xc, Uc, sc))
+        dO = torch.empty((B, K, 23, 14), dtype=torch.float64, device=dev)
+        dT = torch.empty((B, K + 1, 4), dtype=torch.float64, device=dev)
+
+        def step():
+            ctx.linearize_ptr(dX.data_ptr(), dU.data_ptr(), dS.data_ptr(), 1.0 / (K + 1), NPTS, args.mode, K + 1, B,
+                              dO.data_ptr(), 0, dT.data_ptr())
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        steps = 10 if name == "c3" else 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        tf = FLOP_PER_INTERVAL_AERO * B * K / (ms * 1e-3) * 1e-12
+        out[name] = {"workload": f"{name.upper()}: K={K}, {B} trajectories{', per-trajectory parameter sweep' if sweep else ''}, "
+                                 f"device resident, mode={'LITERAL' if args.mode == 0 else 'TEXTBOOK'}, sigma ~ U(1, 15)",
+                     "intervals_per_s": B * K / (ms * 1e-3), "ms_per_step": ms, "steps": steps,
+                     "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak},
+                     "results_finite": bool(torch.isfinite(dO[:: max(1, B // 64)]).all().item()),
+                     "l2": f"outputs {dO.nbytes / 1e9:.1f} GB exceed L2"}
+        del dX, dU, dS, dO, dT
+        torch.cuda.empty_cache()
+        if sweep:
+            from successiveconvexification_b200.defns import ProbInfo
+            ctx.set_params(ProbInfo(prob))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -168,7 +275,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-assembly", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--sigma-range", default="1,15", help="sigma ~ U(lo,hi) of the synthetic batch (C5: 1,15)")
     args = ap.parse_args()
+    sig_lo, sig_hi = (float(v) for v in args.sigma_range.split(","))
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -180,7 +291,7 @@ def main():
     config = {"workload": f"C5 Monte-Carlo dispersion, aero-table 6-DoF sample problem, K={K_NODES} "
                           f"({K_NODES + 1} nodes, {K_NODES} intervals/trajectory), {args.traj_per_gpu} trajectories per GPU, "
                           f"discretise [A|B-|B+|Sigma|z] + lin_err + thrust-LB rows, npts={NPTS}, "
-                          f"mode={'LITERAL' if args.mode == 0 else 'TEXTBOOK'}",
+                          f"mode={'LITERAL' if args.mode == 0 else 'TEXTBOOK'}, sigma ~ U({sig_lo:g}, {sig_hi:g})",
               "trajectories_per_gpu": args.traj_per_gpu, "intervals_per_trajectory": K_NODES, "seed": SEED,
               "sharding": f"trajectory shards, {world} rank(s), no data-path collective",
               "l2": "inputs (227 MB/GPU) and outputs (4.7 GB/GPU) exceed the 126 MB L2; no flush needed"}
@@ -224,13 +335,13 @@ def main():
 
     # ---- this rank's shard (independent reproducible stream per shard; C5 = contiguous shards of 32768)
     B = args.traj_per_gpu
-    X, U, sigma, P = workloads.monte_carlo_batch(prob, K_NODES, B, SEED, shard=rank)
+    X, U, sigma, P = workloads.monte_carlo_batch(prob, K_NODES, B, SEED, shard=rank, sigma_range=(sig_lo, sig_hi))
     n_nodes, ni = K_NODES + 1, K_NODES
     dt = 1.0 / (K_NODES + 1)
     cache = dynamics.make_cache(prob, device_ids=[local_rank])
     ctx = cache.sim_prob
     ctx.set_kernel(args.kernel)
-    fp64_peak = ctx.measure_fp64_peak()
+    fp64_peak = fp64_peak_tf(local_rank)
 
     dX, dU, dS = (torch.from_numpy(a).to(dev) for a in (X, U, sigma))
     dOut = torch.empty((B, ni, 23, 14), dtype=torch.float64, device=dev)
@@ -305,35 +416,57 @@ def main():
                     "note": "in+out 8.7 GB per launch exceed L2; not part of the timed step"}
         del dVals, dRhs
 
-    # ---- end to end through the C ABI with pinned host buffers
+    # ---- end to end through the C ABI with pinned host buffers: the compact call (what a Monte-Carlo host uses: only
+    # the 229 data entries of a block + a status word cross PCIe) and, beside it, the dense-block call
     e2e = None
     if not args.no_e2e:
         hX, hU, hS = (torch.from_numpy(a).pin_memory() for a in (X, U, sigma))
+        hTlb = torch.empty((B, n_nodes, 4), dtype=torch.float64).pin_memory()
+
+        def timed_host(step, steps):
+            for _ in range(2):
+                step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                step()
+            barrier()
+            el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(el, op=dist.ReduceOp.MAX)
+            return total_intervals * steps / float(el.item())
+
+        e2e_steps = max(1, min(args.steps, 5))
+        hCmp = torch.empty((B, ni, 230), dtype=torch.float64).pin_memory()
+
+        def step_compact():
+            ctx.linearize_compact_ptr(hX.data_ptr(), hU.data_ptr(), hS.data_ptr(), dt, NPTS, args.mode, n_nodes, B,
+                                      hCmp.data_ptr(), hTlb.data_ptr())
+        v_compact = timed_host(step_compact, e2e_steps)
+        # the host expander restores the dense blocks bit for bit: check a slice against the device-pointer result
+        eb, ee, flagged = dynamics.expand_compact(hCmp[:4].numpy(), X[:4])
+        assert np.array_equal(eb, dOut[:4].cpu().numpy()), "compact host path and device-pointer path disagree"
+        assert np.array_equal(ee, dErr[:4].cpu().numpy()), "lin_err recomputed on the host differs"
+        d2h_compact = int(hCmp.nbytes + hTlb.nbytes)
+        n_flag = int((hCmp[..., 229] != 0).sum().item())
+        del hCmp
         hOut = torch.empty((B, ni, 23, 14), dtype=torch.float64).pin_memory()
         hErr = torch.empty((B, ni, 14), dtype=torch.float64).pin_memory()
-        hTlb = torch.empty((B, n_nodes, 4), dtype=torch.float64).pin_memory()
 
         def step_host():
             ctx.linearize_ptr(hX.data_ptr(), hU.data_ptr(), hS.data_ptr(), dt, NPTS, args.mode, n_nodes, B,
                               hOut.data_ptr(), hErr.data_ptr(), hTlb.data_ptr())
-        for _ in range(2):
-            step_host()
-        barrier()
-        e2e_steps = max(1, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            step_host()
-        barrier()
-        el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        dev_sample = dOut[:4].cpu()
-        assert torch.equal(hOut[:4], dev_sample), "host-pointer path and device-pointer path disagree"
-        e2e = {"value": total_intervals * e2e_steps / float(el.item()), "unit": UNIT,
+        v_dense = timed_host(step_host, e2e_steps)
+        assert torch.equal(hOut[:4], dOut[:4].cpu()), "host-pointer path and device-pointer path disagree"
+        e2e = {"value": v_compact, "unit": UNIT,
                "h2d_bytes_per_step": int(hX.nbytes + hU.nbytes + hS.nbytes),
-               "d2h_bytes_per_step": int(hOut.nbytes + hErr.nbytes + hTlb.nbytes), "steps": e2e_steps,
-               "note": "pinned host buffers through scvx_linearize_batch; chunked H2D/kernel/D2H pipeline; PCIe-bound; "
-                       + numa_note}
+               "d2h_bytes_per_step": d2h_compact, "steps": e2e_steps,
+               "call": "scvx_linearize_batch_compact (230-double records: 229 data entries + status word; lin_err recomputed "
+                       "exactly by scvx_expand_compact on the host)",
+               "intervals_flagged_non_finite": n_flag,
+               "dense": {"value": v_dense, "call": "scvx_linearize_batch (14x23 blocks + lin_err + tlb)",
+                         "d2h_bytes_per_step": int(hOut.nbytes + hErr.nbytes + hTlb.nbytes)},
+               "note": "pinned host buffers; chunked H2D/kernel/D2H pipeline; PCIe-bound; " + numa_note}
         del hOut, hErr, hTlb
 
     if rank != 0:
@@ -356,9 +489,11 @@ def main():
         pass
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp64_peak, "traffic": traffic,
+                "peak_nominal": FP64_NOMINAL_TF, "frac_nominal": achieved_tf / FP64_NOMINAL_TF,
                 "flop_per_interval": FLOP_PER_INTERVAL_AERO, "kernel_ms": kern_ms, "isolated_step_ms": single_step_ms,
                 "kernels": "stage_value_kernel + tangent_kernel, all launches of one step (W spans both)",
-                "peak_source": "in-run DFMA microbenchmark (scvx_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+                "peak_source": "in-run DFMA microbenchmark (libscvx_benchtools.so: scvx_bench_fp64_peak); MEASURED_PEAKS.json "
+                               "has no FP64 figure; nominal = 148 SM x 64 FMA/clk x 2 x 1.965 GHz",
                 "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                         "frac": achieved_gbs / hbm_peak, "bytes_per_interval": BYTES_PER_INTERVAL,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
@@ -366,6 +501,15 @@ def main():
     if assembly:
         assembly["peak"] = hbm_peak
         assembly["frac"] = assembly["achieved"] / hbm_peak
+    threads_avail = len(os.sched_getaffinity(0))
+    parity = None
+    if not args.no_parity:
+        parity = parity_of_timed_outputs(prob, X, U, sigma, P, dOut, dt, args.mode, threads_avail)
+    extra = None
+    if world == 1 and not args.no_extra:
+        del dOut, dErr, dTlb
+        torch.cuda.empty_cache()
+        extra = other_configs(prob, ctx, dev, args, fp64_peak)
     cpu = None
     if not args.no_cpu and world == 1:
         v, threads, sample, _ = cpu_reference_run(prob, steps=1, warmup=1, traj_per_thread=400)
@@ -376,7 +520,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "assembly": assembly, "results_finite": ok, "kernel": args.kernel}
+            "cpu_baseline": cpu, "parity": parity, "assembly": assembly, "extra": extra, "results_finite": ok,
+            "kernel": args.kernel}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)

@@ -18,7 +18,7 @@
  *     Columns 1..21 are LinRes.derivative (master.jl:90-93), column 0 is LinRes.endpoint,
  *     z = endpoint - D*inp (old_dynamics.jl:139, 150-153).
  *   - Pointers may be host or device memory (detected with cudaPointerGetAttributes); device
- *     pointers must live on the context's first device.  Host pointers stay caller-owned and must
+ *     pointers must live on one of the context's devices (the call runs there).  Host pointers stay caller-owned and must
  *     remain valid until the call returns (calls are synchronous for host pointers).  For device
  *     pointers the work is enqueued on the context stream (scvx_set_stream) and the call returns
  *     without synchronising.
@@ -113,6 +113,41 @@ int scvx_linearize_batch(scvx_ctx* ctx, const double* X, const double* U, const 
 int scvx_predict_batch(scvx_ctx* ctx, const double* X, const double* U, const double* sigma,
                        double base_dt, int npts, int mode, int n_nodes, int B, double* out_endpoints);
 
+/* Compact result format for hosts on the far side of PCIe.  92 of the 322 entries of a block are structural constants of
+ * the dynamics (nothing depends on position, the mass row and the q / w rows have fixed zero
+ * patterns), so the host path is bound by bytes it does not need.  The compact record of one interval holds only the
+ * data entries, in block (column-major) order, SCVX_COMPACT_DOUBLES = 230 doubles:
+ *   slots 0..228  the data entries of the block (scvx_compact_layout gives the dense offset of each slot):
+ *                 endpoint 14 | d/dm rows r,v 6 | d/dv rows r,v 18 | d/dq rows r,v,q 40 | d/dw rows r,v,q,w 39 |
+ *                 B- 42 | B+ 42 | Sigma 14 | z 14
+ *   slot  229     status word: 0.0 if every entry of the dense block is finite, 1.0 otherwise (per-interval non-finite
+ *                 flag; the constants of a flagged interval's dense block are not guaranteed)
+ * lin_err is not shipped: it is endpoint - x_{n+1}, one IEEE subtraction the host repeats exactly (scvx_expand_compact).
+ *   out_compact 230 x (n_nodes-1) x B      out_tlb 4 x n_nodes x B (optional)
+ * Host or device pointers, as scvx_linearize_batch. */
+#define SCVX_COMPACT_DOUBLES 230
+#define SCVX_COMPACT_DATA 229
+int scvx_linearize_batch_compact(scvx_ctx* ctx, const double* X, const double* U, const double* sigma,
+                                 double base_dt, int npts, int mode, int n_nodes, int B,
+                                 double* out_compact, double* out_tlb);
+/* Dense offset (column * 14 + row, 0 <= offset < 322) of compact slots 0..228; no device work.  `index` has room for
+ * SCVX_COMPACT_DATA int32. */
+int scvx_compact_layout(int32_t* index);
+/* Host-side expander (plain C loop on `n_threads` host threads, no device work; all pointers are HOST memory):
+ * compact 230 x K x B  ->  out_blocks 14 x 23 x K x B (may be NULL) with the structural constants filled in, equal to what
+ * scvx_linearize_batch writes for every interval whose status word is 0;  out_lin_err 14 x K x B (may be NULL; needs X
+ * 14 x n_nodes x B).  Returns the number of intervals whose status word is non-zero (>= 0), or a negative error code. */
+int64_t scvx_expand_compact(const double* compact, const double* X, int n_nodes, int B, double* out_blocks,
+                            double* out_lin_err, int n_threads);
+
+/* Page-locked host memory.  The chunked H2D / kernel / D2H pipeline of host-pointer calls overlaps copies with compute
+ * only for page-locked buffers (pageable memory makes every cudaMemcpyAsync a staged, serialising copy): allocate result
+ * arrays here, or pin arrays the host language owns (e.g. Julia Arrays) for the lifetime of the calls. */
+int scvx_host_alloc(void** out, uint64_t bytes);
+int scvx_host_free(void* p);
+int scvx_host_register(void* p, uint64_t bytes);
+int scvx_host_unregister(void* p);
+
 /* Fused cost / defect evaluation of the SCvx ratio test (rocketland.jl:289-290): per trajectory
  *   defect_b = sqrt( sum_k || x_{k+1} - endpoint_k ||^2 )   (= Julia's norm over the K defect vectors, = ||lin_err||_F)
  *   cost_b   = -X[0, n_nodes-1, b] + wNu * defect_b          (J_k; mass of the last node enters with weight -1)
@@ -146,23 +181,29 @@ int scvx_dispersed_setup_batch(scvx_ctx* ctx, const scvx_dim_problem* base, cons
 /* Fixed-pattern sparse SOCP rows.  The reference refreshes the K dynamics equality blocks
  * (rocketland.jl:117-133, 251-258) and the K+1 linearised thrust-lower-bound rows (rocketland.jl:194-201, 260-265)
  * with K*21 + 3(K+1) MOI.modify calls per iteration; their sparsity never changes.  These entry points give that
- * sub-matrix in compressed-sparse-column form for a direct conic-solver interface (ECOS-style A, b / G, h):
+ * sub-matrix in compressed-sparse-column form for a direct conic-solver interface:
  *   rows     14n + i (dynamics row i of interval n, Zeros cone), then 14K + n (thrust lower bound of node n, Nonpositives)
  *   columns  dxv[j,n] -> 14n + j;  duv[j,n] -> 14(K+1) + 3n + j;  dsig -> 17(K+1);  nuv[j,n] -> 17(K+1) + 1 + 14n + j
  *            (the reference's variable creation order, rocketland.jl:73-76: local column j = its variable 17(K+1) + j)
  *   values   A_n, B-_n, B+_n, Sigma_n (all 14 x 21 entries, structural zeros kept as eachcol() emits them), +1 on
- *            nuv[:,n+1], -1 on dxv[:,n+1], H_n = -u_n/|u_n| on duv[:,n];  constants  rhs = [lin_err ; Tmin - |u_n|]
- * with K = n_nodes - 1, n_rows = 15K + 1, n_cols = 31(K+1) + 1, nnz = 325K + 3. */
+ *            nuv[:,n+1], -1 on dxv[:,n+1], H_n = -u_n/|u_n| on duv[:,n];  constants  const = [lin_err ; Tmin - |u_n|]
+ * with K = n_nodes - 1, n_rows = 15K + 1, n_cols = 31(K+1) + 1, nnz = 325K + 3.
+ * SIGN CONVENTION: `const` is the constant term of the MOI VectorAffineFunction, i.e. the constraints read
+ *   M x + const  in Zeros        (rows 0 .. 14K-1,   rocketland.jl:129-131)
+ *   M x + const  in Nonpositives (rows 14K .. 15K,   rocketland.jl:199-201).
+ * A solver interface of the form  A x = b,  G x <= h  (ECOS / SCS style) takes  b = -const[0:14K],  h = -const[14K:]. */
 int scvx_socp_dims(int n_nodes, int* n_rows, int* n_cols, int* nnz);
 /* Pattern (host arrays, no device work): colptr n_cols + 1, rowind nnz; rows ascend inside a column. */
 int scvx_socp_pattern(int n_nodes, int32_t* colptr, int32_t* rowind);
 /* Values for B trajectories from the outputs of scvx_linearize_batch at the same inputs:
- *   blocks 14 x 23 x K x B, lin_err 14 x K x B, tlb 4 x n_nodes x B  ->  out_vals nnz x B, out_rhs n_rows x B (may be NULL;
- *   lin_err may be NULL then).  All host or all device pointers (device: enqueued on the context's stream). */
+ *   blocks 14 x 23 x K x B, lin_err 14 x K x B, tlb 4 x n_nodes x B  ->  out_vals nnz x B, out_const n_rows x B (may be
+ *   NULL; lin_err may be NULL then).  All host or all device pointers (device: enqueued on the context's stream).
+ *   n_nodes <= 50000 (one launch covers 340 K + 4 value/constant indices in blocks of 256 along gridDim.y). */
 int scvx_socp_values_batch(scvx_ctx* ctx, const double* blocks, const double* lin_err, const double* tlb, int n_nodes, int B,
-                           double* out_vals, double* out_rhs);
+                           double* out_vals, double* out_const);
 
-/* Stream used for device-pointer calls on the first device (a cudaStream_t; NULL = library stream). */
+/* Stream used for device-pointer calls (a cudaStream_t of the device the pointers live on; NULL = back to the library's
+ * own stream). */
 int scvx_set_stream(scvx_ctx* ctx, void* cuda_stream);
 /* Kernel selection (SCVX_KERNEL_*). */
 int scvx_set_kernel(scvx_ctx* ctx, int which);
@@ -173,10 +214,6 @@ int64_t scvx_launch_count(scvx_ctx* ctx);
 /* Device-event duration (ms) of the kernels of the last device-pointer linearize/predict call on the
  * first device; synchronises the stream. */
 int scvx_last_kernel_ms(scvx_ctx* ctx, double* ms);
-
-/* Dependent-chain-free FP64 FMA microbenchmark on the first device: writes the sustained DFMA rate
- * in TFLOP/s (2 flop per FMA).  Roofline denominator of the FP64-pipe-bound kernels. */
-int scvx_measure_fp64_peak(scvx_ctx* ctx, double* tflops);
 
 #ifdef __cplusplus
 }

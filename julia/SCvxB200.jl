@@ -8,8 +8,10 @@
 # `SCvxB200.Context`.  Everything else of the reference (SOCP assembly, Mosek solve, initial guess,
 # trust-region logic) is untouched.
 #
-# Written without a Julia toolchain in the build container (see INTEGRATION.md); it is mirrored 1:1 by
-# the ctypes binding successiveconvexification_b200/_lib.py, which the test-suite exercises.
+# UNVERIFIED UNDER JULIA: written without a Julia toolchain in the build container (see INTEGRATION.md).  It is
+# mirrored 1:1 by the ctypes binding successiveconvexification_b200/_lib.py, which the test-suite exercises, and
+# tests/test_abi.py checks its structure (every symbol bound, overrides inside the module).  tools/gen_golden.jl is the
+# recipe that pins the device path against the reference's own rk4 + forward Jacobian on a machine that has Julia.
 module SCvxB200
 
 using ..RocketlandDefns
@@ -45,16 +47,22 @@ check(rc::Integer) = rc == 0 ? nothing : error("scvx_b200 error $rc: $(last_erro
 device_count() = Int(ccall((:scvx_device_count, LIB), Cint, ()))
 version() = Int(ccall((:scvx_version, LIB), Cint, ()))
 
+# `mode` is the stage rule of the rk4-based entry points simulate_zygote / sensitivity_zygote and of the batched calls:
+# LITERAL = the reference's arithmetic (dynamics.jl:126-128).  `live_mode` is the rule used when the device stands in for
+# the reference's LIVE entry points linearize_dynamics / predict_state, which integrate the continuous dynamics with an
+# adaptive BS3 solve (dynamics.jl:288-305): the consistent fixed-step integrator for those is classical RK4, so the
+# default there is TEXTBOOK (the LITERAL rule is not a consistent integrator and would silently change SCvx iterates).
 mutable struct Context
     handle::Ptr{Cvoid}
     npts::Int
     mode::Cint
-    function Context(device_ids::Vector{Int}=[0]; npts::Int=10, mode::Cint=MODE_LITERAL)
+    live_mode::Cint
+    function Context(device_ids::Vector{Int}=[0]; npts::Int=10, mode::Cint=MODE_LITERAL, live_mode::Cint=MODE_TEXTBOOK)
         @assert ccall((:scvx_sizeof_probinfo, LIB), Cint, ()) == sizeof(CProbInfo)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         ids = Cint.(device_ids)
         check(ccall((:scvx_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cint}, Cint), h, ids, length(ids)))
-        ctx = new(h[], npts, mode)
+        ctx = new(h[], npts, mode, live_mode)
         finalizer(c -> (c.handle != C_NULL && ccall((:scvx_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.handle); c.handle = C_NULL), ctx)
         return ctx
     end
@@ -90,15 +98,9 @@ function last_kernel_ms(ctx::Context)
     return ms[]
 end
 
-function measure_fp64_peak(ctx::Context)
-    tf = Ref{Cdouble}(0.0)
-    check(ccall((:scvx_measure_fp64_peak, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}), ctx.handle, tf))
-    return tf[]
-end
-
 # Batched entry points.  X: 14 x n_nodes x B, U: 3 x n_nodes x B, sigma: B  (plain Julia arrays, column-major).
 function linearize_batch(ctx::Context, X::Array{Float64,3}, U::Array{Float64,3}, sigma::Vector{Float64}, base_dt::Float64;
-                         lin_err::Bool=true, tlb::Bool=true)
+                         lin_err::Bool=true, tlb::Bool=true, mode::Cint=ctx.mode)
     n_nodes, B = size(X, 2), size(X, 3)
     blocks = Array{Float64,4}(undef, 14, 23, n_nodes - 1, B)
     err = lin_err ? Array{Float64,3}(undef, 14, n_nodes - 1, B) : Array{Float64,3}(undef, 0, 0, 0)
@@ -107,19 +109,70 @@ function linearize_batch(ctx::Context, X::Array{Float64,3}, U::Array{Float64,3},
         check(ccall((:scvx_linearize_batch, LIB), Cint,
                     (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Cint, Cint, Cint,
                      Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
-                    ctx.handle, X, U, sigma, base_dt, ctx.npts, ctx.mode, n_nodes, B,
+                    ctx.handle, X, U, sigma, base_dt, ctx.npts, mode, n_nodes, B,
                     blocks, lin_err ? pointer(err) : Ptr{Cdouble}(C_NULL), tlb ? pointer(tl) : Ptr{Cdouble}(C_NULL)))
     end
     return blocks, err, tl
 end
 
-function predict_batch(ctx::Context, X::Array{Float64,3}, U::Array{Float64,3}, sigma::Vector{Float64}, base_dt::Float64)
+# Compact result records (scvx_linearize_batch_compact): only the 229 data entries of every 14 x 23 block (+ a
+# per-interval non-finite flag) cross PCIe.  `expand_compact` restores the dense blocks and lin_err on the host.
+const COMPACT_DOUBLES = 230
+const COMPACT_DATA = 229
+
+function linearize_batch_compact(ctx::Context, X::Array{Float64,3}, U::Array{Float64,3}, sigma::Vector{Float64},
+                                 base_dt::Float64; tlb::Bool=true, mode::Cint=ctx.mode,
+                                 out::Union{Nothing,Array{Float64,3}}=nothing)
+    n_nodes, B = size(X, 2), size(X, 3)
+    comp = out === nothing ? Array{Float64,3}(undef, COMPACT_DOUBLES, n_nodes - 1, B) : out
+    tl = tlb ? Array{Float64,3}(undef, 4, n_nodes, B) : Array{Float64,3}(undef, 0, 0, 0)
+    GC.@preserve X U sigma comp tl begin
+        check(ccall((:scvx_linearize_batch_compact, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Cint, Cint, Cint,
+                     Ptr{Cdouble}, Ptr{Cdouble}),
+                    ctx.handle, X, U, sigma, base_dt, ctx.npts, mode, n_nodes, B,
+                    comp, tlb ? pointer(tl) : Ptr{Cdouble}(C_NULL)))
+    end
+    return comp, tl
+end
+
+# dense offsets (0-based, column * 14 + row) of compact slots 1..229
+function compact_layout()
+    idx = Vector{Int32}(undef, COMPACT_DATA)
+    check(ccall((:scvx_compact_layout, LIB), Cint, (Ptr{Int32},), idx))
+    return idx
+end
+
+# -> blocks 14 x 23 x K x B, lin_err 14 x K x B, number of intervals flagged non-finite
+function expand_compact(compact::Array{Float64,3}, X::Array{Float64,3}; n_threads::Int=0)
+    K, B = size(compact, 2), size(compact, 3)
+    blocks = Array{Float64,4}(undef, 14, 23, K, B); err = Array{Float64,3}(undef, 14, K, B)
+    n = GC.@preserve compact X blocks err ccall((:scvx_expand_compact, LIB), Int64,
+            (Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint), compact, X, K + 1, B, blocks, err, n_threads)
+    n < 0 && check(n)
+    return blocks, err, Int(n)
+end
+
+# Page-locked host memory: the H2D / kernel / D2H pipeline of host-pointer calls only overlaps for pinned buffers.
+# `pin!(A)` registers a Julia array in place (keep it alive and call `unpin!(A)` before it is freed);
+# `pinned_array(T, dims...)` allocates one through the library (free with `free_pinned!`).
+pin!(A::Array) = (check(ccall((:scvx_host_register, LIB), Cint, (Ptr{Cvoid}, UInt64), A, sizeof(A))); A)
+unpin!(A::Array) = (check(ccall((:scvx_host_unregister, LIB), Cint, (Ptr{Cvoid},), A)); A)
+function pinned_array(::Type{T}, dims::Integer...) where {T}
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:scvx_host_alloc, LIB), Cint, (Ref{Ptr{Cvoid}}, UInt64), p, prod(dims) * sizeof(T)))
+    return unsafe_wrap(Array, Ptr{T}(p[]), dims; own=false)
+end
+free_pinned!(A::Array) = check(ccall((:scvx_host_free, LIB), Cint, (Ptr{Cvoid},), A))
+
+function predict_batch(ctx::Context, X::Array{Float64,3}, U::Array{Float64,3}, sigma::Vector{Float64}, base_dt::Float64;
+                       mode::Cint=ctx.mode)
     n_nodes, B = size(X, 2), size(X, 3)
     out = Array{Float64,3}(undef, 14, n_nodes - 1, B)
     GC.@preserve X U sigma out begin
         check(ccall((:scvx_predict_batch, LIB), Cint,
                     (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Cint, Cint, Cint, Ptr{Cdouble}),
-                    ctx.handle, X, U, sigma, base_dt, ctx.npts, ctx.mode, n_nodes, B, out))
+                    ctx.handle, X, U, sigma, base_dt, ctx.npts, mode, n_nodes, B, out))
     end
     return out
 end
@@ -207,8 +260,9 @@ end
 
 # IntegratorCache(prob, info) replacement (reference dynamics.jl:258-260): context + parameters + tables.
 # `aero_samples = (drag, lift, torque, aoa_range, mach_range)` are the matrices / ranges of aerodynamics.jl:17-21.
-function make_cache(prob::DescentProblem, info::ProbInfo; device_ids::Vector{Int}=[0], aero_samples=nothing)
-    ctx = Context(device_ids)
+function make_cache(prob::DescentProblem, info::ProbInfo; device_ids::Vector{Int}=[0], aero_samples=nothing,
+                    mode::Cint=MODE_LITERAL, live_mode::Cint=MODE_TEXTBOOK)
+    ctx = Context(device_ids; mode=mode, live_mode=live_mode)
     set_params!(ctx, [CProbInfo(info, prob.Tmin)])
     if info.aero isa AtmosphericData
         aero_samples === nothing && error("AtmosphericData needs aero_samples = (drag, lift, torque, aoa, mach)")
@@ -218,12 +272,17 @@ function make_cache(prob::DescentProblem, info::ProbInfo; device_ids::Vector{Int
     return IntegratorCache(ctx, nothing, nothing, nothing, Any[1.0, info], info)
 end
 
-end # module
+
 
 # ---- methods added to the reference's own entry points -------------------------------------------------
+# Defined INSIDE this module: `using ..RocketlandDefns` brings LinPoint / LinRes / IntegratorCache into scope here
+# (master.jl exports them from RocketlandDefns but never does `using .RocketlandDefns` in Main, so unqualified names at
+# top level would be undefined), and `import ..Dynamics` lets `function Dynamics.f(...)` add methods to its functions.
+# The signatures equal the reference's, so these definitions REPLACE its methods (Julia prints a method-overwrite
+# note); the replacement only acts on caches built by `make_cache` — any other cache raises an error.
 function _scvx_ctx(cache::IntegratorCache)
-    cache.sim_prob isa SCvxB200.Context || error("cache does not hold a SCvxB200.Context")
-    return cache.sim_prob::SCvxB200.Context
+    cache.sim_prob isa Context || error("cache does not hold a Context")
+    return cache.sim_prob::Context
 end
 
 # Replaces the method of dynamics.jl:321-334 (same signature); the cache must hold a device context.
@@ -234,7 +293,7 @@ function Dynamics.linearize_dynamics(states::Array{LinPoint,1}, tf_guess::Float6
     for i = 1:n
         X[:, i, 1] .= states[i].state; U[:, i, 1] .= states[i].control
     end
-    blocks, _, _ = SCvxB200.linearize_batch(ctx, X, U, [tf_guess], base_dt; lin_err=false, tlb=false)
+    blocks, _, _ = linearize_batch(ctx, X, U, [tf_guess], base_dt; lin_err=false, tlb=false, mode=ctx.live_mode)
     return [LinRes(blocks[:, 1, i, 1], blocks[:, 2:22, i, 1]) for i = 1:n-1]
 end
 
@@ -243,7 +302,7 @@ function Dynamics.predict_state(initial_state, uk, up, sigma, dt, pinfo, cache::
     ctx = _scvx_ctx(cache)
     X = zeros(14, 2, 1); U = zeros(3, 2, 1)
     X[:, 1, 1] .= initial_state; U[:, 1, 1] .= uk; U[:, 2, 1] .= up
-    return SCvxB200.predict_batch(ctx, X, U, [Float64(sigma)], Float64(dt))[:, 1, 1]
+    return predict_batch(ctx, X, U, [Float64(sigma)], Float64(dt); mode=ctx.live_mode)[:, 1, 1]
 end
 
 # Replace dynamics.jl:308-313 (same signatures): value and (y, J') of the discrete map of one interval on the device.
@@ -257,7 +316,7 @@ function Dynamics.simulate_zygote(inp::Vector{Float64}, dt::Float64, cache::Inte
     ctx = _scvx_ctx(cache)
     X, U, sig = _scvx_one_interval(inp)
     old = ctx.npts; ctx.npts = npts
-    y = SCvxB200.predict_batch(ctx, X, U, sig, dt)[:, 1, 1]
+    y = predict_batch(ctx, X, U, sig, dt)[:, 1, 1]
     ctx.npts = old
     return y
 end
@@ -265,6 +324,8 @@ end
 function Dynamics.sensitivity_zygote(inp::Vector{Float64}, dt::Float64, cache::IntegratorCache)
     ctx = _scvx_ctx(cache)
     X, U, sig = _scvx_one_interval(inp)
-    blocks, _, _ = SCvxB200.linearize_batch(ctx, X, U, sig, dt; lin_err=false, tlb=false)
+    blocks, _, _ = linearize_batch(ctx, X, U, sig, dt; lin_err=false, tlb=false)
     return blocks[:, 1, 1, 1], permutedims(blocks[:, 2:22, 1, 1])      # (y, J') with J' 21 x 14, as Zygote.forward_jacobian
 end
+
+end # module

@@ -19,7 +19,7 @@ def build(force: bool = False) -> str:
     if (not force) and os.path.exists(OUT) and os.path.getmtime(OUT) >= os.path.getmtime(SRC):
         return OUT
     cmd = ["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-std=c++17",
-           "-Wall", "-o", OUT, SRC]
+           "-Wall", "-o", OUT, SRC, "-lquadmath"]
     subprocess.check_call(cmd)
     return OUT
 

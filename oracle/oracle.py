@@ -142,6 +142,25 @@ def linearize_batch(infos, tables, X, U, sigma, dt, npts=10, mode=0, want_lin_er
     return blocks, lin_err, tlb, used
 
 
+def linearize_batch_ex(infos, tables, X, U, sigma, dt, npts=10, mode=0, nthreads=0, precision=0):
+    """As `linearize_batch`, in IEEE double (precision=0) or IEEE binary128 rounded to double on output
+    (precision=1), plus the branch signature of every interval.
+    -> blocks (B, n_nodes-1, 23, 14), sig (B, n_nodes-1) uint64."""
+    X, U, sigma = _c(X), _c(U), _c(sigma)
+    B, n_nodes, _ = X.shape
+    arr, n = _params(infos)
+    assert n in (1, B)
+    blocks = np.zeros((B, n_nodes - 1, 23, 14))
+    sig = np.zeros((B, n_nodes - 1), dtype=np.uint64)
+    d, l, g = _tb(tables)
+    L = lib()
+    L.oracle_linearize_batch_ex.restype = ctypes.c_int
+    L.oracle_linearize_batch_ex(arr, n, d, l, g, _p(X), _p(U), _p(sigma), ctypes.c_double(dt), npts, mode, n_nodes, B,
+                                _p(blocks), None, None, nthreads, precision,
+                                sig.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
+    return blocks, sig
+
+
 def predict_batch(infos, tables, X, U, sigma, dt, npts=10, mode=0, nthreads=0):
     X, U, sigma = _c(X), _c(U), _c(sigma)
     B, n_nodes, _ = X.shape

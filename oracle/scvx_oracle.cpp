@@ -29,9 +29,10 @@
 // reference legs may load this library.  The product (.so under
 // successiveconvexification_b200/csrc) never links, loads or calls it.
 //
-// Build: oracle/build.py  (g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC)
+// Build: oracle/build.py  (g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC ... -lquadmath)
 
 #include <cmath>
+#include <quadmath.h>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -43,46 +44,63 @@
 namespace {
 
 // ----------------------------------------------------------------------------------------------
-// Dual numbers with N partials (ForwardDiff.Dual{T,Float64,N} semantics).
+// Real types.  The path is evaluated in IEEE double (the reference's Float64) and, for the
+// conditioning-aware parity checks, in IEEE binary128 (__float128, libquadmath): same operation
+// sequence, same double-valued constants, parameters, inputs and spline coefficients, 113-bit
+// arithmetic — i.e. the exact value (to ~1e-33) of the function the FP64 code approximates.  The
+// distance of the FP64 result from it is a direct measurement of kappa * eps for that interval.
 // ----------------------------------------------------------------------------------------------
-template <int N>
+typedef __float128 quad;
+inline double real_sqrt(double a) { return std::sqrt(a); }
+inline quad real_sqrt(quad a) { return sqrtq(a); }
+inline double real_floor(double a) { return std::floor(a); }
+inline quad real_floor(quad a) { return floorq(a); }
+inline double real_abs(double a) { return std::fabs(a); }
+inline quad real_abs(quad a) { return fabsq(a); }
+
+// ----------------------------------------------------------------------------------------------
+// Dual numbers with N partials (ForwardDiff.Dual{T,Float64,N} semantics) over the real type R.
+// ----------------------------------------------------------------------------------------------
+template <class R, int N>
 struct Dual {
-    double v;
-    double d[N];
+    R v;
+    R d[N];
     Dual() : v(0.0) { for (int i = 0; i < N; ++i) d[i] = 0.0; }
-    Dual(double x) : v(x) { for (int i = 0; i < N; ++i) d[i] = 0.0; }
+    Dual(R x) : v(x) { for (int i = 0; i < N; ++i) d[i] = 0.0; }
 };
 
-template <int N> inline Dual<N> operator+(const Dual<N>& a, const Dual<N>& b) {
-    Dual<N> r; r.v = a.v + b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
-template <int N> inline Dual<N> operator-(const Dual<N>& a, const Dual<N>& b) {
-    Dual<N> r; r.v = a.v - b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
-template <int N> inline Dual<N> operator-(const Dual<N>& a) {
-    Dual<N> r; r.v = -a.v; for (int i = 0; i < N; ++i) r.d[i] = -a.d[i]; return r; }
-template <int N> inline Dual<N> operator*(const Dual<N>& a, const Dual<N>& b) {
-    Dual<N> r; r.v = a.v * b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
-template <int N> inline Dual<N> operator/(const Dual<N>& a, const Dual<N>& b) {
-    Dual<N> r; r.v = a.v / b.v; const double ib = 1.0 / b.v;
+#define DT template <class R, int N> inline Dual<R, N>
+DT operator+(const Dual<R, N>& a, const Dual<R, N>& b) {
+    Dual<R, N> r; r.v = a.v + b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
+DT operator-(const Dual<R, N>& a, const Dual<R, N>& b) {
+    Dual<R, N> r; r.v = a.v - b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
+DT operator-(const Dual<R, N>& a) {
+    Dual<R, N> r; r.v = -a.v; for (int i = 0; i < N; ++i) r.d[i] = -a.d[i]; return r; }
+DT operator*(const Dual<R, N>& a, const Dual<R, N>& b) {
+    Dual<R, N> r; r.v = a.v * b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
+DT operator/(const Dual<R, N>& a, const Dual<R, N>& b) {
+    Dual<R, N> r; r.v = a.v / b.v; const R ib = 1.0 / b.v;
     for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
     return r; }
-template <int N> inline Dual<N> operator+(const Dual<N>& a, double b) { Dual<N> r = a; r.v += b; return r; }
-template <int N> inline Dual<N> operator+(double a, const Dual<N>& b) { return b + a; }
-template <int N> inline Dual<N> operator-(const Dual<N>& a, double b) { Dual<N> r = a; r.v -= b; return r; }
-template <int N> inline Dual<N> operator-(double a, const Dual<N>& b) { return (-b) + a; }
-template <int N> inline Dual<N> operator*(const Dual<N>& a, double b) {
-    Dual<N> r; r.v = a.v * b; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b; return r; }
-template <int N> inline Dual<N> operator*(double a, const Dual<N>& b) { return b * a; }
-template <int N> inline Dual<N> operator/(const Dual<N>& a, double b) {
-    Dual<N> r; r.v = a.v / b; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] / b; return r; }
-template <int N> inline Dual<N> operator/(double a, const Dual<N>& b) { return Dual<N>(a) / b; }
-template <int N> inline Dual<N> sqrt(const Dual<N>& a) {
-    Dual<N> r; r.v = std::sqrt(a.v); const double s = 0.5 / r.v;
+DT operator+(const Dual<R, N>& a, double b) { Dual<R, N> r = a; r.v += b; return r; }
+DT operator+(double a, const Dual<R, N>& b) { return b + a; }
+DT operator-(const Dual<R, N>& a, double b) { Dual<R, N> r = a; r.v -= b; return r; }
+DT operator-(double a, const Dual<R, N>& b) { return (-b) + a; }
+DT operator*(const Dual<R, N>& a, double b) {
+    Dual<R, N> r; r.v = a.v * b; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b; return r; }
+DT operator*(double a, const Dual<R, N>& b) { return b * a; }
+DT operator/(const Dual<R, N>& a, double b) {
+    Dual<R, N> r; r.v = a.v / b; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] / b; return r; }
+DT operator/(double a, const Dual<R, N>& b) { return Dual<R, N>(a) / b; }
+DT sqrt(const Dual<R, N>& a) {
+    Dual<R, N> r; r.v = real_sqrt(a.v); const R s = 0.5 / r.v;
     for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * s;
     return r; }
+#undef DT
 inline double sqrt(double a) { return std::sqrt(a); }
 
 inline double value_of(double x) { return x; }
-template <int N> inline double value_of(const Dual<N>& x) { return x.v; }
+template <class R, int N> inline R value_of(const Dual<R, N>& x) { return x.v; }
 
 // Base.clamp(x, lo, hi): returns x itself (partials kept) unless STRICTLY outside,
 // in which case the bound is returned as a constant (zero partials).
@@ -91,6 +109,12 @@ template <class T> inline T clamp_like_julia(const T& x, double lo, double hi) {
     if (value_of(x) < lo) return T(lo);
     return x;
 }
+
+// Branch signature of one evaluation: every data-dependent decision of the path (the |dp| >= 0.95 branch, active
+// clamps, spline cell indices) is folded into a 64-bit hash.  Two evaluations of the same interval (FP64 / binary128)
+// that took different decisions differentiate DIFFERENT smooth pieces of the map and cannot be compared entry by entry.
+thread_local uint64_t g_sig = 0;
+inline void sig_mix(int token) { g_sig = (g_sig ^ (uint64_t)(uint32_t)token) * 1099511628211ULL; }
 
 // ----------------------------------------------------------------------------------------------
 // Problem parameters: mirror of ProbInfo (master.jl:73-83) + AtmosphericData scalars
@@ -164,10 +188,13 @@ template <class T>
 T spline_eval(const Table& t, const T& x, const T& y) {
     const int L1 = t.n1 + 2;
     // scale(): index coordinate; extrapolate(Flat()): clamp to [1, n] (constant when strictly outside)
-    T xi = clamp_like_julia((x - t.x0) / t.dx + 1.0, 1.0, (double)t.n1);
-    T yi = clamp_like_julia((y - t.y0) / t.dy + 1.0, 1.0, (double)t.n2);
-    int i = (int)std::floor(value_of(xi)); if (i > t.n1 - 1) i = t.n1 - 1; if (i < 1) i = 1;
-    int j = (int)std::floor(value_of(yi)); if (j > t.n2 - 1) j = t.n2 - 1; if (j < 1) j = 1;
+    const T xr = (x - t.x0) / t.dx + 1.0, yr = (y - t.y0) / t.dy + 1.0;
+    T xi = clamp_like_julia(xr, 1.0, (double)t.n1);
+    T yi = clamp_like_julia(yr, 1.0, (double)t.n2);
+    int i = (int)real_floor(value_of(xi)); if (i > t.n1 - 1) i = t.n1 - 1; if (i < 1) i = 1;
+    int j = (int)real_floor(value_of(yi)); if (j > t.n2 - 1) j = t.n2 - 1; if (j < 1) j = 1;
+    sig_mix(i); sig_mix(j);
+    sig_mix((value_of(xr) > (double)t.n1 ? 1 : value_of(xr) < 1.0 ? 2 : 0) | (value_of(yr) > (double)t.n2 ? 4 : value_of(yr) < 1.0 ? 8 : 0));
     const T dx = xi - (double)i, dy = yi - (double)j;
     const T ox = 1.0 - dx, oy = 1.0 - dy;
     // value_weights(::Cubic, δ)
@@ -216,10 +243,12 @@ template <class T>
 void aero_force(const ProbInfo& P, const Tables& tb, const T bv[3], const T vel[3], T F[3]) {
     const T nv = norm3(vel);
     const T dp = (bv[0] * vel[0] + bv[1] * vel[1] + bv[2] * vel[2]) / nv;          // :39
-    const T cos_aoa = clamp_like_julia(dp / norm3(bv), -1.0, 1.0);                   // :40
+    const T car = dp / norm3(bv);
+    const T cos_aoa = clamp_like_julia(car, -1.0, 1.0);                              // :40
+    sig_mix((real_abs(value_of(dp)) >= 0.95 ? 16 : 0) | (value_of(car) > 1.0 ? 32 : value_of(car) < -1.0 ? 64 : 0));
     const T mach = nv / P.sos;                                                        // :41
     const T drag = spline_eval(tb.drag, cos_aoa, mach) * P.force_scalar;             // :43 / :47
-    if (std::fabs(value_of(dp)) >= 0.95) {                                            // :42
+    if (real_abs(value_of(dp)) >= 0.95) {                                            // :42
         for (int k = 0; k < 3; ++k) F[k] = drag * vel[k] / nv;                        // :44
         return;
     }
@@ -306,18 +335,27 @@ void rk4(const ProbInfo& P, const Tables& tb, const T inp[21], double dt, int np
 
 // sensitivity_zygote (dynamics.jl:311-313) for one interval + named outputs of old_dynamics.jl:84-98.
 // block: 14 x 23 column-major, col 0 = endpoint, cols 1..21 = D = d endpoint / d inp, col 22 = z.
-void linearize_interval(const ProbInfo& P, const Tables& tb, const double inp[21], double dt, int npts, int mode,
-                        double* block) {
-    typedef Dual<21> D21;
+// R = double: the reference's arithmetic.  R = quad: the same operation sequence in binary128, results rounded to
+// double on output (z is formed in R before rounding).  Returns the branch signature of the evaluation.
+template <class R>
+uint64_t linearize_interval_t(const ProbInfo& P, const Tables& tb, const double inp[21], double dt, int npts, int mode,
+                              double* block) {
+    typedef Dual<R, 21> D21;
     D21 din[21], out[14];
-    for (int k = 0; k < 21; ++k) { din[k] = D21(inp[k]); din[k].d[k] = 1.0; }
+    for (int k = 0; k < 21; ++k) { din[k] = D21((R)inp[k]); din[k].d[k] = 1.0; }
+    g_sig = 1469598103934665603ULL;
     rk4<D21>(P, tb, din, dt, npts, mode, out);
     for (int r = 0; r < 14; ++r) {
-        block[r] = out[r].v;
-        double zr = out[r].v;
-        for (int c = 0; c < 21; ++c) { block[r + 14 * (1 + c)] = out[r].d[c]; zr -= out[r].d[c] * inp[c]; }
-        block[r + 14 * 22] = zr;
+        block[r] = (double)out[r].v;
+        R zr = out[r].v;
+        for (int c = 0; c < 21; ++c) { block[r + 14 * (1 + c)] = (double)out[r].d[c]; zr -= out[r].d[c] * inp[c]; }
+        block[r + 14 * 22] = (double)zr;
     }
+    return g_sig;
+}
+inline void linearize_interval(const ProbInfo& P, const Tables& tb, const double inp[21], double dt, int npts, int mode,
+                               double* block) {
+    linearize_interval_t<double>(P, tb, inp, dt, npts, mode, block);
 }
 
 Tables make_tables(const double* drag_coef, const double* lift_coef, const double* geom) {
@@ -352,8 +390,8 @@ int oracle_prefilter(const double* samples, int n1, int n2, double* coef) {
 // value and gradient (d/dx, d/dy) of the scaled, Flat-extrapolated spline at (x, y)
 double oracle_spline_eval(const double* coef, const double* geom, double x, double y, double* grad) {
     Table t{ coef, (int)geom[0], (int)geom[1], geom[2], geom[3], geom[4], geom[5] };
-    Dual<2> dx(x), dy(y); dx.d[0] = 1.0; dy.d[1] = 1.0;
-    Dual<2> r = spline_eval(t, dx, dy);
+    Dual<double, 2> dx(x), dy(y); dx.d[0] = 1.0; dy.d[1] = 1.0;
+    Dual<double, 2> r = spline_eval(t, dx, dy);
     if (grad) { grad[0] = r.d[0]; grad[1] = r.d[1]; }
     return r.v;
 }
@@ -390,10 +428,12 @@ void oracle_linearize_interval(const ProbInfo* P, const double* drag_coef, const
 //   out_blocks 14 x 23 x (n_nodes-1) x B; out_lin_err 14 x (n_nodes-1) x B (endpoint_n - xbar_{n+1},
 //   rocketland.jl:130,256); out_tlb 4 x n_nodes x B = [-u/|u| ; Tmin - |u|] (rocketland.jl:199-200,261-263).
 // Returns the number of threads used.
-int oracle_linearize_batch(const ProbInfo* P, int n_params, const double* drag_coef, const double* lift_coef,
-                           const double* geom, const double* X, const double* U, const double* sigma, double dt,
-                           int npts, int mode, int n_nodes, int B, double* out_blocks, double* out_lin_err,
-                           double* out_tlb, int nthreads) {
+// precision: 0 = IEEE double (the reference's arithmetic), 1 = IEEE binary128 evaluation rounded to double on output.
+// out_sig (optional, (n_nodes-1) x B): branch signature of every interval (see sig_mix).
+int oracle_linearize_batch_ex(const ProbInfo* P, int n_params, const double* drag_coef, const double* lift_coef,
+                              const double* geom, const double* X, const double* U, const double* sigma, double dt,
+                              int npts, int mode, int n_nodes, int B, double* out_blocks, double* out_lin_err,
+                              double* out_tlb, int nthreads, int precision, uint64_t* out_sig) {
     Tables tb = make_tables(drag_coef, lift_coef, geom);
     const int ni = n_nodes - 1;
     const long total = (long)ni * B;
@@ -401,7 +441,7 @@ int oracle_linearize_batch(const ProbInfo* P, int n_params, const double* drag_c
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
     used = nthreads > 0 ? nthreads : omp_get_max_threads();
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(dynamic, 4)
 #endif
     for (long w = 0; w < total; ++w) {
         const int b = (int)(w / ni), i = (int)(w % ni);
@@ -413,7 +453,9 @@ int oracle_linearize_batch(const ProbInfo* P, int n_params, const double* drag_c
         for (int k = 0; k < 3; ++k) { inp[14 + k] = ub[k]; inp[17 + k] = ub[3 + k]; }
         inp[20] = sigma[b];
         double* blk = out_blocks + (size_t)w * 14 * 23;
-        linearize_interval(Pb, tb, inp, dt, npts, mode, blk);
+        const uint64_t sg = precision == 1 ? linearize_interval_t<quad>(Pb, tb, inp, dt, npts, mode, blk)
+                                           : linearize_interval_t<double>(Pb, tb, inp, dt, npts, mode, blk);
+        if (out_sig) out_sig[w] = sg;
         if (out_lin_err) for (int k = 0; k < 14; ++k) out_lin_err[(size_t)w * 14 + k] = blk[k] - xb[14 + k];
     }
     if (out_tlb) {
@@ -426,6 +468,14 @@ int oracle_linearize_batch(const ProbInfo* P, int n_params, const double* drag_c
         }
     }
     return used;
+}
+
+int oracle_linearize_batch(const ProbInfo* P, int n_params, const double* drag_coef, const double* lift_coef,
+                           const double* geom, const double* X, const double* U, const double* sigma, double dt,
+                           int npts, int mode, int n_nodes, int B, double* out_blocks, double* out_lin_err,
+                           double* out_tlb, int nthreads) {
+    return oracle_linearize_batch_ex(P, n_params, drag_coef, lift_coef, geom, X, U, sigma, dt, npts, mode, n_nodes, B,
+                                     out_blocks, out_lin_err, out_tlb, nthreads, 0, nullptr);
 }
 
 // predict_state / simulate_zygote batched: endpoints 14 x (n_nodes-1) x B

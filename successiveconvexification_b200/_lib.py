@@ -36,6 +36,16 @@ SIGNATURES = {
     "scvx_predict_batch": (ctypes.c_int, [_ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_void_p]),
+    "scvx_linearize_batch_compact": (ctypes.c_int, [_ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                    ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                    ctypes.c_void_p, ctypes.c_void_p]),
+    "scvx_compact_layout": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int32)]),
+    "scvx_expand_compact": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_int]),
+    "scvx_host_alloc": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint64]),
+    "scvx_host_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "scvx_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64]),
+    "scvx_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),
     "scvx_defect_cost_batch": (ctypes.c_int, [_ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "scvx_linear_points_batch": (ctypes.c_int, [_ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
@@ -54,7 +64,6 @@ SIGNATURES = {
     "scvx_synchronize": (ctypes.c_int, [_ctx_p]),
     "scvx_launch_count": (ctypes.c_int64, [_ctx_p]),
     "scvx_last_kernel_ms": (ctypes.c_int, [_ctx_p, _dp]),
-    "scvx_measure_fp64_peak": (ctypes.c_int, [_ctx_p, _dp]),
 }
 
 _LIB = None
@@ -83,6 +92,25 @@ def load():
         raise ImportError("scvx_probinfo layout mismatch between the binding and the library")
     _LIB = lib
     return lib
+
+
+TOOLS_PATH = os.path.join(_HERE, "libscvx_benchtools.so")
+_TOOLS = None
+
+
+def load_benchtools():
+    """Measurement helpers of bench.py / profiles/ (DFMA peak, DMMA probe): a separate library, not the product ABI."""
+    global _TOOLS
+    if _TOOLS is None:
+        if not os.path.exists(TOOLS_PATH):
+            raise ImportError(f"{TOOLS_PATH} is missing: build it with `python successiveconvexification_b200/csrc/build.py`")
+        lib = ctypes.CDLL(TOOLS_PATH)
+        lib.scvx_bench_fp64_peak.restype = ctypes.c_int
+        lib.scvx_bench_fp64_peak.argtypes = [ctypes.c_int, _dp]
+        lib.scvx_bench_dmma_probe.restype = ctypes.c_int
+        lib.scvx_bench_dmma_probe.argtypes = [ctypes.c_int, _dp]
+        _TOOLS = lib
+    return _TOOLS
 
 
 def check(rc: int):

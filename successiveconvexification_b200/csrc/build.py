@@ -13,7 +13,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libscvx_b200.so")
-SOURCES = ["scvx_api.cu", "scvx_kernels_basic.cu", "scvx_kernels_staged.cu", "scvx_kernels_socp.cu"]
+SOURCES = ["scvx_api.cu", "scvx_kernels_basic.cu", "scvx_kernels_staged.cu", "scvx_kernels_socp.cu",
+           "scvx_kernels_compact.cu"]
+# measurement helpers of bench.py / profiles/ (DFMA peak, DMMA probe): a separate library, not part of the product ABI
+TOOLS_OUT = os.path.join(PKG, "libscvx_benchtools.so")
+TOOLS_SOURCES = ["bench_tools.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--fmad=true", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 
@@ -32,7 +36,14 @@ def _newest_source():
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    srcs = [os.path.join(HERE, s) for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
+    _build(SOURCES, OUT, force, verbose)
+    _build(TOOLS_SOURCES, TOOLS_OUT, force, verbose)
+    return OUT
+
+
+def _build(sources, out, force, verbose):
+    OUT = out
+    srcs = [os.path.join(HERE, s) for s in sources]
     if (not force) and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_source():
         return OUT
     objs = []

@@ -6,7 +6,10 @@
 // Trajectories are independent (reference dynamics.jl:324-332 reads only nodes i, i+1), so multi-device
 // contexts shard them in contiguous blocks with no exchange step.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +20,7 @@
 
 #include "scvx_kernels.h"
 #include "scvx_socp_pattern.h"
+#include "scvx_compact.h"
 
 static_assert(sizeof(scvx_probinfo) == 248 && sizeof(scvx_dim_problem) == 216, "ABI record sizes are part of the contract");
 
@@ -45,8 +49,23 @@ constexpr int NSLOT = 3;
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    double *dX = nullptr, *dU = nullptr, *dS = nullptr, *dOut = nullptr, *dErr = nullptr, *dTlb = nullptr, *dEnd = nullptr;
-    size_t capX = 0, capU = 0, capS = 0, capOut = 0, capErr = 0, capTlb = 0, capEnd = 0;
+    double *dX = nullptr, *dU = nullptr, *dS = nullptr, *dOut = nullptr, *dErr = nullptr, *dTlb = nullptr, *dEnd = nullptr,
+           *dCmp = nullptr;
+    size_t capX = 0, capU = 0, capS = 0, capOut = 0, capErr = 0, capTlb = 0, capEnd = 0, capCmp = 0;
+};
+
+// NVTX range over a scope (host timeline of the enqueue; the kernels and copies it covers show up under it in a trace)
+struct Range {
+    explicit Range(const char* name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+};
+
+// device temporaries that must not leak on an early return
+struct DevTmp {
+    void* p = nullptr;
+    ~DevTmp() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+    double* d() const { return (double*)p; }
 };
 
 struct Dev {
@@ -63,6 +82,8 @@ struct Dev {
     int sm_count = 0;
     cudaStream_t scratch_user = nullptr;   // stream that last used the scratch
     cudaEvent_t ev_scratch = nullptr;
+    double* dense = nullptr;               // dense blocks behind a device-pointer compact call
+    size_t dense_cap = 0;
 };
 
 }  // namespace
@@ -97,6 +118,9 @@ bool is_device_ptr(const void* p) {
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
+
+// index (into c->devs) of the device a device pointer lives on, or -1
+int dev_index_of(const scvx_ctx* c, const void* p);
 
 ScvxTables tables_of(const Dev& d) {
     ScvxTables t;
@@ -162,12 +186,38 @@ int launch_predict(scvx_ctx* c, Dev& d, const ScvxBatch& bt, cudaStream_t s) {
     return 0;
 }
 
+// Drain every pipeline stream of the context (after a failure: async copies into caller-owned buffers must not outlive
+// the call).  Errors are ignored — the caller already reports one.
+void drain(scvx_ctx* c) {
+    for (Dev& d : c->devs) {
+        cudaSetDevice(d.id);
+        for (int q = 0; q < NSLOT; ++q) cudaStreamSynchronize(d.slot[q].stream);
+    }
+    cudaGetLastError();
+}
+
+int run_impl(scvx_ctx* c, bool predict, const double* X, const double* U, const double* sigma, double dt, int npts,
+             int mode, int n_nodes, int B, double* out_blocks, double* out_lin_err, double* out_tlb, double* out_end,
+             double* out_compact);
+
 // Run one call. predict=false: linearize. Handles host pointers (chunked, all devices) and device pointers.
+// out_compact != nullptr: compact records instead of dense blocks (out_blocks / out_lin_err must be null then).
 int run(scvx_ctx* c, bool predict, const double* X, const double* U, const double* sigma, double dt, int npts,
-        int mode, int n_nodes, int B, double* out_blocks, double* out_lin_err, double* out_tlb, double* out_end) {
+        int mode, int n_nodes, int B, double* out_blocks, double* out_lin_err, double* out_tlb, double* out_end,
+        double* out_compact = nullptr) {
+    const int rc = run_impl(c, predict, X, U, sigma, dt, npts, mode, n_nodes, B, out_blocks, out_lin_err, out_tlb, out_end,
+                            out_compact);
+    if (rc != 0 && c) drain(c);
+    return rc;
+}
+
+int run_impl(scvx_ctx* c, bool predict, const double* X, const double* U, const double* sigma, double dt, int npts,
+             int mode, int n_nodes, int B, double* out_blocks, double* out_lin_err, double* out_tlb, double* out_end,
+             double* out_compact) {
     if (!c) return fail(SCVX_ERR_ARG, "null context");
     if (!X || !U || !sigma) return fail(SCVX_ERR_ARG, "X, U and sigma must be non-null");
-    if (predict ? !out_end : !out_blocks) return fail(SCVX_ERR_ARG, "output pointer is null");
+    double* const out_main = predict ? out_end : (out_compact ? out_compact : out_blocks);
+    if (!out_main) return fail(SCVX_ERR_ARG, "output pointer is null");
     if (n_nodes < 2) return fail(SCVX_ERR_ARG, "n_nodes=%d: at least two nodes (one interval) are required", n_nodes);
     if (B < 0) return fail(SCVX_ERR_ARG, "B=%d is negative", B);
     if (npts < 1) return fail(SCVX_ERR_ARG, "npts=%d must be >= 1", npts);
@@ -181,21 +231,35 @@ int run(scvx_ctx* c, bool predict, const double* X, const double* U, const doubl
     const int nP = (int)c->hP.size();
 
     const bool dev_in = is_device_ptr(X);
-    if (dev_in != is_device_ptr(U) || dev_in != is_device_ptr(sigma) ||
-        dev_in != is_device_ptr(predict ? out_end : out_blocks) ||
+    if (dev_in != is_device_ptr(U) || dev_in != is_device_ptr(sigma) || dev_in != is_device_ptr(out_main) ||
         (out_lin_err && dev_in != is_device_ptr(out_lin_err)) || (out_tlb && dev_in != is_device_ptr(out_tlb)))
         return fail(SCVX_ERR_ARG, "all array arguments must be either host or device pointers, not a mix");
 
     if (dev_in) {
-        Dev& d = c->devs[0];
+        const int di = dev_index_of(c, X);
+        if (di < 0 || di != dev_index_of(c, out_main))
+            return fail(SCVX_ERR_ARG, "device pointers must live on one device of this context");
+        Dev& d = c->devs[di];
         CK(cudaSetDevice(d.id));
         cudaStream_t s = c->have_user_stream ? c->user_stream : d.slot[0].stream;
         ScvxBatch bt;
         bt.X = X; bt.U = U; bt.sigma = sigma; bt.P = d.dP; bt.n_params = nP; bt.n_nodes = n_nodes; bt.B = B;
         bt.dt = dt; bt.npts = npts; bt.mode = mode;
         bt.out_blocks = out_blocks; bt.out_lin_err = out_lin_err; bt.out_tlb = out_tlb; bt.out_endpoints = out_end;
+        if (out_compact) {
+            // dense blocks go to a context-owned buffer, the pack kernel gathers the data entries behind them
+            const size_t need = (size_t)ni * B * SCVX_BLOCK_DOUBLES;
+            if (need > d.dense_cap) { CK(cudaDeviceSynchronize()); }
+            if (grow(&d.dense, &d.dense_cap, need)) return SCVX_ERR_NOMEM;
+            bt.out_blocks = d.dense;
+        }
+        Range r(predict ? "scvx:predict(device)" : "scvx:linearize(device)");
         CK(cudaEventRecord(d.ev0, s));
         if (int rc = predict ? launch_predict(c, d, bt, s) : launch_linearize(c, d, bt, s)) return rc;
+        if (out_compact) {
+            CK(scvx_launch_compact_pack(d.dense, (long)ni * B, out_compact, d.sm_count, s));
+            c->launches += 1;
+        }
         CK(cudaEventRecord(d.ev1, s));
         c->timed = true;
         return 0;
@@ -203,7 +267,8 @@ int run(scvx_ctx* c, bool predict, const double* X, const double* U, const doubl
 
     // Host pointers: contiguous trajectory blocks per device, chunked + double-buffered inside a device.
     const int nd = (int)c->devs.size();
-    const size_t per_traj_out = predict ? (size_t)ni * 14 : (size_t)ni * SCVX_BLOCK_DOUBLES;
+    const size_t per_traj_out = predict ? (size_t)ni * 14 : (size_t)ni * (out_compact ? SCVX_COMPACT_DOUBLES : SCVX_BLOCK_DOUBLES);
+    Range whole(predict ? "scvx:predict(host)" : (out_compact ? "scvx:linearize_compact(host)" : "scvx:linearize(host)"));
     static const long chunk_mb = getenv("SCVX_HOST_CHUNK_MB") ? atol(getenv("SCVX_HOST_CHUNK_MB")) : 256;
     long chunk = (long)(((size_t)chunk_mb << 20) / (per_traj_out * sizeof(double)));   // output per pipeline chunk (D2H saturates this pool's PCIe at ~43 GB/s from 128 MiB up, profiles/e2e_sweep.py)
     chunk = std::max(1L, chunk);
@@ -227,6 +292,7 @@ int run(scvx_ctx* c, bool predict, const double* X, const double* U, const doubl
             if (grow(&sl.dX, &sl.capX, (size_t)nb * n_nodes * 14) || grow(&sl.dU, &sl.capU, (size_t)nb * n_nodes * 3) ||
                 grow(&sl.dS, &sl.capS, (size_t)nb))
                 return SCVX_ERR_NOMEM;
+            Range chunk_range("scvx:chunk h2d+kernels+d2h");
             CK(cudaMemcpyAsync(sl.dX, X + (size_t)cb * n_nodes * 14, (size_t)nb * n_nodes * 14 * 8, cudaMemcpyHostToDevice, sl.stream));
             CK(cudaMemcpyAsync(sl.dU, U + (size_t)cb * n_nodes * 3, (size_t)nb * n_nodes * 3 * 8, cudaMemcpyHostToDevice, sl.stream));
             CK(cudaMemcpyAsync(sl.dS, sigma + cb, (size_t)nb * 8, cudaMemcpyHostToDevice, sl.stream));
@@ -245,8 +311,16 @@ int run(scvx_ctx* c, bool predict, const double* X, const double* U, const doubl
                 if (out_lin_err) { if (grow(&sl.dErr, &sl.capErr, (size_t)nb * ni * 14)) return SCVX_ERR_NOMEM; bt.out_lin_err = sl.dErr; }
                 if (out_tlb) { if (grow(&sl.dTlb, &sl.capTlb, (size_t)nb * n_nodes * 4)) return SCVX_ERR_NOMEM; bt.out_tlb = sl.dTlb; }
                 if (int rc = launch_linearize(c, d, bt, sl.stream)) return rc;
-                CK(cudaMemcpyAsync(out_blocks + (size_t)cb * ni * SCVX_BLOCK_DOUBLES, sl.dOut,
-                                   (size_t)nb * ni * SCVX_BLOCK_DOUBLES * 8, cudaMemcpyDeviceToHost, sl.stream));
+                if (out_compact) {
+                    if (grow(&sl.dCmp, &sl.capCmp, (size_t)nb * ni * SCVX_COMPACT_DOUBLES)) return SCVX_ERR_NOMEM;
+                    CK(scvx_launch_compact_pack(sl.dOut, (long)nb * ni, sl.dCmp, d.sm_count, sl.stream));
+                    c->launches += 1;
+                    CK(cudaMemcpyAsync(out_compact + (size_t)cb * ni * SCVX_COMPACT_DOUBLES, sl.dCmp,
+                                       (size_t)nb * ni * SCVX_COMPACT_DOUBLES * 8, cudaMemcpyDeviceToHost, sl.stream));
+                } else {
+                    CK(cudaMemcpyAsync(out_blocks + (size_t)cb * ni * SCVX_BLOCK_DOUBLES, sl.dOut,
+                                       (size_t)nb * ni * SCVX_BLOCK_DOUBLES * 8, cudaMemcpyDeviceToHost, sl.stream));
+                }
                 if (out_lin_err)
                     CK(cudaMemcpyAsync(out_lin_err + (size_t)cb * ni * 14, sl.dErr, (size_t)nb * ni * 14 * 8, cudaMemcpyDeviceToHost, sl.stream));
                 if (out_tlb)
@@ -263,6 +337,25 @@ int run(scvx_ctx* c, bool predict, const double* X, const double* U, const doubl
     return 0;
 }
 
+}  // namespace
+
+namespace {
+int dev_index_of(const scvx_ctx* c, const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (size_t i = 0; i < c->devs.size(); ++i) if (c->devs[i].id == a.device) return (int)i;
+    return -1;
+}
+
+// the stream device-pointer work of entry points other than linearize / predict runs on, and its device
+int device_call_target(scvx_ctx* c, const void* p, Dev** d, cudaStream_t* s) {
+    const int di = dev_index_of(c, p);
+    if (di < 0) return fail(SCVX_ERR_ARG, "device pointers must live on one device of this context");
+    *d = &c->devs[di];
+    CK(cudaSetDevice((*d)->id));
+    *s = c->have_user_stream ? c->user_stream : (*d)->slot[0].stream;
+    return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -298,6 +391,7 @@ int scvx_create(scvx_ctx** out, const int* device_ids, int n_dev) {
         if (e == cudaSuccess) e = cudaEventCreate(&d.ev1);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_scratch, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.id);
+        if (e == cudaSuccess) e = scvx_staged_init();          // per-device kernel attributes, once per context
         if (e != cudaSuccess) { scvx_destroy(c); return fail(SCVX_ERR_CUDA, "context setup on device %d failed: %s", d.id, cudaGetErrorString(e)); }
     }
     *out = c;
@@ -311,12 +405,13 @@ void scvx_destroy(scvx_ctx* c) {
         for (int s = 0; s < NSLOT; ++s) {
             Slot& sl = d.slot[s];
             if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
-            double* bufs[] = { sl.dX, sl.dU, sl.dS, sl.dOut, sl.dErr, sl.dTlb, sl.dEnd };
+            double* bufs[] = { sl.dX, sl.dU, sl.dS, sl.dOut, sl.dErr, sl.dTlb, sl.dEnd, sl.dCmp };
             for (double* b : bufs) if (b) cudaFree(b);
         }
         for (int t = 0; t < 3; ++t) if (d.coef[t]) cudaFree(d.coef[t]);
         if (d.dP) cudaFree(d.dP);
         if (d.scratch) cudaFree(d.scratch);
+        if (d.dense) cudaFree(d.dense);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.ev_scratch) cudaEventDestroy(d.ev_scratch);
@@ -334,7 +429,8 @@ int scvx_set_params(scvx_ctx* c, const scvx_probinfo* p, int n) {
     for (int i = 0; i < n; ++i) if (p[i].aero_kind == SCVX_AERO_TABLE) c->any_aero = true;
     for (Dev& d : c->devs) {
         CK(cudaSetDevice(d.id));
-        for (int q = 0; q < NSLOT; ++q) CK(cudaStreamSynchronize(d.slot[q].stream));
+        // kernels still in flight (on the pipeline streams or on a non-blocking user stream) read the records
+        CK(cudaDeviceSynchronize());
         if (d.nP < n) {
             if (d.dP) cudaFree(d.dP);
             d.dP = nullptr; d.nP = 0;
@@ -369,16 +465,15 @@ int scvx_set_aero_table(scvx_ctx* c, int which, const double* samples, int n_cos
         if (prefiltered) {
             CK(cudaMemcpyAsync(d.coef[which], samples, ncoef * sizeof(double), cudaMemcpyHostToDevice, s));
         } else {
-            double *ds = nullptr, *dt = nullptr, *dcp = nullptr;
-            CK(cudaMalloc((void**)&ds, (size_t)n_cos * n_mach * 8));
-            CK(cudaMalloc((void**)&dt, (size_t)(n_cos + 2) * n_mach * 8));
-            CK(cudaMalloc((void**)&dcp, (size_t)nmax * 8));
-            CK(cudaMemcpyAsync(ds, samples, (size_t)n_cos * n_mach * 8, cudaMemcpyHostToDevice, s));
-            CK(cudaMemcpyAsync(dcp, cp.data(), (size_t)nmax * 8, cudaMemcpyHostToDevice, s));
-            CK(scvx_launch_prefilter(ds, n_cos, n_mach, dt, d.coef[which], dcp, s));
+            DevTmp ds, dt, dcp;                              // freed on every exit path
+            CK(ds.alloc((size_t)n_cos * n_mach * 8));
+            CK(dt.alloc((size_t)(n_cos + 2) * n_mach * 8));
+            CK(dcp.alloc((size_t)nmax * 8));
+            CK(cudaMemcpyAsync(ds.d(), samples, (size_t)n_cos * n_mach * 8, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(dcp.d(), cp.data(), (size_t)nmax * 8, cudaMemcpyHostToDevice, s));
+            CK(scvx_launch_prefilter(ds.d(), n_cos, n_mach, dt.d(), d.coef[which], dcp.d(), s));
             c->launches += 2;
             CK(cudaStreamSynchronize(s));
-            cudaFree(ds); cudaFree(dt); cudaFree(dcp);
         }
         CK(cudaStreamSynchronize(s));
         d.n1 = n_cos; d.n2 = n_mach; d.x0 = cos0; d.dx = dcos; d.y0 = mach0; d.dy = dmach;
@@ -420,14 +515,15 @@ int scvx_defect_cost_batch(scvx_ctx* c, const double* X, const double* lin_err, 
     const bool dev = is_device_ptr(X);
     if (dev != is_device_ptr(lin_err) || dev != is_device_ptr(out_defect) || (out_cost && dev != is_device_ptr(out_cost)))
         return fail(SCVX_ERR_ARG, "all array arguments must be either host or device pointers, not a mix");
-    Dev& d = c->devs[0];
-    CK(cudaSetDevice(d.id));
     if (dev) {
-        cudaStream_t s = c->have_user_stream ? c->user_stream : d.slot[0].stream;
+        Dev* dd; cudaStream_t s;
+        if (int rc = device_call_target(c, X, &dd, &s)) return rc;
         CK(scvx_launch_defect_cost(X, lin_err, n_nodes, B, wNu, out_defect, out_cost, s));
         c->launches += 1;
         return 0;
     }
+    Dev& d = c->devs[0];
+    CK(cudaSetDevice(d.id));
     // host pointers: small arrays, one staging round trip on the first device
     Slot& sl = d.slot[0];
     CK(cudaStreamSynchronize(sl.stream));
@@ -454,15 +550,16 @@ int scvx_linear_points_batch(scvx_ctx* c, const double* rIi, const double* vIi, 
     const bool dev = is_device_ptr(rIi);
     if (dev != is_device_ptr(vIi) || dev != is_device_ptr(X) || dev != is_device_ptr(U) || (mwet && dev != is_device_ptr(mwet)))
         return fail(SCVX_ERR_ARG, "all array arguments must be either host or device pointers, not a mix");
-    Dev& d = c->devs[0];
-    CK(cudaSetDevice(d.id));
     const size_t n = (size_t)(K + 1) * B;
     if (dev) {
-        cudaStream_t s = c->have_user_stream ? c->user_stream : d.slot[0].stream;
+        Dev* dd; cudaStream_t s;
+        if (int rc = device_call_target(c, X, &dd, &s)) return rc;
         CK(scvx_launch_linear_points(rIi, vIi, mwet, mwet_shared, mdry, rIf, vIf, g, K, B, X, U, s));
         c->launches += 1;
         return 0;
     }
+    Dev& d = c->devs[0];
+    CK(cudaSetDevice(d.id));
     Slot& sl = d.slot[0];
     CK(cudaStreamSynchronize(sl.stream));
     if (grow(&sl.dX, &sl.capX, n * 14) || grow(&sl.dU, &sl.capU, n * 3) || grow(&sl.dS, &sl.capS, (size_t)7 * B)) return SCVX_ERR_NOMEM;
@@ -493,14 +590,16 @@ int scvx_dispersed_setup_batch(scvx_ctx* c, const scvx_dim_problem* base, const 
         (mwet && dev != is_device_ptr(mwet)) || (scales && dev != is_device_ptr(scales)) ||
         (out_params && dev != is_device_ptr(out_params)))
         return fail(SCVX_ERR_ARG, "all array arguments must be either host or device pointers, not a mix");
+    if (dev && dev_index_of(c, rIi) != 0)
+        return fail(SCVX_ERR_ARG, "scvx_dispersed_setup_batch: device pointers must live on the context's first device");
     Dev& d = c->devs[0];
     CK(cudaSetDevice(d.id));
     const size_t n = (size_t)(base->K + 1) * B;
     cudaStream_t s = (dev && c->have_user_stream) ? c->user_stream : d.slot[0].stream;
     scvx_probinfo* dP = nullptr;
     if (install) {
-        // the records are written straight into the context's parameter array
-        for (int q = 0; q < NSLOT; ++q) CK(cudaStreamSynchronize(d.slot[q].stream));
+        // the records are written straight into the context's parameter array (nothing in flight may still read it)
+        CK(cudaDeviceSynchronize());
         if (d.nP < B) {
             if (d.dP) cudaFree(d.dP);
             d.dP = nullptr; d.nP = 0;
@@ -585,8 +684,18 @@ int scvx_socp_pattern(int n_nodes, int32_t* colptr, int32_t* rowind) {
     return 0;
 }
 
+static int socp_values_impl(scvx_ctx* c, const double* blocks, const double* lin_err, const double* tlb, int n_nodes, int B,
+                            double* out_vals, double* out_rhs);
+
 int scvx_socp_values_batch(scvx_ctx* c, const double* blocks, const double* lin_err, const double* tlb, int n_nodes, int B,
-                           double* out_vals, double* out_rhs) {
+                           double* out_vals, double* out_const) {
+    const int rc = socp_values_impl(c, blocks, lin_err, tlb, n_nodes, B, out_vals, out_const);
+    if (rc != 0 && c) drain(c);        // no async copy into caller-owned buffers may outlive a failed call
+    return rc;
+}
+
+static int socp_values_impl(scvx_ctx* c, const double* blocks, const double* lin_err, const double* tlb, int n_nodes, int B,
+                            double* out_vals, double* out_rhs) {
     if (!c) return fail(SCVX_ERR_ARG, "null context");
     if (!blocks || !tlb || !out_vals) return fail(SCVX_ERR_ARG, "blocks, tlb and out_vals must be non-null");
     if (out_rhs && !lin_err) return fail(SCVX_ERR_ARG, "out_rhs needs lin_err");
@@ -598,15 +707,19 @@ int scvx_socp_values_batch(scvx_ctx* c, const double* blocks, const double* lin_
         (out_rhs && dev != is_device_ptr(out_rhs)))
         return fail(SCVX_ERR_ARG, "all array arguments must be either host or device pointers, not a mix");
     const int K = n_nodes - 1;
+    if (n_nodes > 50000)
+        return fail(SCVX_ERR_ARG, "n_nodes=%d: scvx_socp_values_batch covers the 340K+4 value indices of a trajectory with one "
+                                  "launch (gridDim.y <= 65535 blocks of 256), i.e. n_nodes <= 50000", n_nodes);
     const size_t nnz = socp_nnz(K), nr = socp_rows(K), nblk = (size_t)K * SCVX_BLOCK_DOUBLES, nerr = (size_t)14 * K, ntlb = (size_t)4 * n_nodes;
-    Dev& d = c->devs[0];
-    CK(cudaSetDevice(d.id));
     if (dev) {
-        cudaStream_t s = c->have_user_stream ? c->user_stream : d.slot[0].stream;
+        Dev* dd; cudaStream_t s;
+        if (int rc = device_call_target(c, blocks, &dd, &s)) return rc;
         CK(scvx_launch_socp_values(blocks, lin_err, tlb, n_nodes, B, out_vals, out_rhs, s));
         c->launches += 1;
         return 0;
     }
+    Dev& d = c->devs[0];
+    CK(cudaSetDevice(d.id));
     // host pointers: trajectory chunks through the two pipeline slots of the first device
     long chunk = std::max(1L, (long)(((size_t)128 << 20) / (nblk * sizeof(double))));
     for (long cb = 0, ci = 0; cb < B; cb += chunk, ++ci) {
@@ -631,7 +744,7 @@ int scvx_socp_values_batch(scvx_ctx* c, const double* blocks, const double* lin_
 int scvx_set_stream(scvx_ctx* c, void* stream) {
     if (!c) return fail(SCVX_ERR_ARG, "null context");
     c->user_stream = (cudaStream_t)stream;
-    c->have_user_stream = true;
+    c->have_user_stream = stream != nullptr;        // NULL = back to the library's own stream
     return 0;
 }
 
@@ -666,31 +779,93 @@ int scvx_last_kernel_ms(scvx_ctx* c, double* ms) {
     return 0;
 }
 
-int scvx_measure_fp64_peak(scvx_ctx* c, double* tflops) {
-    if (!c || !tflops) return fail(SCVX_ERR_ARG, "null argument");
-    Dev& d = c->devs[0];
-    CK(cudaSetDevice(d.id));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, d.id));
-    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
-    double* buf = nullptr;
-    CK(cudaMalloc((void**)&buf, (size_t)blocks * 256 * 8));
-    cudaStream_t s = d.slot[0].stream;
-    double best = 0.0;
-    for (int rep = 0; rep < 5; ++rep) {
-        CK(cudaEventRecord(d.ev0, s));
-        CK(scvx_launch_fp64_peak(buf, blocks, iters, s));
-        CK(cudaEventRecord(d.ev1, s));
-        CK(cudaEventSynchronize(d.ev1));
-        c->launches += 1;
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
-        const double fl = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;   // 8 chains x 8 unroll FMAs per iteration
-        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) * 1e-12);
-    }
-    cudaFree(buf);
-    c->timed = false;
-    *tflops = best;
+int scvx_linearize_batch_compact(scvx_ctx* c, const double* X, const double* U, const double* sigma, double base_dt,
+                                 int npts, int mode, int n_nodes, int B, double* out_compact, double* out_tlb) {
+    try {
+        if (!out_compact) return fail(SCVX_ERR_ARG, "out_compact is null");
+        return run(c, false, X, U, sigma, base_dt, npts, mode, n_nodes, B, nullptr, nullptr, out_tlb, nullptr, out_compact);
+    } catch (...) { return fail(SCVX_ERR_STATE, "unexpected C++ exception"); }
+}
+
+int scvx_compact_layout(int32_t* index) {
+    if (!index) return fail(SCVX_ERR_ARG, "index is null");
+    int tmp[SCVX_COMPACT_DATA];
+    const int n = compact_fill_layout(tmp);
+    for (int i = 0; i < n; ++i) index[i] = tmp[i];
+    return n == SCVX_COMPACT_DATA ? 0 : fail(SCVX_ERR_STATE, "compact layout has %d entries", n);
+}
+
+int64_t scvx_expand_compact(const double* compact, const double* X, int n_nodes, int B, double* out_blocks,
+                            double* out_lin_err, int n_threads) {
+    if (!compact) return fail(SCVX_ERR_ARG, "compact is null");
+    if (n_nodes < 2 || B < 0) return fail(SCVX_ERR_ARG, "bad n_nodes / B");
+    if (out_lin_err && !X) return fail(SCVX_ERR_ARG, "out_lin_err needs X");
+    if (is_device_ptr(compact) || is_device_ptr(out_blocks) || is_device_ptr(out_lin_err))
+        return fail(SCVX_ERR_ARG, "scvx_expand_compact works on host memory");
+    try {
+        const int ni = n_nodes - 1;
+        const long total = (long)ni * B;
+        // template block: the structural constants; the data entries are overwritten per interval
+        double tmpl[SCVX_BLOCK_DOUBLES];
+        int idx[SCVX_COMPACT_DATA];
+        compact_fill_layout(idx);
+        for (int cc = 0; cc < 23; ++cc) for (int r = 0; r < 14; ++r) tmpl[cc * 14 + r] = compact_constant(cc, r);
+        int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+        nt = (int)std::max(1L, std::min((long)nt, (total + 4095) / 4096));
+        std::atomic<int64_t> flagged(0);
+        auto work = [&](long w0, long w1) {
+            int64_t bad = 0;
+            for (long w = w0; w < w1; ++w) {
+                const double* rec = compact + (size_t)w * SCVX_COMPACT_DOUBLES;
+                if (rec[SCVX_COMPACT_DATA] != 0.0) ++bad;
+                if (out_blocks) {
+                    double* blk = out_blocks + (size_t)w * SCVX_BLOCK_DOUBLES;
+                    memcpy(blk, tmpl, sizeof(tmpl));
+                    for (int k = 0; k < SCVX_COMPACT_DATA; ++k) blk[idx[k]] = rec[k];
+                }
+                if (out_lin_err) {
+                    const long b = w / ni, i = w - b * ni;
+                    const double* xn = X + ((size_t)b * n_nodes + i + 1) * 14;       // x_{n+1} (rocketland.jl:130, 256)
+                    double* e = out_lin_err + (size_t)w * 14;
+                    for (int r = 0; r < 14; ++r) e[r] = rec[r] - xn[r];
+                }
+            }
+            flagged += bad;
+        };
+        if (nt == 1) work(0, total);
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nt; ++t) pool.emplace_back(work, total * t / nt, total * (t + 1) / nt);
+            for (auto& th : pool) th.join();
+        }
+        return flagged.load();
+    } catch (...) { return fail(SCVX_ERR_STATE, "unexpected C++ exception"); }
+}
+
+int scvx_host_alloc(void** out, uint64_t bytes) {
+    if (!out) return fail(SCVX_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (bytes == 0) return 0;
+    cudaError_t e = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(SCVX_ERR_NOMEM, "cudaHostAlloc(%llu B) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e)); }
+    return 0;
+}
+
+int scvx_host_free(void* p) {
+    if (!p) return 0;
+    CK(cudaFreeHost(p));
+    return 0;
+}
+
+int scvx_host_register(void* p, uint64_t bytes) {
+    if (!p || bytes == 0) return fail(SCVX_ERR_ARG, "scvx_host_register: null pointer or zero size");
+    CK(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable));
+    return 0;
+}
+
+int scvx_host_unregister(void* p) {
+    if (!p) return 0;
+    CK(cudaHostUnregister(p));
     return 0;
 }
 

@@ -17,9 +17,10 @@ cudaError_t scvx_launch_socp_values(const double* blocks, const double* lin_err,
 cudaError_t scvx_launch_dispersed_setup(const scvx_dim_problem& base, const double* rIi, const double* vIi, const double* mwet,
                                         int B, double* X, double* U, double* sigma, double* scales, scvx_probinfo* P0,
                                         scvx_probinfo* P1, cudaStream_t s);
-cudaError_t scvx_launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t s);
+cudaError_t scvx_launch_compact_pack(const double* blocks, long n_intervals, double* out, int sm_count, cudaStream_t s);
 
 // STAGED path (scvx_kernels_staged.cu): value kernel + persistent tangent kernel, chunked over a scratch buffer.
+cudaError_t scvx_staged_init();          // kernel attributes of the current device (once per context and device)
 size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals);
 int scvx_staged_chunk_intervals(int sm_count);
 cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, void* scratch,

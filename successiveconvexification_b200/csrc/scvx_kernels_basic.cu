@@ -7,7 +7,6 @@
 //   * predict_kernel            : one thread per interval, value only (predict_state / simulate_zygote,
 //                                 dynamics.jl:308-310, 315-317).
 //   * prefilter kernels         : Interpolations.jl cubic-B-spline prefilter, one thread per grid line.
-//   * fp64_peak_kernel          : DFMA throughput microbenchmark (roofline denominator).
 #include "scvx_common.cuh"
 #include "scvx_kernels.h"
 
@@ -141,26 +140,6 @@ __global__ void prefilter_axis1_kernel(const double* tmp, int n1, int n2, double
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n1 + 2) return;
     prefilter_line(tmp + i, n2, (size_t)(n1 + 2), coef + i, (size_t)(n1 + 2), cp);
-}
-
-// ---------------------------------------------------------------------------------------------
-// FP64 FMA throughput microbenchmark: 8 independent chains per thread in the shape the tangent kernel issues them,
-// x_i = fma(coefficient, stage value, x_i) with the chain through the addend (measured 35.8 TFLOP/s on this pool's
-// B200; chains through the multiplicand with two shared operands reach 34.0; nominal 148 x 64 x 2 x 1.965 GHz = 37.2).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a0, double b0) {
-    double x[8], a[8], y[4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { x[i] = threadIdx.x * 1e-3 + i; a[i] = a0 + i * 1e-9; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) y[i] = b0 + i * 1e-10;
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = fma(a[(i + r) & 7], y[i >> 1], x[i]);
-    }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -373,10 +352,5 @@ cudaError_t scvx_launch_dispersed_setup(const scvx_dim_problem& base, const doub
     const long threads = (long)(base.K + 1) * B;
     if (threads <= 0) return cudaSuccess;
     dispersed_setup_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(base, rIi, vIi, mwet, B, X, U, sigma, scales, P0, P1);
-    return cudaGetLastError();
-}
-
-cudaError_t scvx_launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t s) {
-    fp64_peak_kernel<<<blocks, 256, 0, s>>>(d_out, iters, 0.999999, 1e-9);
     return cudaGetLastError();
 }

@@ -403,18 +403,16 @@ size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals) {
 // tangent kernel 32 intervals per pass: 768 intervals per SM = 3 waves / 24 passes.
 int scvx_staged_chunk_intervals(int sm_count) { return sm_count * 768; }
 
+cudaError_t scvx_staged_init() {
+    cudaError_t e = cudaFuncSetAttribute(stage_value_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIGHT_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tangent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
+}
+
 cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, void* scratch,
                                int chunk_intervals, int sm_count, cudaStream_t s, int* launches) {
     const long total = (long)(bt.n_nodes - 1) * bt.B;
-    {
-        cudaError_t e = cudaFuncSetAttribute(stage_value_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIGHT_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-    }
     const size_t smem = sizeof(StepSmem);
-    {
-        cudaError_t e = cudaFuncSetAttribute(tangent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
     for (long first = 0; first < total; first += chunk_intervals) {
         StagedArgs a;
         a.bt = bt; a.tb = tb; a.rec = (double*)scratch; a.first = (int)first;

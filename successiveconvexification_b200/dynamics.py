@@ -49,7 +49,13 @@ class DeviceContext:
             rc = self._lib.scvx_create(ctypes.byref(self._h), ids, len(device_ids))
         _lib.check(rc)
         self.n_params = 0
+        # `mode`: stage rule of the rk4-based entry points simulate_zygote / sensitivity_zygote (and the default of the
+        # batched calls): LITERAL = the reference's arithmetic (dynamics.jl:126-128), the parity contract.
+        # `live_mode`: rule used where the device stands in for the reference's LIVE entry points linearize_dynamics /
+        # predict_state / simulate / sensitivity, which integrate the continuous dynamics with an adaptive BS3 solve
+        # (dynamics.jl:288-305); the consistent fixed-step integrator for those is classical RK4, so TEXTBOOK.
         self.mode = MODE_LITERAL
+        self.live_mode = MODE_TEXTBOOK
         self.npts = 10
 
     def close(self):
@@ -103,10 +109,9 @@ class DeviceContext:
         _lib.check(self._lib.scvx_last_kernel_ms(self._h, ctypes.byref(ms)))
         return ms.value
 
-    def measure_fp64_peak(self) -> float:
-        tf = ctypes.c_double()
-        _lib.check(self._lib.scvx_measure_fp64_peak(self._h, ctypes.byref(tf)))
-        return tf.value
+    def linearize_compact_ptr(self, X, U, sigma, base_dt, npts, mode, n_nodes, B, out_compact, out_tlb=0):
+        _lib.check(self._lib.scvx_linearize_batch_compact(self._h, X, U, sigma, base_dt, npts, mode, n_nodes, B,
+                                                          out_compact, out_tlb or None))
 
     # ---- raw pointer calls (host or device addresses)
     def linearize_ptr(self, X, U, sigma, base_dt, npts, mode, n_nodes, B, out_blocks, out_lin_err=0, out_tlb=0):
@@ -190,6 +195,51 @@ def linearize_batch(cache: IntegratorCache, X, U, sigma, base_dt: float, npts: i
     return blocks, err, tl
 
 
+COMPACT_DOUBLES, COMPACT_DATA = 230, 229      # include/scvx_b200.h
+
+
+def compact_layout() -> np.ndarray:
+    """Dense offsets (column * 14 + row) of compact slots 0..228 (`scvx_compact_layout`)."""
+    idx = np.empty(COMPACT_DATA, np.int32)
+    _lib.check(_lib.load().scvx_compact_layout(idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+    return idx
+
+
+def linearize_batch_compact(cache: IntegratorCache, X, U, sigma, base_dt: float, npts: int = 10, mode: int = MODE_LITERAL,
+                            tlb: bool = True):
+    """`linearize_batch` with compact result records: only the 229 data entries of every 14x23 block (+ a per-interval
+    non-finite flag) cross PCIe.  -> compact (B, n_int, 230), tlb (B, n_nodes, 4) | None.  `expand_compact` restores the
+    dense blocks and lin_err on the host."""
+    ctx = _ctx(cache)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64).reshape(-1)
+    if X.ndim != 3 or X.shape[2] != 14 or U.shape != (X.shape[0], X.shape[1], 3) or sigma.shape[0] != X.shape[0]:
+        raise ValueError("expected X (B, n_nodes, 14), U (B, n_nodes, 3), sigma (B,)")
+    B, n_nodes, _ = X.shape
+    ni = max(n_nodes - 1, 0)
+    comp = np.empty((B, ni, COMPACT_DOUBLES))
+    tl = np.empty((B, n_nodes, 4)) if tlb else None
+    ctx.linearize_compact_ptr(X.ctypes.data, U.ctypes.data, sigma.ctypes.data, float(base_dt), int(npts), int(mode),
+                              n_nodes, B, comp.ctypes.data, tl.ctypes.data if tlb else 0)
+    return comp, tl
+
+
+def expand_compact(compact, X, lin_err: bool = True, n_threads: int = 0):
+    """Host-side expander (`scvx_expand_compact`): compact (B, n_int, 230) + X (B, n_nodes, 14) ->
+    blocks (B, n_int, 23, 14), lin_err (B, n_int, 14) | None, number of intervals flagged non-finite."""
+    compact = np.ascontiguousarray(compact, dtype=np.float64)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    B, ni, _ = compact.shape
+    blocks = np.empty((B, ni, ACC_WIDTH, STATE_DIM))
+    err = np.empty((B, ni, STATE_DIM)) if lin_err else None
+    n = _lib.load().scvx_expand_compact(compact.ctypes.data, X.ctypes.data, ni + 1, B, blocks.ctypes.data,
+                                        err.ctypes.data if lin_err else None, int(n_threads))
+    if n < 0:
+        _lib.check(int(n))
+    return blocks, err, int(n)
+
+
 def predict_batch(cache: IntegratorCache, X, U, sigma, base_dt: float, npts: int = 10, mode: int = MODE_LITERAL):
     ctx = _ctx(cache)
     X = np.ascontiguousarray(X, dtype=np.float64)
@@ -246,43 +296,48 @@ def linearize_dynamics(states: Sequence[LinPoint], tf_guess: float, base_dt: flo
     ctx = _ctx(cache)
     X = np.stack([p.state for p in states])[None]
     U = np.stack([p.control for p in states])[None]
-    blocks, _, _ = linearize_batch(cache, X, U, [float(tf_guess)], base_dt, ctx.npts, ctx.mode, lin_err=False, tlb=False)
+    blocks, _, _ = linearize_batch(cache, X, U, [float(tf_guess)], base_dt, ctx.npts, ctx.live_mode, lin_err=False,
+                                   tlb=False)
     return blocks_to_linres(blocks[0])
 
 
-def simulate_zygote(inp, dt: float, cache: IntegratorCache, npts: int = 10) -> np.ndarray:
-    """dynamics.jl:308-310: rk4(inp, dt, info) -> absolute end state (14)."""
+def _one_interval(inp):
     inp = np.asarray(inp, dtype=np.float64)
     if inp.shape != (INP_DIM,):
         raise ValueError("inp must have 21 entries [x; uk; up; sigma]")
     X = np.zeros((1, 2, 14)); U = np.zeros((1, 2, 3))
     X[0, 0] = inp[state_idx]; U[0, 0] = inp[uk_idx]; U[0, 1] = inp[up_idx]
-    return predict_batch(cache, X, U, [inp[sigma_idx]], dt, npts, _ctx(cache).mode)[0, 0]
+    return inp, X, U
 
 
-def sensitivity_zygote(inp, dt: float, cache: IntegratorCache):
+def simulate_zygote(inp, dt: float, cache: IntegratorCache, npts: int = 10, mode: Optional[int] = None) -> np.ndarray:
+    """dynamics.jl:308-310: rk4(inp, dt, info) -> absolute end state (14).  LITERAL stage rule unless told otherwise."""
+    inp, X, U = _one_interval(inp)
+    return predict_batch(cache, X, U, [inp[sigma_idx]], dt, npts, _ctx(cache).mode if mode is None else mode)[0, 0]
+
+
+def sensitivity_zygote(inp, dt: float, cache: IntegratorCache, mode: Optional[int] = None):
     """dynamics.jl:311-313: (y(14), J^T (21x14)) as Zygote.forward_jacobian returns them."""
-    inp = np.asarray(inp, dtype=np.float64)
-    if inp.shape != (INP_DIM,):
-        raise ValueError("inp must have 21 entries [x; uk; up; sigma]")
+    inp, X, U = _one_interval(inp)
     ctx = _ctx(cache)
-    X = np.zeros((1, 2, 14)); U = np.zeros((1, 2, 3))
-    X[0, 0] = inp[state_idx]; U[0, 0] = inp[uk_idx]; U[0, 1] = inp[up_idx]
-    blocks, _, _ = linearize_batch(cache, X, U, [inp[sigma_idx]], dt, ctx.npts, ctx.mode, lin_err=False, tlb=False)
+    blocks, _, _ = linearize_batch(cache, X, U, [inp[sigma_idx]], dt, ctx.npts, ctx.mode if mode is None else mode,
+                                   lin_err=False, tlb=False)
     blk = blocks[0, 0]
     return blk[0].copy(), blk[1:22].copy()          # rows of blk[1:22] are the columns of D, i.e. J^T
 
 
 def simulate(inp, dt: float, cache: IntegratorCache) -> np.ndarray:
-    """dynamics.jl:288-296: absolute end state (the reference returns `(u .+ inp)[1:14]`)."""
-    return simulate_zygote(inp, dt, cache, _ctx(cache).npts)
+    """dynamics.jl:288-296: absolute end state (the reference returns `(u .+ inp)[1:14]`).  The reference integrates
+    the continuous dynamics (adaptive BS3); the device uses the consistent fixed-step rule (`live_mode`, TEXTBOOK)."""
+    ctx = _ctx(cache)
+    return simulate_zygote(inp, dt, cache, ctx.npts, ctx.live_mode)
 
 
 def sensitivity(inp, dt: float, cache: IntegratorCache):
     """dynamics.jl:298-305 in the live code's DEVIATION form: val(21) = x(dt) - x(0) (zero-padded),
-    mat(21x21) with mat[0:14, :] = D - [I 0]; `linearize_dynamics` adds x and I back (327-330)."""
+    mat(21x21) with mat[0:14, :] = D - [I 0]; `linearize_dynamics` adds x and I back (327-330).  `live_mode` rule."""
     inp = np.asarray(inp, dtype=np.float64)
-    y, JT = sensitivity_zygote(inp, dt, cache)
+    y, JT = sensitivity_zygote(inp, dt, cache, _ctx(cache).live_mode)
     val = np.zeros(INP_DIM); val[:14] = y - inp[:14]
     mat = np.zeros((INP_DIM, INP_DIM), order="F"); mat[:14, :] = JT.T
     mat[np.arange(14), np.arange(14)] -= 1.0

@@ -35,6 +35,32 @@ def gather_shards(local, group=None):
     return torch.cat([b[:s] for b, s in zip(bufs, sizes)])
 
 
+def gather_to_root(local, dst: int = 0, group=None):
+    """Result collection for a host-side consumer: every rank sends its leading-axis shard to `dst`,
+    which receives each one straight into its slice of ONE result tensor — no padding and no copy on the other ranks
+    (`gather_shards` leaves the whole result on every rank: world x the memory, for device-side consumers only).
+    Returns the concatenation in rank order on `dst`, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    local = local.contiguous()
+    if rank != dst:
+        if sizes[rank]:
+            dist.send(local, dst, group=group)
+        return None
+    out = local.new_empty((sum(sizes),) + tuple(local.shape[1:]))
+    offs = [sum(sizes[:r]) for r in range(world)]
+    out[offs[dst]:offs[dst] + sizes[dst]] = local
+    for r in range(world):
+        if r != dst and sizes[r]:
+            dist.recv(out[offs[r]:offs[r] + sizes[r]], r, group=group)
+    return out
+
+
 def reduce_status(ok: bool, checksum: float, device, group=None):
     """Tiny status / checksum all-reduce: (all ranks ok?, sum of per-shard checksums)."""
     import torch

@@ -6,7 +6,8 @@ import os
 import numpy as np
 import pytest
 
-from conftest import AERO_NPZ, GOLDEN, PARITY_TOL, assert_parity, parity_report
+from conftest import (AERO_NPZ, GOLDEN, PARITY_TOL, ROOT, assert_conditioned_parity, assert_parity,
+                      assert_structural_constants, conditioned_parity, parity_protocol, parity_report)
 
 pytestmark = pytest.mark.gpu
 
@@ -67,6 +68,14 @@ def test_c2_sample_trajectory_vs_golden_and_oracle(dyn, cache_aero, cache_exo, p
     # structural zeros: nothing depends on position
     expect = np.zeros((3, 14)); expect[[0, 1, 2], [1, 2, 3]] = 1.0
     assert np.array_equal(blocks[0, :, 2:5, :], np.broadcast_to(expect, (50, 3, 14)))
+    # parity protocol items (ii) and (iii) of SURVEY.md §8d: strict relative maximum (reported: it is dominated by
+    # cancellation zeros), structural constants exact
+    rep = parity_protocol(blocks, ref)
+    print(f"\n[parity protocol C2 {aero} mode={mode} kernel={kernel}] (i) {rep['metric']} (ii) strict rel max "
+          f"{rep['strict_rel_max']:.3e} at {rep.get('strict_rel_where')} (iii) structural {rep['structural_max']:.1e}")
+    assert rep["structural_max"] <= 1e-16
+    if kernel == 2:
+        assert_structural_constants(blocks)
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -81,11 +90,16 @@ def test_reference_entry_points(dyn, cache_aero, prob_aero, oracle_tables, kerne
     assert res[0].derivative.flags.f_contiguous
     info = ProbInfo(prob_aero)
     inp = dyn.make_state(pts[0], pts[1], 1.0)
-    blk = _oracle().linearize_interval(info, oracle_tables, inp, 1 / 51)
+    # the rk4-based entry points follow the reference's LITERAL stage rule (dynamics.jl:126-128) ...
+    lit = _oracle().linearize_interval(info, oracle_tables, inp, 1 / 51, 10, 0)
+    y, JT = dyn.sensitivity_zygote(inp, 1 / 51, cache_aero)
+    assert JT.shape == (21, 14) and np.abs(JT.T - lit[:, 1:22]).max() <= 1e-12 and np.abs(y - lit[:, 0]).max() <= 1e-14
+    assert np.abs(dyn.simulate_zygote(inp, 1 / 51, cache_aero) - lit[:, 0]).max() <= 1e-14
+    # ... the live entry points (adaptive BS3 in the reference, dynamics.jl:288-305) use the consistent rule, TEXTBOOK
+    assert cache_aero.sim_prob.live_mode == dyn.MODE_TEXTBOOK
+    blk = _oracle().linearize_interval(info, oracle_tables, inp, 1 / 51, 10, 1)
     assert np.abs(res[0].endpoint - blk[:, 0]).max() <= 1e-14
     assert np.abs(res[0].derivative - blk[:, 1:22]).max() <= 1e-12
-    y, JT = dyn.sensitivity_zygote(inp, 1 / 51, cache_aero)
-    assert JT.shape == (21, 14) and np.abs(JT.T - blk[:, 1:22]).max() <= 1e-12
     val, mat = dyn.sensitivity(inp, 1 / 51, cache_aero)
     assert val.shape == (21,) and mat.shape == (21, 21)
     assert np.abs(val[:14] + inp[:14] - blk[:, 0]).max() <= 1e-14
@@ -419,9 +433,16 @@ def test_edge_cases_and_errors(dyn, cache_aero, prob_aero):
         dyn.linearize_batch(IntegratorCache(sim_prob=fresh), X, U, sigma, 0.5)
 
 
-def test_fp64_peak_microbenchmark(cache_aero):
-    tf = cache_aero.sim_prob.measure_fp64_peak()
-    assert 5.0 < tf < 80.0
+def test_fp64_peak_microbenchmark_and_dmma_probe():
+    """Measurement helpers (libscvx_benchtools.so, not part of the product ABI): DFMA peak and the DMMA experiment."""
+    import ctypes
+    from successiveconvexification_b200 import _lib
+    tools = _lib.load_benchtools()
+    tf = ctypes.c_double()
+    assert tools.scvx_bench_fp64_peak(0, ctypes.byref(tf)) == 0 and 5.0 < tf.value < 80.0
+    out = (ctypes.c_double * 8)()
+    assert tools.scvx_bench_dmma_probe(0, out) == 0
+    assert all(0.5 < out[k] < 200.0 for k in range(7)), list(out)
 
 
 def _device_properties(blocks, dX, dU, dS):
@@ -440,35 +461,41 @@ def _device_properties(blocks, dX, dU, dS):
     return zerr, scale, pos_ok, bool(torch.isfinite(blocks).all())
 
 
-def test_c3_full_size_properties(dyn, cache_aero, prob_aero, oracle_tables):
-    """BASELINE config 3 at full size: aero tables, K=100, 4096 perturbed trajectories (409 600 intervals), TEXTBOOK
-    with the survey's sigma ~ U(1,15): properties on the device + a random sample against the oracle."""
+@pytest.mark.parametrize("mode,srange", [(1, (1.0, 15.0)), (0, (0.8, 1.5))])
+def test_c3_full_size_properties(dyn, cache_aero, prob_aero, oracle_tables, mode, srange):
+    """BASELINE config 3 at full size: aero tables, K=100, 4096 perturbed trajectories (409 600 intervals); TEXTBOOK
+    with the survey's sigma ~ U(1,15) and LITERAL (the parity contract) around the reference's sigma = 1: properties on
+    the device + a random sample against the oracle."""
     import torch
     from successiveconvexification_b200 import workloads
     ctx = cache_aero.sim_prob
     ctx.set_kernel(0)
     B, K = 4096, 100
-    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, K, B, 1001)
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, K, B, 1001, sigma_range=srange)
     dX, dU, dS = (torch.from_numpy(a).cuda() for a in (X, U, sigma))
     out = torch.empty((B, K, 23, 14), dtype=torch.float64, device="cuda")
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    ctx.linearize_ptr(dX.data_ptr(), dU.data_ptr(), dS.data_ptr(), 1 / (K + 1), 10, 1, K + 1, B, out.data_ptr())
+    ctx.linearize_ptr(dX.data_ptr(), dU.data_ptr(), dS.data_ptr(), 1 / (K + 1), 10, mode, K + 1, B, out.data_ptr())
     torch.cuda.synchronize()
     zerr, scale, pos_ok, finite = _device_properties(out, dX, dU, dS)
     assert finite and pos_ok and zerr <= 1e-12 * scale
     pick = np.random.default_rng(9).choice(B, 8, replace=False)
-    ref, _, _, _ = _oracle().linearize_batch(P, oracle_tables, X[pick], U[pick], sigma[pick], 1 / (K + 1), 10, 1,
+    ref, _, _, _ = _oracle().linearize_batch(P, oracle_tables, X[pick], U[pick], sigma[pick], 1 / (K + 1), 10, mode,
                                             False, False)
-    assert_parity(out[torch.from_numpy(pick).cuda()].cpu().numpy(), ref)
+    got = out[torch.from_numpy(pick).cuda()].cpu().numpy()
+    assert_parity(got, ref)
+    assert_structural_constants(got)
 
 
-def test_c4_full_size_properties(dyn, prob_aero, oracle_tables):
+@pytest.mark.parametrize("mode,srange", [(1, (1.0, 15.0)), (0, (0.8, 1.5))])
+def test_c4_full_size_properties(dyn, prob_aero, oracle_tables, mode, srange):
     """BASELINE config 4 at full size: K=400, 16384 trajectories (6.55 M intervals, 16.9 GB of blocks, device
-    resident), per-trajectory mass / alpha / thrust-bound sweep.  Properties on the device, sampled oracle parity."""
+    resident), per-trajectory mass / alpha / thrust-bound sweep; TEXTBOOK with sigma ~ U(1,15) and LITERAL around the
+    reference's sigma = 1.  Properties on the device, sampled oracle parity."""
     import torch
     from successiveconvexification_b200 import workloads
     B, K = 16384, 400
-    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, K, B, 1002, sweep=True)
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, K, B, 1002, sweep=True, sigma_range=srange)
     cache = dyn.make_cache(prob_aero)
     ptr, n, keep = workloads.as_c_params(P)
     ctx = cache.sim_prob
@@ -477,7 +504,7 @@ def test_c4_full_size_properties(dyn, prob_aero, oracle_tables):
     out = torch.empty((B, K, 23, 14), dtype=torch.float64, device="cuda")
     tlb = torch.empty((B, K + 1, 4), dtype=torch.float64, device="cuda")
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    ctx.linearize_ptr(dX.data_ptr(), dU.data_ptr(), dS.data_ptr(), 1 / (K + 1), 10, 1, K + 1, B, out.data_ptr(), 0,
+    ctx.linearize_ptr(dX.data_ptr(), dU.data_ptr(), dS.data_ptr(), 1 / (K + 1), 10, mode, K + 1, B, out.data_ptr(), 0,
                       tlb.data_ptr())
     torch.cuda.synchronize()
     # properties in slabs of 2048 trajectories to bound temporary memory
@@ -489,6 +516,121 @@ def test_c4_full_size_properties(dyn, prob_aero, oracle_tables):
     tmin = torch.from_numpy(np.ascontiguousarray(P["Tmin"])).cuda()
     assert float((tlb[..., 3] - (tmin[:, None] - nu)).abs().max()) <= 1e-15
     pick = np.random.default_rng(10).choice(B, 2, replace=False)
-    ref, _, _, _ = _oracle().linearize_batch(P[pick], oracle_tables, X[pick], U[pick], sigma[pick], 1 / (K + 1), 10, 1,
+    ref, _, _, _ = _oracle().linearize_batch(P[pick], oracle_tables, X[pick], U[pick], sigma[pick], 1 / (K + 1), 10, mode,
                                             False, False)
     assert_parity(out[torch.from_numpy(pick).cuda()].cpu().numpy(), ref)
+    del out, tlb, dX, dU, dS
+    torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The configuration bench.py times: C5 shard, LITERAL, sigma ~ U(1, 15), lin_err + thrust-LB rows, device pointers.
+# ---------------------------------------------------------------------------------------------------------------
+def headline_batch_check(dyn, cache, prob, tables, B, n_sample, dump=None):
+    """Run the exact bench batch (workloads.monte_carlo_batch(prob, 50, B, 1003, shard=0), LITERAL, npts=10) through the
+    device-pointer path and check `n_sample` random trajectories with the conditioning-aware protocol
+    (conftest.conditioned_parity).  Returns the report."""
+    import torch
+    from successiveconvexification_b200 import workloads
+    K = 50
+    X, U, sigma, P = workloads.monte_carlo_batch(prob, K, B, 1003, shard=0)
+    ctx = cache.sim_prob
+    ctx.set_kernel(0)
+    dX, dU, dS = (torch.from_numpy(a).cuda() for a in (X, U, sigma))
+    out = torch.empty((B, K, 23, 14), dtype=torch.float64, device="cuda")
+    err = torch.empty((B, K, 14), dtype=torch.float64, device="cuda")
+    tlb = torch.empty((B, K + 1, 4), dtype=torch.float64, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.linearize_ptr(dX.data_ptr(), dU.data_ptr(), dS.data_ptr(), 1 / (K + 1), 10, 0, K + 1, B, out.data_ptr(),
+                      err.data_ptr(), tlb.data_ptr())
+    torch.cuda.synchronize()
+    pick = np.sort(np.random.default_rng(1003).choice(B, n_sample, replace=False))
+    tp = torch.from_numpy(pick).cuda()
+    got, gerr = out[tp].cpu().numpy(), err[tp].cpu().numpy()
+    orc = _oracle()
+    ref64, sig64 = orc.linearize_batch_ex(P, tables, X[pick], U[pick], sigma[pick], 1 / (K + 1), 10, 0, precision=0)
+    refq, sigq = orc.linearize_batch_ex(P, tables, X[pick], U[pick], sigma[pick], 1 / (K + 1), 10, 0, precision=1)
+    rep = conditioned_parity(got, ref64, refq, sig64, sigq)
+    rep["trajectories_sampled"] = int(n_sample)
+    rep["lin_err_consistent"] = bool(np.array_equal(gerr, got[:, :, 0, :] - X[pick][:, 1:]))
+    if dump:
+        np.savez_compressed(dump, got=got, pick=pick, sigma=sigma[pick])
+    return rep, (got, ref64, refq, sig64, sigq)
+
+
+def test_headline_config_literal_sigma_1_15(dyn, cache_aero, prob_aero, oracle_tables):
+    """The benchmarked configuration is a verified configuration: C5 shard (32 768 trajectories x 50 intervals), LITERAL
+    stage rule, sigma ~ U(1, 15), lin_err + thrust-LB rows, device pointers.  64 random trajectories (3 200 intervals)
+    against the oracle in FP64 and in IEEE binary128: 1e-10 wherever FP64 can hold it, within K_COND x the reference
+    arithmetic's own distance from the binary128 value elsewhere (conftest.py, "Conditioning-aware parity")."""
+    dump = os.path.join(ROOT, "gpurun_out", "headline_sample.npz") if os.environ.get("SCVX_DUMP") else None
+    rep, (got, ref64, refq, sig64, sigq) = headline_batch_check(dyn, cache_aero, prob_aero, oracle_tables, 32768, 64, dump)
+    print(f"\n[headline parity] {rep}")
+    assert rep["lin_err_consistent"]
+    assert rep["well_conditioned"] >= 200, rep            # the sample must contain a meaningful well-conditioned share
+    assert_conditioned_parity(got, ref64, refq, sig64, sigq)
+    assert_structural_constants(got[np.isfinite(got).all(axis=(1, 2, 3))])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Compact result records
+# ---------------------------------------------------------------------------------------------------------------
+def test_compact_layout_is_the_structural_complement(dyn):
+    from conftest import structural_constants
+    idx = dyn.compact_layout()
+    mask, _ = structural_constants()
+    assert idx.shape == (229,) and np.array_equal(np.sort(idx), np.flatnonzero(~mask.reshape(-1)))
+    assert np.all(np.diff(idx) > 0)                        # block (column-major) order
+
+
+@pytest.mark.parametrize("mode,srange", [(0, (0.8, 1.5)), (1, (1.0, 15.0))])
+def test_compact_expands_to_dense_bit_for_bit(dyn, cache_aero, prob_aero, mode, srange):
+    """expand(compact) == dense, bit for bit, through the chunked host path (several pipeline chunks) and through device
+    pointers; lin_err is recomputed exactly; the thrust-LB rows are the same bytes."""
+    import torch
+    from successiveconvexification_b200 import workloads
+    cache_aero.sim_prob.set_kernel(0)
+    B, K = 3000, 50
+    X, U, sigma, _ = workloads.monte_carlo_batch(prob_aero, K, B, 606, sigma_range=srange)
+    blocks, err, tlb = dyn.linearize_batch(cache_aero, X, U, sigma, 1 / (K + 1), 10, mode)
+    comp, ctlb = dyn.linearize_batch_compact(cache_aero, X, U, sigma, 1 / (K + 1), 10, mode)
+    assert comp.shape == (B, K, 230) and np.array_equal(ctlb, tlb)
+    eb, ee, flagged = dyn.expand_compact(comp, X)
+    assert flagged == 0 and not comp[..., 229].any()
+    assert np.array_equal(eb, blocks) and np.array_equal(np.signbit(eb), np.signbit(blocks))
+    assert np.array_equal(ee, err)
+    # device pointers on torch's stream
+    ctx = cache_aero.sim_prob
+    dX, dU, dS = (torch.from_numpy(a).cuda() for a in (X, U, sigma))
+    dC = torch.empty((B, K, 230), dtype=torch.float64, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.linearize_compact_ptr(dX.data_ptr(), dU.data_ptr(), dS.data_ptr(), 1 / (K + 1), 10, mode, K + 1, B, dC.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(dC.cpu().numpy(), comp)
+    ctx.set_stream(0)                                      # NULL = back to the library's own stream
+    comp2, _ = dyn.linearize_batch_compact(cache_aero, X[:7], U[:7], sigma[:7], 1 / (K + 1), 10, mode, tlb=False)
+    assert np.array_equal(comp2, comp[:7])
+
+
+def test_compact_flags_non_finite_intervals(dyn, cache_aero, prob_aero):
+    from successiveconvexification_b200 import workloads
+    X, U, sigma, _ = workloads.monte_carlo_batch(prob_aero, 6, 5, 9, sigma_range=(0.8, 1.5))
+    X[2, 3, 4:7] = 0.0                                      # |v| = 0: the aero force divides by it (aerodynamics.jl:39)
+    comp, _ = dyn.linearize_batch_compact(cache_aero, X, U, sigma, 1 / 7)
+    flags = comp[..., 229]
+    assert flags[2, 3] == 1.0 and flags.sum() == 1.0
+    _, _, n = dyn.expand_compact(comp, X)
+    assert n == 1
+
+
+def test_pinned_host_memory_round_trip():
+    import ctypes
+    from successiveconvexification_b200 import _lib
+    lib = _lib.load()
+    p = ctypes.c_void_p()
+    _lib.check(lib.scvx_host_alloc(ctypes.byref(p), 1 << 20))
+    assert p.value
+    _lib.check(lib.scvx_host_free(p))
+    a = np.zeros(1 << 17)
+    _lib.check(lib.scvx_host_register(a.ctypes.data, a.nbytes))
+    _lib.check(lib.scvx_host_unregister(a.ctypes.data))

@@ -210,3 +210,36 @@ def test_predict_matches_block_endpoint(prob_aero, oracle_tables):
     blocks, _, _, _ = oracle.linearize_batch(params, oracle_tables, X, U, sigma, 0.25, 10, 0, False, False)
     end, _ = oracle.predict_batch(params, oracle_tables, X, U, sigma, 0.25)
     assert np.array_equal(end, blocks[:, :, 0, :])
+
+
+def test_binary128_evaluation_and_branch_signatures(prob_aero, oracle_tables):
+    """The oracle's IEEE binary128 evaluation (same operation sequence, 113-bit arithmetic) is the yardstick of the
+    conditioning-aware parity checks: at the reference's sigma = 1 the FP64 oracle sits within rounding of it; the
+    distance grows with sigma under the LITERAL stage rule (dynamics.jl:126-128) and stays small under TEXTBOOK."""
+    from conftest import parity_metric_per_interval
+    X, U, sigma, dt = workloads.sample_trajectory(prob_aero)
+    info = ProbInfo(prob_aero)
+    b64, s64 = oracle.linearize_batch_ex(info, oracle_tables, X, U, sigma, dt, 10, 0, precision=0)
+    bq, sq = oracle.linearize_batch_ex(info, oracle_tables, X, U, sigma, dt, 10, 0, precision=1)
+    plain, _, _, _ = oracle.linearize_batch(info, oracle_tables, X, U, sigma, dt, 10, 0, False, False)
+    assert np.array_equal(b64, plain)                       # the _ex entry point is the same FP64 arithmetic
+    # the sample trajectory flies exactly tail-first (cos(aoa) = -1): rounding decides on which side of the clamp bound a
+    # few intervals land (the signature differs, the value does not — the clamped quantity has zero gradient there)
+    assert (s64 != sq).sum() <= 8 and len(set(s64.reshape(-1).tolist())) > 1
+    assert parity_metric_per_interval(b64, bq).max() <= 1e-12
+    # 50-digit central differences (mp_restatement) and binary128 forward mode agree far below FP64 resolution
+    from oracle import mp_restatement as mpr
+    inp = np.concatenate([X[0, 0], U[0, 0], U[0, 1], sigma[:1]])
+    T = dict(drag=oracle_tables.drag, lift=oracle_tables.lift, geom=oracle_tables.geom)
+    e, D = mpr.linearize_interval(mpr.probinfo_mp(info), T, inp, dt, 10, 0)
+    D64 = np.array([[float(v) for v in row] for row in D])
+    assert np.abs(D64.T - bq[0, 0, 1:22]).max() <= 1e-15 * np.abs(D64).max()
+    # conditioning: LITERAL degrades with sigma, TEXTBOOK does not
+    Xm, Um, sm, P = workloads.monte_carlo_batch(prob_aero, 4, 12, 1003, sigma_range=(12.0, 15.0))
+    lit64, a = oracle.linearize_batch_ex(P, oracle_tables, Xm, Um, sm, 0.2, 10, 0, precision=0)
+    litq, b = oracle.linearize_batch_ex(P, oracle_tables, Xm, Um, sm, 0.2, 10, 0, precision=1)
+    txt64, _ = oracle.linearize_batch_ex(P, oracle_tables, Xm, Um, sm, 0.2, 10, 1, precision=0)
+    txtq, _ = oracle.linearize_batch_ex(P, oracle_tables, Xm, Um, sm, 0.2, 10, 1, precision=1)
+    same = (a == b).reshape(-1)
+    assert parity_metric_per_interval(txt64, txtq).max() <= 1e-10
+    assert parity_metric_per_interval(lit64, litq)[same].max() > 1e-10     # no FP64 implementation holds 1e-10 here

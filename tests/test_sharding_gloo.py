@@ -33,6 +33,10 @@ def _worker(rank, world, port, B, K, out_dir):
     blocks, _, _, _ = oracle.linearize_batch(params, tb, X[b0:b1], U[b0:b1], sigma[b0:b1], 1.0 / (K + 1),
                                              want_lin_err=False, want_tlb=False, nthreads=1)
     full = sharding.gather_shards(torch.from_numpy(blocks))
+    rooted = sharding.gather_to_root(torch.from_numpy(blocks), dst=0)
+    assert (rooted is None) == (rank != 0)
+    if rank == 0:
+        assert torch.equal(rooted, full)
     ok, csum = sharding.reduce_status(bool(np.isfinite(blocks).all()), float(blocks.sum()), torch.device("cpu"))
     if rank == 0:
         np.save(os.path.join(out_dir, "gathered.npy"), full.numpy())
