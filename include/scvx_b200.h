@@ -202,8 +202,9 @@ int scvx_socp_pattern(int n_nodes, int32_t* colptr, int32_t* rowind);
 int scvx_socp_values_batch(scvx_ctx* ctx, const double* blocks, const double* lin_err, const double* tlb, int n_nodes, int B,
                            double* out_vals, double* out_const);
 
-/* Stream used for device-pointer calls (a cudaStream_t of the device the pointers live on; NULL = back to the library's
- * own stream). */
+/* Stream used for device-pointer calls (a cudaStream_t of the device the pointers live on).  NULL = back to the library's
+ * own non-blocking stream; to run on the legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1), which is what
+ * frameworks mean by "stream 0". */
 int scvx_set_stream(scvx_ctx* ctx, void* cuda_stream);
 /* Kernel selection (SCVX_KERNEL_*). */
 int scvx_set_kernel(scvx_ctx* ctx, int which);

@@ -88,6 +88,7 @@ function aero_coefficients(ctx::Context, which::Integer, n_cos::Integer, n_mach:
 end
 
 set_kernel!(ctx::Context, which::Integer) = check(ccall((:scvx_set_kernel, LIB), Cint, (Ptr{Cvoid}, Cint), ctx.handle, which))
+# C_NULL = back to the library's own stream; the legacy default stream is cudaStreamLegacy = Ptr{Cvoid}(1)
 set_stream!(ctx::Context, stream::Ptr{Cvoid}) = check(ccall((:scvx_set_stream, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.handle, stream))
 synchronize(ctx::Context) = check(ccall((:scvx_synchronize, LIB), Cint, (Ptr{Cvoid},), ctx.handle))
 launch_count(ctx::Context) = ccall((:scvx_launch_count, LIB), Int64, (Ptr{Cvoid},), ctx.handle)

@@ -1,0 +1,35 @@
+"""Build kernel variants of libscvx_b200.so for A/B runs on the GPU box (compile-time switches of the STAGED kernels).
+
+    python profiles/build_variants.py            ->  successiveconvexification_b200/variants/libscvx_b200_<name>.so
+    SCVX_B200_LIB=successiveconvexification_b200/variants/libscvx_b200_<name>.so python profiles/quick_gpu.py
+
+Only scvx_kernels_staged.cu is recompiled per variant; the other objects come from the default build."""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from successiveconvexification_b200.csrc import build as b
+
+VARIANTS = {
+    "base": [],
+    "mb3": ["-DSCVX_A_MINBLOCKS=3"],
+    "mb3_park": ["-DSCVX_A_MINBLOCKS=3", "-DSCVX_A_PARK=1"],
+    "mb4_park": ["-DSCVX_A_MINBLOCKS=4", "-DSCVX_A_PARK=1"],
+}
+
+
+def main(names):
+    b.build()
+    out_dir = os.path.join(b.PKG, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    objs = [os.path.join(b.HERE, s[:-3] + ".o") for s in b.SOURCES if s != "scvx_kernels_staged.cu"]
+    for name in names:
+        flags = VARIANTS[name]
+        o = os.path.join(out_dir, f"staged_{name}.o")
+        subprocess.check_call([b._nvcc()] + b.NVCC_FLAGS + flags + ["-c", os.path.join(b.HERE, "scvx_kernels_staged.cu"), "-o", o])
+        so = os.path.join(out_dir, f"libscvx_b200_{name}.so")
+        subprocess.check_call([b._nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so] + objs + [o])
+        print(so)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or list(VARIANTS))

@@ -20,3 +20,4 @@ for it in range(6):
     torch.cuda.synchronize()
     ms = ctx.last_kernel_ms()
     print('ms', round(ms, 4), 'intervals/s %.4e' % (B * K / ms * 1e3))
+print('checksum %.17g' % float(out.abs().sum().item()), 'finite', bool(torch.isfinite(out).all().item()))

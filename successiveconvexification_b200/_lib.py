@@ -12,7 +12,8 @@ import os
 from .defns import CProbInfo
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscvx_b200.so")
+# SCVX_B200_LIB selects another build of the same library (kernel-variant A/B runs of profiles/build_variants.py)
+LIB_PATH = os.environ.get("SCVX_B200_LIB") or os.path.join(_HERE, "libscvx_b200.so")
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ctx_p = ctypes.c_void_p

@@ -35,7 +35,14 @@ namespace {
 // (conflict-free), because the value chain already uses every register;
 // the Jacobian blocks they need (dF/dv, f_v, m) are at hand here, so no separate pass re-reads the stage records
 // (a separate one-thread-per-interval kernel was latency bound on those reads: 0.13 ms per chunk vs +0.03 ms here).
-constexpr size_t LIGHT_SMEM_BYTES = 24 * 128 * sizeof(double);
+#ifndef SCVX_A_PARK
+#define SCVX_A_PARK 0
+#endif
+// SCVX_A_PARK: the step-start state x and the rk4 accumulator (28 doubles) also live in lane-private shared memory, so
+// that the kernel fits 168 registers and a third block per SM (3 warps per scheduler hide the dependent-issue latency of
+// the serial value chain better than 2).
+constexpr int VALUE_SMEM_DOUBLES = 24 + (SCVX_A_PARK ? 28 : 0);
+constexpr size_t LIGHT_SMEM_BYTES = VALUE_SMEM_DOUBLES * 128 * sizeof(double);
 __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(StagedArgs a) {
     extern __shared__ double light_smem[];            // [24][128] doubles
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,10 +80,22 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
             }
     }
     double pca = 0.0;
+#if SCVX_A_PARK
+    double* PX = L + 24 * 128;            // step-start state [14][128]
+    double* PA = L + 38 * 128;            // rk4 accumulator  [14][128]
+#pragma unroll
+    for (int r = 0; r < 14; ++r) PX[r * 128] = x[r];
+#endif
     for (int it = 0; it < bt.npts; ++it) {
-        double acc[14], y[14];
+        double y[14];
+#if SCVX_A_PARK
+#pragma unroll
+        for (int r = 0; r < 14; ++r) { y[r] = PX[r * 128]; PA[r * 128] = 0.0; }
+#else
+        double acc[14];
 #pragma unroll
         for (int r = 0; r < 14; ++r) { y[r] = x[r]; acc[r] = 0.0; }
+#endif
 #pragma unroll 1
         for (int st = 0; st < 4; ++st) {
             const double pc = (st == 0) ? pca : (st == 3 ? pca + pcs : pca + 0.5 * pcs);
@@ -132,17 +151,35 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
                     }
                 }
             }
+#if SCVX_A_PARK
+#pragma unroll
+            for (int r = 0; r < 14; ++r) {
+                const double k = f[r] * sigma;
+                PA[r * 128] = fma(wgt, k, PA[r * 128]);
+                y[r] = fma(cy, k, PX[r * 128]);
+            }
+#else
 #pragma unroll
             for (int r = 0; r < 14; ++r) {
                 const double k = f[r] * sigma;
                 acc[r] = fma(wgt, k, acc[r]);
                 y[r] = fma(cy, k, x[r]);
             }
+#endif
         }
         pca += pcs;
+#if SCVX_A_PARK
+#pragma unroll
+        for (int r = 0; r < 14; ++r) PX[r * 128] = fma(h * (1.0 / 6.0), PA[r * 128], PX[r * 128]);
+#else
 #pragma unroll
         for (int r = 0; r < 14; ++r) x[r] = fma(h * (1.0 / 6.0), acc[r], x[r]);
+#endif
     }
+#if SCVX_A_PARK
+#pragma unroll
+    for (int r = 0; r < 14; ++r) x[r] = PX[r * 128];
+#endif
     if (!live) return;
     double* blk = bt.out_blocks + (size_t)w * SCVX_BLOCK_DOUBLES;
 #pragma unroll

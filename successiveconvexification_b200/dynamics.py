@@ -96,7 +96,15 @@ class DeviceContext:
         _lib.check(self._lib.scvx_set_kernel(self._h, which))
 
     def set_stream(self, cuda_stream: int):
-        _lib.check(self._lib.scvx_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+        """Stream of device-pointer calls.  `cuda_stream` is a stream handle as torch reports it
+        (`torch.cuda.current_stream().cuda_stream`): torch's default stream has handle 0, which the C ABI reserves for
+        "back to the library's own stream", so 0 is passed on as cudaStreamLegacy (handle 1) — the same stream."""
+        CUDA_STREAM_LEGACY = 1
+        _lib.check(self._lib.scvx_set_stream(self._h, ctypes.c_void_p(cuda_stream or CUDA_STREAM_LEGACY)))
+
+    def use_library_stream(self):
+        """Device-pointer calls go back to the library's own (non-blocking) stream: `scvx_set_stream(ctx, NULL)`."""
+        _lib.check(self._lib.scvx_set_stream(self._h, None))
 
     def synchronize(self):
         _lib.check(self._lib.scvx_synchronize(self._h))

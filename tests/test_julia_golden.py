@@ -1,0 +1,98 @@
+"""Reference-produced golden vectors (tools/gen_golden.jl -> tests/golden/julia_golden.f64).
+
+The reference ships no tests or known-answer vectors for this path and Julia is not installed in the build image, so
+until a maintainer with Julia runs `julia tools/gen_golden.jl /path/to/SuccessiveConvexification`, parity is
+"unpinned by the reference" and the two consumer tests below SKIP LOUDLY.  When the file is present they are the pin:
+the CPU oracle and the CUDA path against the reference's own `Dynamics.rk4` + forward-mode Jacobian
+(dynamics.jl:112-134, 311-313) at 1e-10, conditioning-aware for the sigma ~ U(1, 15) case (conftest.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_parity, parity_metric_per_interval
+
+sys.path.insert(0, GOLDEN)
+import make_julia_inputs  # noqa: E402
+
+GOLD_BIN = os.path.join(GOLDEN, "julia_golden.f64")
+GOLD_TXT = os.path.join(GOLDEN, "julia_golden.txt")
+SKIP_MSG = ("PARITY UNPINNED BY THE REFERENCE: tests/golden/julia_golden.f64 is absent. Run "
+            "`julia tools/gen_golden.jl /path/to/SuccessiveConvexification` on a machine with Julia and commit the two files.")
+
+
+def _cases():
+    return {name: (X, U, sigma, dt) for name, X, U, sigma, dt in make_julia_inputs.cases()}
+
+
+def _julia_blocks():
+    """{case: (B, n_int, 22, 14)}: row 0 the endpoint, rows 1..21 the columns of D — the first 22 block columns."""
+    if not (os.path.exists(GOLD_BIN) and os.path.exists(GOLD_TXT)):
+        pytest.skip(SKIP_MSG)
+    data = np.fromfile(GOLD_BIN, dtype="<f8")
+    out = {}
+    for line in open(GOLD_TXT):
+        if line.startswith("#") or not line.strip():
+            continue
+        name, B, n, off = line.split()
+        B, n, off = int(B), int(n), int(off)
+        out[name] = data[off:off + B * (n - 1) * 308].reshape(B, n - 1, 22, 14)
+    return out
+
+
+def _as_blocks(j22, X, U, sigma):
+    """Append z = endpoint - D * inp (formed here in FP64 from the Julia numbers) -> (B, n_int, 23, 14)."""
+    B, ni = j22.shape[:2]
+    inp = np.concatenate([X[:, :-1], U[:, :-1], U[:, 1:], np.broadcast_to(sigma[:, None, None], (B, ni, 1))], axis=-1)
+    z = j22[:, :, 0, :] - np.einsum("bicr,bic->bir", j22[:, :, 1:22, :], inp)
+    return np.concatenate([j22, z[:, :, None, :]], axis=2)
+
+
+def test_committed_inputs_are_reproducible():
+    data, manifest = make_julia_inputs.build()
+    assert np.array_equal(np.fromfile(os.path.join(GOLDEN, "julia_inputs.f64"), dtype="<f8"), data)
+    committed = [l for l in open(os.path.join(GOLDEN, "julia_inputs.txt")) if not l.startswith("#")]
+    assert "".join(committed) == manifest
+
+
+def test_generator_script_evaluates_the_reference_functions():
+    """Structure check of the (unexecuted) recipe: it loads the reference's own files and calls its own functions."""
+    src = open(os.path.join(os.path.dirname(os.path.dirname(GOLDEN)), "tools", "gen_golden.jl")).read()
+    for needle in ("Dynamics.rk4(", "Dynamics.sensitivity_zygote(", "ForwardDiff.jacobian(", 'include(joinpath(REFDIR, "dynamics.jl"))',
+                   "SampleProblems.base_prob_aero_scaled", "julia_inputs.f64", "julia_golden.f64"):
+        assert needle in src, needle
+    assert "SCvxB200" not in src and "libscvx" not in src          # nothing of this repository is loaded
+
+
+def _check(case, got, ref23):
+    m = parity_metric_per_interval(got, ref23)[:, :5]                     # endpoint, A, B-, B+, Sigma (z is not a Julia output)
+    if case == "mc_sigma_1_15":
+        # LITERAL rk4 at sigma up to 15: FP64 itself cannot hold 1e-10 (conftest.py); two FP64 evaluations of the same
+        # map (Julia's ForwardDiff and this one) agree to the conditioning of each interval, measured by the oracle's
+        # binary128 run in test_gpu_parity.test_headline_config_literal_sigma_1_15.  Report, and bound loosely.
+        print(f"\n[julia golden {case}] max metric {m.max():.3e} (ill-conditioned case, informational bound 1e-6)")
+        assert m.max() <= 1e-6
+    else:
+        assert m.max() <= 1e-10, f"{case}: {m.max():.3e}"
+
+
+def test_oracle_vs_julia_golden(prob_aero, oracle_tables):
+    from oracle import oracle
+    from successiveconvexification_b200.defns import ProbInfo
+    gold = _julia_blocks()
+    for case, (X, U, sigma, dt) in _cases().items():
+        ref, _, _, _ = oracle.linearize_batch(ProbInfo(prob_aero), oracle_tables, X, U, sigma, dt, 10, 0, False, False)
+        _check(case, ref, _as_blocks(gold[case], X, U, sigma))
+
+
+@pytest.mark.gpu
+def test_cuda_vs_julia_golden(prob_aero):
+    from successiveconvexification_b200 import dynamics as dyn
+    gold = _julia_blocks()
+    cache = dyn.make_cache(prob_aero)
+    for case, (X, U, sigma, dt) in _cases().items():
+        for kernel in (1, 2):
+            cache.sim_prob.set_kernel(kernel)
+            blocks, _, _ = dyn.linearize_batch(cache, X, U, sigma, dt, 10, 0)
+            _check(case, blocks, _as_blocks(gold[case], X, U, sigma))
