@@ -452,6 +452,15 @@ def main():
         d2h_compact = int(hCmp.nbytes + hTlb.nbytes)
         n_flag = int((hCmp[..., 229] != 0).sum().item())
         del hCmp
+        # layout NO_Z (216-double records: the reference's SOCP consumes D and lin_err, not z)
+        hC2 = torch.empty((B, ni, 216), dtype=torch.float64).pin_memory()
+
+        def step_no_z():
+            ctx.linearize_compact_ptr(hX.data_ptr(), hU.data_ptr(), hS.data_ptr(), dt, NPTS, args.mode, n_nodes, B,
+                                      hC2.data_ptr(), hTlb.data_ptr(), dynamics.COMPACT_NO_Z)
+        v_no_z = timed_host(step_no_z, e2e_steps)
+        d2h_no_z = int(hC2.nbytes + hTlb.nbytes)
+        del hC2
         hOut = torch.empty((B, ni, 23, 14), dtype=torch.float64).pin_memory()
         hErr = torch.empty((B, ni, 14), dtype=torch.float64).pin_memory()
 
@@ -466,6 +475,9 @@ def main():
                "call": "scvx_linearize_batch_compact (230-double records: 229 data entries + status word; lin_err recomputed "
                        "exactly by scvx_expand_compact on the host)",
                "intervals_flagged_non_finite": n_flag,
+               "d2h_gb_per_s_per_gpu": d2h_compact * v_compact / total_intervals * 1e-9,
+               "no_z": {"value": v_no_z, "call": "scvx_linearize_batch_compact, layout NO_Z (216-double records; z re-formed on the host)",
+                        "d2h_bytes_per_step": d2h_no_z},
                "dense": {"value": v_dense, "call": "scvx_linearize_batch (14x23 blocks + lin_err + tlb)",
                          "d2h_bytes_per_step": int(hOut.nbytes + hErr.nbytes + hTlb.nbytes)},
                "note": "pinned host buffers; chunked H2D/kernel/D2H pipeline; PCIe-bound; " + numa_note}

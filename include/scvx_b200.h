@@ -109,6 +109,33 @@ int scvx_linearize_batch(scvx_ctx* ctx, const double* X, const double* U, const 
                          double base_dt, int npts, int mode, int n_nodes, int B,
                          double* out_blocks, double* out_lin_err, double* out_tlb);
 
+/* SURVEY.md §8f-4 — fin forces and aero torque (control_dim 3 -> 5).  The reference carries these terms as COMMENTS and
+ * never runs them (control_dim = 3, rocketland.jl:17; ff and bdy_trq commented out at dynamics.jl:63, 66, 69), so there is
+ * NO REFERENCE CONSUMER and no reference behaviour to match; the entry point restores exactly the commented expressions:
+ *   ff = u[4]*fd1 + u[5]*fd2, fd1 = normalize((C(q) e2) x v), fd2 = fd1 x v          dynamics.jl:60-63
+ *   aero_frc = aerf + ff;  aero_trq = cross(rFB, ff) + bdy_trq                           dynamics.jl:66, 69
+ *   bdy_trq = trq_itrp(cos_aoa, mach) * length_scalar * force_scalar * normalize(v x bv) (zero when |dp| >= 0.95)
+ *                                                                                         aerodynamics.jl:45, 49-56
+ * Needs aero_kind = TABLE and all three tables (drag, lift, torque).  The torque makes wdot depend on q and v, so the
+ * structural zeros the STAGED kernels exploit are gone: this variant runs on the generic forward-mode kernel (one warp
+ * per interval, lane L < 25 carries d/d inp[L]), exact by construction, ~7x slower than the 3-control path.
+ *   X 14 x n_nodes x B    U5 5 x n_nodes x B    sigma B      inp = [x; u_k(5); u_{k+1}(5); sigma] (25)
+ *   out_blocks 14 x 27 x (n_nodes-1) x B = [ endpoint | D (25 columns) | z ]   (acc_width = 14 + 2*5 + 3, rocketland.jl:22)
+ *   out_lin_err 14 x (n_nodes-1) x B (optional).  All host or all device pointers. */
+int scvx_linearize_batch_fins(scvx_ctx* ctx, const double* X, const double* U5, const double* sigma,
+                              double base_dt, int npts, int mode, int n_nodes, int B,
+                              double* out_blocks, double* out_lin_err);
+
+/* Fin-force tables (aero/fin.csv: columns lift, drag over 60 Mach numbers x 901 deflection angles, written by
+ * aero/AeroTable.jl:94-112; read and dropped at aerodynamics.jl:23-26 — no consumer in the reference).  Staged like the
+ * other tables (same cubic B-spline prefilter and Flat extrapolation): which = 0 lift, 1 drag; samples n_mach x n_defl
+ * column-major (Mach fastest, the file's row order).  scvx_fin_force_batch evaluates both splines for n (mach,
+ * deflection) pairs: the lookup a fin-deflection control model would build on.  Host or device pointers. */
+int scvx_set_fin_table(scvx_ctx* ctx, int which, const double* samples, int n_mach, int n_defl,
+                       double mach0, double dmach, double defl0, double ddefl, int prefiltered);
+int scvx_fin_force_batch(scvx_ctx* ctx, const double* mach, const double* deflection, int n,
+                         double* out_lift, double* out_drag);
+
 /* predict_state / simulate_zygote for every interval (value only): out 14 x (n_nodes-1) x B. */
 int scvx_predict_batch(scvx_ctx* ctx, const double* X, const double* U, const double* sigma,
                        double base_dt, int npts, int mode, int n_nodes, int B, double* out_endpoints);
@@ -123,22 +150,31 @@ int scvx_predict_batch(scvx_ctx* ctx, const double* X, const double* U, const do
  *   slot  229     status word: 0.0 if every entry of the dense block is finite, 1.0 otherwise (per-interval non-finite
  *                 flag; the constants of a flagged interval's dense block are not guaranteed)
  * lin_err is not shipped: it is endpoint - x_{n+1}, one IEEE subtraction the host repeats exactly (scvx_expand_compact).
- *   out_compact 230 x (n_nodes-1) x B      out_tlb 4 x n_nodes x B (optional)
+ * layout SCVX_COMPACT_NO_Z drops the z column as well (the reference's SOCP consumes D and lin_err only,
+ * rocketland.jl:123-133, 251-258; z is the named output of old_dynamics.jl:139): 215 data entries + status word =
+ * SCVX_COMPACT_NO_Z_DOUBLES = 216 doubles; the expander then re-forms z = endpoint - D*inp on the host in FP64 (same
+ * value to rounding, not the same bits: the summation order differs from the device's).
+ *   out_compact R x (n_nodes-1) x B, R = scvx_compact_record_doubles(layout)      out_tlb 4 x n_nodes x B (optional)
  * Host or device pointers, as scvx_linearize_batch. */
+enum { SCVX_COMPACT_FULL = 0, SCVX_COMPACT_NO_Z = 1 };
 #define SCVX_COMPACT_DOUBLES 230
 #define SCVX_COMPACT_DATA 229
+#define SCVX_COMPACT_NO_Z_DOUBLES 216
+int scvx_compact_record_doubles(int layout);      /* 230, 216, or a negative error code */
 int scvx_linearize_batch_compact(scvx_ctx* ctx, const double* X, const double* U, const double* sigma,
-                                 double base_dt, int npts, int mode, int n_nodes, int B,
+                                 double base_dt, int npts, int mode, int n_nodes, int B, int layout,
                                  double* out_compact, double* out_tlb);
 /* Dense offset (column * 14 + row, 0 <= offset < 322) of compact slots 0..228; no device work.  `index` has room for
  * SCVX_COMPACT_DATA int32. */
 int scvx_compact_layout(int32_t* index);
 /* Host-side expander (plain C loop on `n_threads` host threads, no device work; all pointers are HOST memory):
- * compact 230 x K x B  ->  out_blocks 14 x 23 x K x B (may be NULL) with the structural constants filled in, equal to what
- * scvx_linearize_batch writes for every interval whose status word is 0;  out_lin_err 14 x K x B (may be NULL; needs X
- * 14 x n_nodes x B).  Returns the number of intervals whose status word is non-zero (>= 0), or a negative error code. */
-int64_t scvx_expand_compact(const double* compact, const double* X, int n_nodes, int B, double* out_blocks,
-                            double* out_lin_err, int n_threads);
+ * compact R x K x B  ->  out_blocks 14 x 23 x K x B (may be NULL) with the structural constants filled in, equal to what
+ * scvx_linearize_batch writes for every interval whose status word is 0 (layout NO_Z: except the z column, see above);
+ * out_lin_err 14 x K x B (may be NULL).  X 14 x n_nodes x B is needed for out_lin_err and for NO_Z; U 3 x n_nodes x B
+ * and sigma B for NO_Z only (may be NULL otherwise).
+ * Returns the number of intervals whose status word is non-zero (>= 0), or a negative error code. */
+int64_t scvx_expand_compact(const double* compact, int layout, const double* X, const double* U, const double* sigma,
+                            int n_nodes, int B, double* out_blocks, double* out_lin_err, int n_threads);
 
 /* Page-locked host memory.  The chunked H2D / kernel / D2H pipeline of host-pointer calls overlaps copies with compute
  * only for page-locked buffers (pageable memory makes every cudaMemcpyAsync a staged, serialising copy): allocate result

@@ -120,18 +120,22 @@ end
 # per-interval non-finite flag) cross PCIe.  `expand_compact` restores the dense blocks and lin_err on the host.
 const COMPACT_DOUBLES = 230
 const COMPACT_DATA = 229
+const COMPACT_FULL = Cint(0)     # 229 data entries + status word
+const COMPACT_NO_Z = Cint(1)     # without the z column (the SOCP consumes D and lin_err only): 215 + status word = 216
+
+compact_record_doubles(layout::Integer) = Int(ccall((:scvx_compact_record_doubles, LIB), Cint, (Cint,), layout))
 
 function linearize_batch_compact(ctx::Context, X::Array{Float64,3}, U::Array{Float64,3}, sigma::Vector{Float64},
-                                 base_dt::Float64; tlb::Bool=true, mode::Cint=ctx.mode,
+                                 base_dt::Float64; tlb::Bool=true, mode::Cint=ctx.mode, layout::Cint=COMPACT_FULL,
                                  out::Union{Nothing,Array{Float64,3}}=nothing)
     n_nodes, B = size(X, 2), size(X, 3)
-    comp = out === nothing ? Array{Float64,3}(undef, COMPACT_DOUBLES, n_nodes - 1, B) : out
+    comp = out === nothing ? Array{Float64,3}(undef, compact_record_doubles(layout), n_nodes - 1, B) : out
     tl = tlb ? Array{Float64,3}(undef, 4, n_nodes, B) : Array{Float64,3}(undef, 0, 0, 0)
     GC.@preserve X U sigma comp tl begin
         check(ccall((:scvx_linearize_batch_compact, LIB), Cint,
-                    (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Cint, Cint, Cint,
+                    (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Cint, Cint, Cint, Cint,
                      Ptr{Cdouble}, Ptr{Cdouble}),
-                    ctx.handle, X, U, sigma, base_dt, ctx.npts, mode, n_nodes, B,
+                    ctx.handle, X, U, sigma, base_dt, ctx.npts, mode, n_nodes, B, layout,
                     comp, tlb ? pointer(tl) : Ptr{Cdouble}(C_NULL)))
     end
     return comp, tl
@@ -145,11 +149,14 @@ function compact_layout()
 end
 
 # -> blocks 14 x 23 x K x B, lin_err 14 x K x B, number of intervals flagged non-finite
-function expand_compact(compact::Array{Float64,3}, X::Array{Float64,3}; n_threads::Int=0)
+function expand_compact(compact::Array{Float64,3}, X::Array{Float64,3}, U::Array{Float64,3}, sigma::Vector{Float64};
+                        n_threads::Int=0)
     K, B = size(compact, 2), size(compact, 3)
+    layout = size(compact, 1) == COMPACT_DOUBLES ? COMPACT_FULL : COMPACT_NO_Z
     blocks = Array{Float64,4}(undef, 14, 23, K, B); err = Array{Float64,3}(undef, 14, K, B)
-    n = GC.@preserve compact X blocks err ccall((:scvx_expand_compact, LIB), Int64,
-            (Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint), compact, X, K + 1, B, blocks, err, n_threads)
+    n = GC.@preserve compact X U sigma blocks err ccall((:scvx_expand_compact, LIB), Int64,
+            (Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint),
+            compact, layout, X, U, sigma, K + 1, B, blocks, err, n_threads)
     n < 0 && check(n)
     return blocks, err, Int(n)
 end
@@ -165,6 +172,36 @@ function pinned_array(::Type{T}, dims::Integer...) where {T}
     return unsafe_wrap(Array, Ptr{T}(p[]), dims; own=false)
 end
 free_pinned!(A::Array) = check(ccall((:scvx_host_free, LIB), Cint, (Ptr{Cvoid},), A))
+
+# SURVEY §8f-4 variant: fin forces + aero torque, control_dim = 5 (the terms commented out at dynamics.jl:60-63, 66, 69).
+# NO REFERENCE CONSUMER.  X 14 x n x B, U5 5 x n x B  ->  blocks 14 x 27 x (n-1) x B = [endpoint | D (25) | z], lin_err.
+function linearize_batch_fins(ctx::Context, X::Array{Float64,3}, U5::Array{Float64,3}, sigma::Vector{Float64}, base_dt::Float64;
+                              mode::Cint=ctx.mode)
+    n_nodes, B = size(X, 2), size(X, 3)
+    blocks = Array{Float64,4}(undef, 14, 27, n_nodes - 1, B); err = Array{Float64,3}(undef, 14, n_nodes - 1, B)
+    GC.@preserve X U5 sigma blocks err begin
+        check(ccall((:scvx_linearize_batch_fins, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}),
+                    ctx.handle, X, U5, sigma, base_dt, ctx.npts, mode, n_nodes, B, blocks, err))
+    end
+    return blocks, err
+end
+
+# fin-force tables of aero/fin.csv (n_mach x n_defl, Mach fastest): which = 0 lift, 1 drag
+function set_fin_table!(ctx::Context, which::Integer, samples::Matrix{Float64}, mach::AbstractRange, defl::AbstractRange)
+    check(ccall((:scvx_set_fin_table, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Cint, Cdouble, Cdouble, Cdouble, Cdouble, Cint),
+                ctx.handle, which, samples, length(mach), length(defl), first(mach), step(mach), first(defl), step(defl), 0))
+end
+
+function fin_force_batch(ctx::Context, mach::Vector{Float64}, deflection::Vector{Float64})
+    n = length(mach); lift = Vector{Float64}(undef, n); drag = Vector{Float64}(undef, n)
+    GC.@preserve mach deflection lift drag begin
+        check(ccall((:scvx_fin_force_batch, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}),
+                    ctx.handle, mach, deflection, n, lift, drag))
+    end
+    return lift, drag
+end
 
 function predict_batch(ctx::Context, X::Array{Float64,3}, U::Array{Float64,3}, sigma::Vector{Float64}, base_dt::Float64;
                        mode::Cint=ctx.mode)

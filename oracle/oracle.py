@@ -40,20 +40,21 @@ def _c(a):
 
 
 class OracleTables:
-    """Prefiltered drag/lift coefficient tables ((n1+2) x (n2+2), column-major)."""
+    """Prefiltered drag/lift (and, for the fins variant, torque) coefficient tables ((n1+2) x (n2+2), column-major)."""
 
-    def __init__(self, drag_samples, lift_samples, cos0, dcos, mach0, dmach):
+    def __init__(self, drag_samples, lift_samples, cos0, dcos, mach0, dmach, trq_samples=None):
         drag = np.asfortranarray(drag_samples, dtype=np.float64)
         lift = np.asfortranarray(lift_samples, dtype=np.float64)
         n1, n2 = drag.shape
         self.geom = np.array([n1, n2, cos0, dcos, mach0, dmach], dtype=np.float64)
         self.drag = prefilter(drag)
         self.lift = prefilter(lift)
+        self.trq = prefilter(np.asfortranarray(trq_samples, dtype=np.float64)) if trq_samples is not None else None
 
     @classmethod
     def from_aero(cls, aero):
-        d, l = aero.drag_itrp, aero.lift_itrp
-        return cls(d.samples, l.samples, d.cos0, d.dcos, d.mach0, d.dmach)
+        d, l, t = aero.drag_itrp, aero.lift_itrp, getattr(aero, "trq_itrp", None)
+        return cls(d.samples, l.samples, d.cos0, d.dcos, d.mach0, d.dmach, None if t is None else t.samples)
 
 
 def prefilter(samples):
@@ -159,6 +160,23 @@ def linearize_batch_ex(infos, tables, X, U, sigma, dt, npts=10, mode=0, nthreads
                                 _p(blocks), None, None, nthreads, precision,
                                 sig.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
     return blocks, sig
+
+
+def linearize_batch_fins(infos, tables, X, U5, sigma, dt, npts=10, mode=0, want_lin_err=True, nthreads=0):
+    """SURVEY.md §8f-4 variant (fin forces + aero torque, control_dim = 5): X (B, n_nodes, 14), U5 (B, n_nodes, 5).
+    -> blocks (B, n_nodes-1, 27, 14) = [endpoint | D (25 columns) | z], lin_err (B, n_nodes-1, 14)."""
+    X, U5, sigma = _c(X), _c(U5), _c(sigma)
+    B, n_nodes, _ = X.shape
+    assert U5.shape == (B, n_nodes, 5) and tables.trq is not None
+    arr, n = _params(infos)
+    blocks = np.zeros((B, n_nodes - 1, 27, 14))
+    lin_err = np.zeros((B, n_nodes - 1, 14)) if want_lin_err else None
+    L = lib()
+    L.oracle_linearize_batch_fins.restype = ctypes.c_int
+    rc = L.oracle_linearize_batch_fins(arr, n, _p(tables.drag), _p(tables.lift), _p(tables.trq), _p(tables.geom), _p(X), _p(U5),
+                                       _p(sigma), ctypes.c_double(dt), npts, mode, n_nodes, B, _p(blocks), _p(lin_err), nthreads)
+    assert rc > 0
+    return blocks, lin_err
 
 
 def predict_batch(infos, tables, X, U, sigma, dt, npts=10, mode=0, nthreads=0):

@@ -140,8 +140,8 @@ struct Table {
 };
 
 struct Tables {
-    Table drag, lift;
-    int have;
+    Table drag, lift, trq;
+    int have, have_trq;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -333,6 +333,124 @@ void rk4(const ProbInfo& P, const Tables& tb, const T inp[21], double dt, int np
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// the fin-force and aero-torque terms the reference carries as COMMENTS, restored (control_dim 3 -> 5).
+// There is no live consumer in the reference (`control_dim = 3`, rocketland.jl:17; `aero_trq = [0,0,0]`,
+// dynamics.jl:69), so nothing here can be checked against reference behaviour: the formulas are the commented-out
+// expressions themselves,
+//     ff       = u[4]*fd1 + u[5]*fd2                       dynamics.jl:60-63   (fd1 = normalize(C e2 x v), fd2 = fd1 x v)
+//     aero_frc = aerf + ff                                 dynamics.jl:66
+//     aero_trq = cross(rFB, ff) + bdy_trq                  dynamics.jl:69
+// with bdy_trq the torque `aero_force` already returns (aerodynamics.jl:45, 49-56): zero in the |dp| >= 0.95 branch,
+// trq_itrp(cos_aoa, mach) * length_scalar * force_scalar * normalize(v x bv) otherwise.
+// ----------------------------------------------------------------------------------------------
+template <class T>
+void aero_force_trq(const ProbInfo& P, const Tables& tb, const T bv[3], const T vel[3], T F[3], T Tq[3]) {
+    const T nv = norm3(vel);
+    const T dp = (bv[0] * vel[0] + bv[1] * vel[1] + bv[2] * vel[2]) / nv;
+    const T car = dp / norm3(bv);
+    const T cos_aoa = clamp_like_julia(car, -1.0, 1.0);
+    const T mach = nv / P.sos;
+    const T drag = spline_eval(tb.drag, cos_aoa, mach) * P.force_scalar;
+    if (real_abs(value_of(dp)) >= 0.95) {
+        for (int k = 0; k < 3; ++k) { F[k] = drag * vel[k] / nv; Tq[k] = T(0.0); }                // :44-45
+        return;
+    }
+    const T lift = spline_eval(tb.lift, cos_aoa, mach) * P.force_scalar;
+    const T trq = spline_eval(tb.trq, cos_aoa, mach) * P.length_scalar * P.force_scalar;          // :49
+    T trqd[3]; cross3(vel, bv, trqd);
+    T ntrqd[3] = { -trqd[0], -trqd[1], -trqd[2] };
+    T liftd[3]; cross3(ntrqd, vel, liftd);
+    const T nl = norm3(liftd), nt = norm3(trqd);
+    for (int k = 0; k < 3; ++k) {
+        F[k] = drag * vel[k] / nv + lift * (liftd[k] / nl);                                       // :52-56
+        Tq[k] = (trqd[k] / nt) * trq;                                                             // :53, :56
+    }
+}
+
+template <class T>
+void dx_static_fins(const ProbInfo& P, const Tables& tb, const T x[14], const T u[5], const T& mult, T out[14]) {
+    const T* q = x + 7;  const T* w = x + 11;  const T* v = x + 4;
+    T C[3][3]; DCM(q, C);
+    T bv[3] = { C[0][0], C[1][0], C[2][0] };
+    T aerf[3], btrq[3];
+    aero_force_trq(P, tb, bv, v, aerf, btrq);
+    T by[3] = { C[0][1], C[1][1], C[2][1] };                                                      // DCM(qbi) * [0,1,0]   :60
+    T fd1[3]; cross3(by, v, fd1);
+    const T n1 = sqrt(fd1[0] * fd1[0] + fd1[1] * fd1[1] + fd1[2] * fd1[2]);
+    for (int k = 0; k < 3; ++k) fd1[k] = fd1[k] / n1;                                             // :61
+    T fd2[3]; cross3(fd1, v, fd2);                                                                // :62
+    T ff[3];
+    for (int k = 0; k < 3; ++k) ff[k] = u[3] * fd1[k] + u[4] * fd2[k];                            // :63
+    T thr[3], acc[3];
+    for (int r = 0; r < 3; ++r) thr[r] = C[r][0] * u[0] + C[r][1] * u[1] + C[r][2] * u[2];
+    for (int r = 0; r < 3; ++r) acc[r] = (thr[r] + (aerf[r] + ff[r])) / x[0];                     // :66-67
+    T rv[4];
+    rv[0] = 0.5 * (-(w[0] * q[1]) - w[1] * q[2] - w[2] * q[3]);
+    rv[1] = 0.5 * (w[0] * q[0] + w[2] * q[2] - w[1] * q[3]);
+    rv[2] = 0.5 * (w[1] * q[0] - w[2] * q[1] + w[0] * q[3]);
+    rv[3] = 0.5 * (w[2] * q[0] + w[1] * q[1] - w[0] * q[2]);
+    T rTB[3] = { T(P.rTB[0]), T(P.rTB[1]), T(P.rTB[2]) };
+    T rFB[3] = { T(P.rFB[0]), T(P.rFB[1]), T(P.rFB[2]) };
+    T t1[3]; cross3(rTB, u, t1);
+    T tf[3]; cross3(rFB, ff, tf);
+    T Jw[3];
+    for (int r = 0; r < 3; ++r) Jw[r] = P.jB[r + 0] * w[0] + P.jB[r + 3] * w[1] + P.jB[r + 6] * w[2];
+    T t2[3]; cross3(w, Jw, t2);
+    T rhs[3];
+    for (int k = 0; k < 3; ++k) rhs[k] = t1[k] + (tf[k] + btrq[k]) - t2[k];                       // :69-70
+    T ra[3];
+    for (int r = 0; r < 3; ++r) ra[r] = P.jBi[r + 0] * rhs[0] + P.jBi[r + 3] * rhs[1] + P.jBi[r + 6] * rhs[2];
+    out[0] = (-P.a * sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2])) * mult;
+    out[1] = x[4] * mult; out[2] = x[5] * mult; out[3] = x[6] * mult;
+    out[4] = (acc[0] - P.g0) * mult; out[5] = acc[1] * mult; out[6] = acc[2] * mult;
+    for (int k = 0; k < 4; ++k) out[7 + k] = rv[k] * mult;
+    for (int k = 0; k < 3; ++k) out[11 + k] = ra[k] * mult;
+}
+
+// rk4 (dynamics.jl:112-134) over inp = [x(14); u_k(5); u_{k+1}(5); sigma] (25)
+template <class T>
+void rk4_fins(const ProbInfo& P, const Tables& tb, const T inp[25], double dt, int npts, int mode, T state[14]) {
+    for (int k = 0; k < 14; ++k) state[k] = inp[k];
+    const T* su = inp + 14; const T* eu = inp + 19;
+    const double idt = dt / npts, pcs = 1.0 / npts, s = (mode == 0) ? 1.0 : idt;
+    double pca = 0.0;
+    for (int i = 0; i < npts; ++i) {
+        T ict[5], mct[5], ect[5];
+        for (int k = 0; k < 5; ++k) {
+            ict[k] = (1.0 - pca) * su[k] + pca * eu[k];
+            mct[k] = (1.0 - (pca + pcs / 2)) * su[k] + (pca + pcs / 2) * eu[k];
+            ect[k] = (1.0 - (pca + pcs)) * su[k] + (pca + pcs) * eu[k];
+        }
+        T k1[14], k2[14], k3[14], k4[14], tmp[14];
+        dx_static_fins(P, tb, state, ict, inp[24], k1);
+        for (int k = 0; k < 14; ++k) tmp[k] = state[k] + (mode == 0 ? k1[k] / 2.0 : (k1[k] * s) / 2.0);
+        dx_static_fins(P, tb, tmp, mct, inp[24], k2);
+        for (int k = 0; k < 14; ++k) tmp[k] = state[k] + (mode == 0 ? k2[k] / 2.0 : (k2[k] * s) / 2.0);
+        dx_static_fins(P, tb, tmp, mct, inp[24], k3);
+        for (int k = 0; k < 14; ++k) tmp[k] = state[k] + (mode == 0 ? k3[k] : k3[k] * s);
+        dx_static_fins(P, tb, tmp, ect, inp[24], k4);
+        pca += pcs;
+        for (int k = 0; k < 14; ++k) state[k] = state[k] + idt * (k1[k] / 6.0 + k2[k] / 3.0 + k3[k] / 3.0 + k4[k] / 6.0);
+    }
+}
+
+// block: 14 x 27 column-major, col 0 endpoint, cols 1..25 D = d endpoint / d inp (25), col 26 z  (acc_width =
+// state_dim + 2*control_dim + 3 with control_dim = 5, rocketland.jl:22)
+void linearize_interval_fins(const ProbInfo& P, const Tables& tb, const double inp[25], double dt, int npts, int mode,
+                             double* block) {
+    typedef Dual<double, 25> D25;
+    D25 din[25], out[14];
+    for (int k = 0; k < 25; ++k) { din[k] = D25(inp[k]); din[k].d[k] = 1.0; }
+    rk4_fins<D25>(P, tb, din, dt, npts, mode, out);
+    for (int r = 0; r < 14; ++r) {
+        block[r] = out[r].v;
+        double zr = out[r].v;
+        for (int c = 0; c < 25; ++c) { block[r + 14 * (1 + c)] = out[r].d[c]; zr -= out[r].d[c] * inp[c]; }
+        block[r + 14 * 26] = zr;
+    }
+}
+
 // sensitivity_zygote (dynamics.jl:311-313) for one interval + named outputs of old_dynamics.jl:84-98.
 // block: 14 x 23 column-major, col 0 = endpoint, cols 1..21 = D = d endpoint / d inp, col 22 = z.
 // R = double: the reference's arithmetic.  R = quad: the same operation sequence in binary128, results rounded to
@@ -365,6 +483,15 @@ Tables make_tables(const double* drag_coef, const double* lift_coef, const doubl
         tb.drag = Table{ drag_coef, n1, n2, geom[2], geom[3], geom[4], geom[5] };
         tb.lift = Table{ lift_coef, n1, n2, geom[2], geom[3], geom[4], geom[5] };
         tb.have = 1;
+    }
+    return tb;
+}
+
+Tables make_tables3(const double* drag_coef, const double* lift_coef, const double* trq_coef, const double* geom) {
+    Tables tb = make_tables(drag_coef, lift_coef, geom);
+    if (tb.have && trq_coef) {
+        tb.trq = Table{ trq_coef, tb.drag.n1, tb.drag.n2, geom[2], geom[3], geom[4], geom[5] };
+        tb.have_trq = 1;
     }
     return tb;
 }
@@ -476,6 +603,37 @@ int oracle_linearize_batch(const ProbInfo* P, int n_params, const double* drag_c
                            double* out_tlb, int nthreads) {
     return oracle_linearize_batch_ex(P, n_params, drag_coef, lift_coef, geom, X, U, sigma, dt, npts, mode, n_nodes, B,
                                      out_blocks, out_lin_err, out_tlb, nthreads, 0, nullptr);
+}
+
+// SURVEY.md §8f-4 variant (fin forces + aero torque, control_dim = 5): X 14 x n_nodes x B, U 5 x n_nodes x B;
+// out_blocks 14 x 27 x (n_nodes-1) x B; out_lin_err 14 x (n_nodes-1) x B (optional).  Needs all three tables.
+int oracle_linearize_batch_fins(const ProbInfo* P, int n_params, const double* drag_coef, const double* lift_coef,
+                                const double* trq_coef, const double* geom, const double* X, const double* U,
+                                const double* sigma, double dt, int npts, int mode, int n_nodes, int B,
+                                double* out_blocks, double* out_lin_err, int nthreads) {
+    Tables tb = make_tables3(drag_coef, lift_coef, trq_coef, geom);
+    if (!tb.have_trq) return -1;
+    const int ni = n_nodes - 1;
+    const long total = (long)ni * B;
+    int used = 1;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+    used = nthreads > 0 ? nthreads : omp_get_max_threads();
+#pragma omp parallel for schedule(static)
+#endif
+    for (long w = 0; w < total; ++w) {
+        const int b = (int)(w / ni), i = (int)(w % ni);
+        const double* xb = X + ((size_t)b * n_nodes + i) * 14;
+        const double* ub = U + ((size_t)b * n_nodes + i) * 5;
+        double inp[25];
+        for (int k = 0; k < 14; ++k) inp[k] = xb[k];
+        for (int k = 0; k < 10; ++k) inp[14 + k] = ub[k];
+        inp[24] = sigma[b];
+        double* blk = out_blocks + (size_t)w * 14 * 27;
+        linearize_interval_fins(P[n_params == 1 ? 0 : b], tb, inp, dt, npts, mode, blk);
+        if (out_lin_err) for (int k = 0; k < 14; ++k) out_lin_err[(size_t)w * 14 + k] = blk[k] - xb[14 + k];
+    }
+    return used;
 }
 
 // predict_state / simulate_zygote batched: endpoints 14 x (n_nodes-1) x B

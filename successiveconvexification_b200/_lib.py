@@ -34,15 +34,23 @@ SIGNATURES = {
     "scvx_linearize_batch": (ctypes.c_int, [_ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "scvx_linearize_batch_fins": (ctypes.c_int, [_ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_void_p, ctypes.c_void_p]),
+    "scvx_set_fin_table": (ctypes.c_int, [_ctx_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int]),
+    "scvx_fin_force_batch": (ctypes.c_int, [_ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_void_p]),
     "scvx_predict_batch": (ctypes.c_int, [_ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_void_p]),
+    "scvx_compact_record_doubles": (ctypes.c_int, [ctypes.c_int]),
     "scvx_linearize_batch_compact": (ctypes.c_int, [_ctx_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                     ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                                    ctypes.c_void_p, ctypes.c_void_p]),
+                                                    ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "scvx_compact_layout": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int32)]),
-    "scvx_expand_compact": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
-                                             ctypes.c_void_p, ctypes.c_int]),
+    "scvx_expand_compact": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "scvx_host_alloc": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint64]),
     "scvx_host_free": (ctypes.c_int, [ctypes.c_void_p]),
     "scvx_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64]),

@@ -45,3 +45,27 @@ def rescale_aerodata(data, Ul: float, Ut: float, Um: float):
     if isinstance(data, ExoatmosphericData):
         return data
     return AtmosphericData(data.drag_itrp, data.lift_itrp, data.trq_itrp, 1 / (Ul * Um / Ut ** 2), 1 / Ul)
+
+
+# aero/AeroTable.jl:94-112 — fin.csv: header `lift,drag,mach,aoa`; rows = 901 deflection angles (0:0.1:90 deg) x 60 Mach
+# numbers (0.01:0.025:1.485, fastest varying).  Read and dropped by the reference (aerodynamics.jl:23-26).
+FIN_N_MACH, FIN_N_DEFL = 60, 901
+FIN_MACH0, FIN_DMACH = 0.01, 0.025
+FIN_DEFL0, FIN_DDEFL = 0.0, 0.1
+
+
+def load_fin_table(finforce, n_mach: int = FIN_N_MACH, n_defl: int = FIN_N_DEFL):
+    """The fin-force table of `aero/fin.csv` as two (n_mach, n_defl) column-major arrays (lift, drag): the samples
+    `scvx_set_fin_table` stages (no consumer in the reference).  The axes are read from the file's own
+    `mach` / `aoa` columns."""
+    raw = np.loadtxt(os.fspath(finforce), delimiter=",", skiprows=1, dtype=np.float64)
+    with open(os.fspath(finforce)) as fh:
+        header = fh.readline().strip().split(",")
+    if raw.shape[0] != n_mach * n_defl:
+        raise ValueError(f"fin table must hold {n_mach}x{n_defl} rows, got {raw.shape[0]}")
+    col = {n: raw[:, header.index(n)] for n in ("lift", "drag", "mach", "aoa")}
+    mach = col["mach"].reshape((n_mach, n_defl), order="F")[:, 0]
+    defl = col["aoa"].reshape((n_mach, n_defl), order="F")[0, :]
+    axes = (float(mach[0]), float(mach[1] - mach[0]), float(defl[0]), float(defl[1] - defl[0]))
+    lift, drag = (np.asfortranarray(col[n].reshape((n_mach, n_defl), order="F")) for n in ("lift", "drag"))
+    return lift, drag, axes

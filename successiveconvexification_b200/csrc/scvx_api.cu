@@ -84,6 +84,9 @@ struct Dev {
     cudaEvent_t ev_scratch = nullptr;
     double* dense = nullptr;               // dense blocks behind a device-pointer compact call
     size_t dense_cap = 0;
+    double* fin[2] = { nullptr, nullptr }; // fin-force tables (lift, drag), SURVEY.md §8f-4
+    int fn1 = 0, fn2 = 0;
+    double fx0 = 0, fdx = 1, fy0 = 0, fdy = 1;
 };
 
 }  // namespace
@@ -97,6 +100,7 @@ struct scvx_ctx {
     bool timed = false;
     std::vector<scvx_probinfo> hP;
     bool any_aero = false;
+    bool hP_values = false;      // hP holds the records' values (set by scvx_set_params), not just their count / aero kind
 };
 
 namespace {
@@ -124,7 +128,7 @@ int dev_index_of(const scvx_ctx* c, const void* p);
 
 ScvxTables tables_of(const Dev& d) {
     ScvxTables t;
-    t.drag = d.coef[SCVX_TABLE_DRAG]; t.lift = d.coef[SCVX_TABLE_LIFT];
+    t.drag = d.coef[SCVX_TABLE_DRAG]; t.lift = d.coef[SCVX_TABLE_LIFT]; t.trq = d.coef[SCVX_TABLE_TORQUE];
     t.n1 = d.n1; t.n2 = d.n2; t.x0 = d.x0; t.inv_dx = 1.0 / d.dx; t.y0 = d.y0; t.inv_dy = 1.0 / d.dy;
     return t;
 }
@@ -173,7 +177,8 @@ int launch_linearize(scvx_ctx* c, Dev& d, const ScvxBatch& bt, cudaStream_t s) {
     // event recorded now on that stream would also wait for its D2H copy and serialise copy and compute
     if (d.scratch_user && d.scratch_user != s) CK(cudaStreamWaitEvent(s, d.ev_scratch, 0));
     int n = 0;
-    CK(scvx_launch_staged(bt, tb, c->any_aero, d.scratch, chunk, d.sm_count, s, &n));
+    const scvx_probinfo* shared = (bt.n_params == 1 && c->hP_values && c->hP.size() == 1) ? c->hP.data() : nullptr;
+    CK(scvx_launch_staged(bt, tb, c->any_aero, shared, d.scratch, chunk, d.sm_count, s, &n));
     c->launches += n;
     CK(cudaEventRecord(d.ev_scratch, s));
     d.scratch_user = s;
@@ -198,22 +203,22 @@ void drain(scvx_ctx* c) {
 
 int run_impl(scvx_ctx* c, bool predict, const double* X, const double* U, const double* sigma, double dt, int npts,
              int mode, int n_nodes, int B, double* out_blocks, double* out_lin_err, double* out_tlb, double* out_end,
-             double* out_compact);
+             double* out_compact, int rec);
 
 // Run one call. predict=false: linearize. Handles host pointers (chunked, all devices) and device pointers.
 // out_compact != nullptr: compact records instead of dense blocks (out_blocks / out_lin_err must be null then).
 int run(scvx_ctx* c, bool predict, const double* X, const double* U, const double* sigma, double dt, int npts,
         int mode, int n_nodes, int B, double* out_blocks, double* out_lin_err, double* out_tlb, double* out_end,
-        double* out_compact = nullptr) {
+        double* out_compact = nullptr, int rec = SCVX_COMPACT_DOUBLES) {
     const int rc = run_impl(c, predict, X, U, sigma, dt, npts, mode, n_nodes, B, out_blocks, out_lin_err, out_tlb, out_end,
-                            out_compact);
+                            out_compact, rec);
     if (rc != 0 && c) drain(c);
     return rc;
 }
 
 int run_impl(scvx_ctx* c, bool predict, const double* X, const double* U, const double* sigma, double dt, int npts,
              int mode, int n_nodes, int B, double* out_blocks, double* out_lin_err, double* out_tlb, double* out_end,
-             double* out_compact) {
+             double* out_compact, int rec) {
     if (!c) return fail(SCVX_ERR_ARG, "null context");
     if (!X || !U || !sigma) return fail(SCVX_ERR_ARG, "X, U and sigma must be non-null");
     double* const out_main = predict ? out_end : (out_compact ? out_compact : out_blocks);
@@ -257,7 +262,7 @@ int run_impl(scvx_ctx* c, bool predict, const double* X, const double* U, const 
         CK(cudaEventRecord(d.ev0, s));
         if (int rc = predict ? launch_predict(c, d, bt, s) : launch_linearize(c, d, bt, s)) return rc;
         if (out_compact) {
-            CK(scvx_launch_compact_pack(d.dense, (long)ni * B, out_compact, d.sm_count, s));
+            CK(scvx_launch_compact_pack(d.dense, (long)ni * B, rec, out_compact, d.sm_count, s));
             c->launches += 1;
         }
         CK(cudaEventRecord(d.ev1, s));
@@ -267,7 +272,7 @@ int run_impl(scvx_ctx* c, bool predict, const double* X, const double* U, const 
 
     // Host pointers: contiguous trajectory blocks per device, chunked + double-buffered inside a device.
     const int nd = (int)c->devs.size();
-    const size_t per_traj_out = predict ? (size_t)ni * 14 : (size_t)ni * (out_compact ? SCVX_COMPACT_DOUBLES : SCVX_BLOCK_DOUBLES);
+    const size_t per_traj_out = predict ? (size_t)ni * 14 : (size_t)ni * (out_compact ? rec : SCVX_BLOCK_DOUBLES);
     Range whole(predict ? "scvx:predict(host)" : (out_compact ? "scvx:linearize_compact(host)" : "scvx:linearize(host)"));
     static const long chunk_mb = getenv("SCVX_HOST_CHUNK_MB") ? atol(getenv("SCVX_HOST_CHUNK_MB")) : 256;
     long chunk = (long)(((size_t)chunk_mb << 20) / (per_traj_out * sizeof(double)));   // output per pipeline chunk (D2H saturates this pool's PCIe at ~43 GB/s from 128 MiB up, profiles/e2e_sweep.py)
@@ -312,11 +317,11 @@ int run_impl(scvx_ctx* c, bool predict, const double* X, const double* U, const 
                 if (out_tlb) { if (grow(&sl.dTlb, &sl.capTlb, (size_t)nb * n_nodes * 4)) return SCVX_ERR_NOMEM; bt.out_tlb = sl.dTlb; }
                 if (int rc = launch_linearize(c, d, bt, sl.stream)) return rc;
                 if (out_compact) {
-                    if (grow(&sl.dCmp, &sl.capCmp, (size_t)nb * ni * SCVX_COMPACT_DOUBLES)) return SCVX_ERR_NOMEM;
-                    CK(scvx_launch_compact_pack(sl.dOut, (long)nb * ni, sl.dCmp, d.sm_count, sl.stream));
+                    if (grow(&sl.dCmp, &sl.capCmp, (size_t)nb * ni * rec)) return SCVX_ERR_NOMEM;
+                    CK(scvx_launch_compact_pack(sl.dOut, (long)nb * ni, rec, sl.dCmp, d.sm_count, sl.stream));
                     c->launches += 1;
-                    CK(cudaMemcpyAsync(out_compact + (size_t)cb * ni * SCVX_COMPACT_DOUBLES, sl.dCmp,
-                                       (size_t)nb * ni * SCVX_COMPACT_DOUBLES * 8, cudaMemcpyDeviceToHost, sl.stream));
+                    CK(cudaMemcpyAsync(out_compact + (size_t)cb * ni * rec, sl.dCmp, (size_t)nb * ni * rec * 8,
+                                       cudaMemcpyDeviceToHost, sl.stream));
                 } else {
                     CK(cudaMemcpyAsync(out_blocks + (size_t)cb * ni * SCVX_BLOCK_DOUBLES, sl.dOut,
                                        (size_t)nb * ni * SCVX_BLOCK_DOUBLES * 8, cudaMemcpyDeviceToHost, sl.stream));
@@ -412,6 +417,7 @@ void scvx_destroy(scvx_ctx* c) {
         if (d.dP) cudaFree(d.dP);
         if (d.scratch) cudaFree(d.scratch);
         if (d.dense) cudaFree(d.dense);
+        for (int t = 0; t < 2; ++t) if (d.fin[t]) cudaFree(d.fin[t]);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.ev_scratch) cudaEventDestroy(d.ev_scratch);
@@ -425,6 +431,7 @@ int scvx_set_params(scvx_ctx* c, const scvx_probinfo* p, int n) {
         if (p[i].aero_kind != SCVX_AERO_EXO && p[i].aero_kind != SCVX_AERO_TABLE)
             return fail(SCVX_ERR_ARG, "record %d: unknown aero_kind %d", i, p[i].aero_kind);
     c->hP.assign(p, p + n);
+    c->hP_values = true;
     c->any_aero = false;
     for (int i = 0; i < n; ++i) if (p[i].aero_kind == SCVX_AERO_TABLE) c->any_aero = true;
     for (Dev& d : c->devs) {
@@ -442,40 +449,171 @@ int scvx_set_params(scvx_ctx* c, const scvx_probinfo* p, int n) {
     return 0;
 }
 
+// upload (and, unless prefiltered, prefilter on the device) one n1 x n2 table into *dst (freshly allocated)
+static int upload_table(scvx_ctx* c, Dev& d, double** dst, const double* samples, int n1, int n2, int prefiltered) {
+    const size_t ncoef = (size_t)(n1 + 2) * (n2 + 2);
+    const int nmax = std::max(n1, n2);
+    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    CK(cudaMalloc((void**)dst, ncoef * sizeof(double)));
+    cudaStream_t s = d.slot[0].stream;
+    if (prefiltered) {
+        CK(cudaMemcpyAsync(*dst, samples, ncoef * sizeof(double), cudaMemcpyHostToDevice, s));
+    } else {
+        std::vector<double> cp(nmax);
+        cp[0] = 0.25;
+        for (int m = 1; m < nmax; ++m) cp[m] = 1.0 / (4.0 - cp[m - 1]);
+        DevTmp ds, dt, dcp;                              // freed on every exit path
+        CK(ds.alloc((size_t)n1 * n2 * 8));
+        CK(dt.alloc((size_t)(n1 + 2) * n2 * 8));
+        CK(dcp.alloc((size_t)nmax * 8));
+        CK(cudaMemcpyAsync(ds.d(), samples, (size_t)n1 * n2 * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dcp.d(), cp.data(), (size_t)nmax * 8, cudaMemcpyHostToDevice, s));
+        CK(scvx_launch_prefilter(ds.d(), n1, n2, dt.d(), *dst, dcp.d(), s));
+        c->launches += 2;
+        CK(cudaStreamSynchronize(s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int scvx_set_fin_table(scvx_ctx* c, int which, const double* samples, int n_mach, int n_defl, double mach0, double dmach,
+                       double defl0, double ddefl, int prefiltered) {
+    if (!c || !samples) return fail(SCVX_ERR_ARG, "scvx_set_fin_table: null argument");
+    if (which < 0 || which > 1) return fail(SCVX_ERR_ARG, "unknown fin table id %d (0 lift, 1 drag)", which);
+    if (n_mach < 2 || n_defl < 2) return fail(SCVX_ERR_ARG, "table needs at least 2 samples per axis");
+    if (!(dmach > 0.0) || !(ddefl > 0.0)) return fail(SCVX_ERR_ARG, "axis steps must be positive");
+    for (Dev& d : c->devs) {
+        CK(cudaSetDevice(d.id));
+        if (d.fn1 && (d.fn1 != n_mach || d.fn2 != n_defl || d.fx0 != mach0 || d.fdx != dmach || d.fy0 != defl0 || d.fdy != ddefl)) {
+            const int o = 1 - which;
+            if (d.fin[o]) { cudaFree(d.fin[o]); d.fin[o] = nullptr; }       // a new geometry invalidates the other table
+        }
+        if (int rc = upload_table(c, d, &d.fin[which], samples, n_mach, n_defl, prefiltered)) return rc;
+        d.fn1 = n_mach; d.fn2 = n_defl; d.fx0 = mach0; d.fdx = dmach; d.fy0 = defl0; d.fdy = ddefl;
+    }
+    return 0;
+}
+
+int scvx_fin_force_batch(scvx_ctx* c, const double* mach, const double* deflection, int n, double* out_lift, double* out_drag) {
+    if (!c || !mach || !deflection) return fail(SCVX_ERR_ARG, "scvx_fin_force_batch: null argument");
+    if (!out_lift && !out_drag) return fail(SCVX_ERR_ARG, "no output requested");
+    if (n < 0) return fail(SCVX_ERR_ARG, "n=%d is negative", n);
+    if (n == 0) return 0;
+    const bool dev = is_device_ptr(mach);
+    if (dev != is_device_ptr(deflection) || (out_lift && dev != is_device_ptr(out_lift)) || (out_drag && dev != is_device_ptr(out_drag)))
+        return fail(SCVX_ERR_ARG, "all array arguments must be either host or device pointers, not a mix");
+    Dev* dp = &c->devs[0];
+    cudaStream_t s = dp->slot[0].stream;
+    if (dev) { if (int rc = device_call_target(c, mach, &dp, &s)) return rc; }
+    Dev& d = *dp;
+    CK(cudaSetDevice(d.id));
+    if ((out_lift && !d.fin[0]) || (out_drag && !d.fin[1])) return fail(SCVX_ERR_STATE, "fin table not uploaded (scvx_set_fin_table)");
+    ScvxTables lt, dt;
+    lt.drag = d.fin[0]; lt.lift = nullptr; lt.trq = nullptr; lt.n1 = d.fn1; lt.n2 = d.fn2;
+    lt.x0 = d.fx0; lt.inv_dx = 1.0 / d.fdx; lt.y0 = d.fy0; lt.inv_dy = 1.0 / d.fdy;
+    dt = lt; dt.drag = d.fin[1];
+    if (dev) {
+        CK(scvx_launch_fin_force(lt, dt, mach, deflection, n, out_lift, out_drag, s));
+        c->launches += 1;
+        return 0;
+    }
+    Slot& sl = d.slot[0];
+    CK(cudaStreamSynchronize(sl.stream));
+    if (grow(&sl.dS, &sl.capS, (size_t)4 * n)) return SCVX_ERR_NOMEM;
+    double *dm = sl.dS, *dd = sl.dS + n, *dl = sl.dS + 2 * (size_t)n, *dg = sl.dS + 3 * (size_t)n;
+    CK(cudaMemcpyAsync(dm, mach, (size_t)n * 8, cudaMemcpyHostToDevice, sl.stream));
+    CK(cudaMemcpyAsync(dd, deflection, (size_t)n * 8, cudaMemcpyHostToDevice, sl.stream));
+    CK(scvx_launch_fin_force(lt, dt, dm, dd, n, out_lift ? dl : nullptr, out_drag ? dg : nullptr, sl.stream));
+    c->launches += 1;
+    if (out_lift) CK(cudaMemcpyAsync(out_lift, dl, (size_t)n * 8, cudaMemcpyDeviceToHost, sl.stream));
+    if (out_drag) CK(cudaMemcpyAsync(out_drag, dg, (size_t)n * 8, cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaStreamSynchronize(sl.stream));
+    return 0;
+}
+
+// SURVEY.md §8f-4 variant on the generic forward-mode kernel (see the header)
+static int linearize_fins_impl(scvx_ctx* c, const double* X, const double* U5, const double* sigma, double dt, int npts, int mode,
+                               int n_nodes, int B, double* out_blocks, double* out_lin_err) {
+    if (!c) return fail(SCVX_ERR_ARG, "null context");
+    if (!X || !U5 || !sigma || !out_blocks) return fail(SCVX_ERR_ARG, "X, U5, sigma and out_blocks must be non-null");
+    if (n_nodes < 2) return fail(SCVX_ERR_ARG, "n_nodes=%d: at least two nodes (one interval) are required", n_nodes);
+    if (B < 0) return fail(SCVX_ERR_ARG, "B=%d is negative", B);
+    if (npts < 1) return fail(SCVX_ERR_ARG, "npts=%d must be >= 1", npts);
+    if (mode != SCVX_MODE_LITERAL && mode != SCVX_MODE_TEXTBOOK) return fail(SCVX_ERR_ARG, "unknown mode %d", mode);
+    if (!(dt > 0.0)) return fail(SCVX_ERR_ARG, "base_dt must be positive");
+    if (B == 0) return 0;
+    if ((long)(n_nodes - 1) * (long)B >= (1L << 31) - 64) return fail(SCVX_ERR_ARG, "too many intervals for one call");
+    if (int rc = check_ready(c, B)) return rc;
+    for (const auto& p : c->hP) if (p.aero_kind != SCVX_AERO_TABLE) return fail(SCVX_ERR_STATE, "the fins variant needs aero_kind = TABLE");
+    const int ni = n_nodes - 1, nP = (int)c->hP.size();
+    const bool dev = is_device_ptr(X);
+    if (dev != is_device_ptr(U5) || dev != is_device_ptr(sigma) || dev != is_device_ptr(out_blocks) ||
+        (out_lin_err && dev != is_device_ptr(out_lin_err)))
+        return fail(SCVX_ERR_ARG, "all array arguments must be either host or device pointers, not a mix");
+    Dev* dp = &c->devs[0];
+    cudaStream_t s = dp->slot[0].stream;
+    if (dev) { if (int rc = device_call_target(c, X, &dp, &s)) return rc; }
+    Dev& d = *dp;
+    CK(cudaSetDevice(d.id));
+    if (!d.coef[SCVX_TABLE_TORQUE]) return fail(SCVX_ERR_STATE, "the fins variant needs the torque table (scvx_set_aero_table, which = 2)");
+    ScvxBatch bt;
+    bt.P = d.dP; bt.n_params = nP; bt.n_nodes = n_nodes; bt.dt = dt; bt.npts = npts; bt.mode = mode;
+    bt.out_tlb = nullptr; bt.out_endpoints = nullptr;
+    if (dev) {
+        bt.X = X; bt.U = U5; bt.sigma = sigma; bt.B = B; bt.out_blocks = out_blocks; bt.out_lin_err = out_lin_err;
+        CK(scvx_launch_dualwarp_fins(bt, tables_of(d), s));
+        c->launches += 1;
+        return 0;
+    }
+    // host pointers: sequential trajectory chunks through the first pipeline slot (a feature variant, not the hot path)
+    Slot& sl = d.slot[0];
+    const size_t per_traj = (size_t)ni * 14 * 27;
+    const long chunk = std::max(1L, (long)(((size_t)256 << 20) / (per_traj * 8)));
+    for (long cb = 0; cb < B; cb += chunk) {
+        const int nb = (int)std::min(chunk, (long)B - cb);
+        CK(cudaStreamSynchronize(sl.stream));
+        if (grow(&sl.dX, &sl.capX, (size_t)nb * n_nodes * 14) || grow(&sl.dU, &sl.capU, (size_t)nb * n_nodes * 5) ||
+            grow(&sl.dS, &sl.capS, (size_t)nb) || grow(&sl.dOut, &sl.capOut, (size_t)nb * per_traj) ||
+            (out_lin_err && grow(&sl.dErr, &sl.capErr, (size_t)nb * ni * 14)))
+            return SCVX_ERR_NOMEM;
+        CK(cudaMemcpyAsync(sl.dX, X + (size_t)cb * n_nodes * 14, (size_t)nb * n_nodes * 14 * 8, cudaMemcpyHostToDevice, sl.stream));
+        CK(cudaMemcpyAsync(sl.dU, U5 + (size_t)cb * n_nodes * 5, (size_t)nb * n_nodes * 5 * 8, cudaMemcpyHostToDevice, sl.stream));
+        CK(cudaMemcpyAsync(sl.dS, sigma + cb, (size_t)nb * 8, cudaMemcpyHostToDevice, sl.stream));
+        bt.X = sl.dX; bt.U = sl.dU; bt.sigma = sl.dS; bt.B = nb; bt.out_blocks = sl.dOut; bt.out_lin_err = out_lin_err ? sl.dErr : nullptr;
+        bt.P = (nP == 1) ? d.dP : d.dP + cb; bt.n_params = (nP == 1) ? 1 : nb;
+        CK(scvx_launch_dualwarp_fins(bt, tables_of(d), sl.stream));
+        c->launches += 1;
+        CK(cudaMemcpyAsync(out_blocks + (size_t)cb * per_traj, sl.dOut, (size_t)nb * per_traj * 8, cudaMemcpyDeviceToHost, sl.stream));
+        if (out_lin_err)
+            CK(cudaMemcpyAsync(out_lin_err + (size_t)cb * ni * 14, sl.dErr, (size_t)nb * ni * 14 * 8, cudaMemcpyDeviceToHost, sl.stream));
+    }
+    CK(cudaStreamSynchronize(sl.stream));
+    return 0;
+}
+
+int scvx_linearize_batch_fins(scvx_ctx* c, const double* X, const double* U5, const double* sigma, double base_dt, int npts,
+                              int mode, int n_nodes, int B, double* out_blocks, double* out_lin_err) {
+    try {
+        const int rc = linearize_fins_impl(c, X, U5, sigma, base_dt, npts, mode, n_nodes, B, out_blocks, out_lin_err);
+        if (rc != 0 && c) drain(c);
+        return rc;
+    } catch (...) { return fail(SCVX_ERR_STATE, "unexpected C++ exception"); }
+}
+
 int scvx_set_aero_table(scvx_ctx* c, int which, const double* samples, int n_cos, int n_mach, double cos0,
                         double dcos, double mach0, double dmach, int prefiltered) {
     if (!c || !samples) return fail(SCVX_ERR_ARG, "scvx_set_aero_table: null argument");
     if (which < 0 || which > 2) return fail(SCVX_ERR_ARG, "unknown table id %d", which);
     if (n_cos < 2 || n_mach < 2) return fail(SCVX_ERR_ARG, "table needs at least 2 samples per axis");
     if (!(dcos > 0.0) || !(dmach > 0.0)) return fail(SCVX_ERR_ARG, "axis steps must be positive");
-    const size_t ncoef = (size_t)(n_cos + 2) * (n_mach + 2);
-    const int nmax = std::max(n_cos, n_mach);
-    std::vector<double> cp(nmax);
-    cp[0] = 0.25;
-    for (int m = 1; m < nmax; ++m) cp[m] = 1.0 / (4.0 - cp[m - 1]);
     for (Dev& d : c->devs) {
         CK(cudaSetDevice(d.id));
+        CK(cudaDeviceSynchronize());                   // nothing in flight may still read the table being replaced
         if (d.n1 && (d.n1 != n_cos || d.n2 != n_mach || d.x0 != cos0 || d.dx != dcos || d.y0 != mach0 || d.dy != dmach)) {
             // a new geometry invalidates tables uploaded with the old one
             for (int t = 0; t < 3; ++t) if (t != which && d.coef[t]) { cudaFree(d.coef[t]); d.coef[t] = nullptr; }
         }
-        if (d.coef[which]) { cudaFree(d.coef[which]); d.coef[which] = nullptr; }
-        CK(cudaMalloc((void**)&d.coef[which], ncoef * sizeof(double)));
-        cudaStream_t s = d.slot[0].stream;
-        if (prefiltered) {
-            CK(cudaMemcpyAsync(d.coef[which], samples, ncoef * sizeof(double), cudaMemcpyHostToDevice, s));
-        } else {
-            DevTmp ds, dt, dcp;                              // freed on every exit path
-            CK(ds.alloc((size_t)n_cos * n_mach * 8));
-            CK(dt.alloc((size_t)(n_cos + 2) * n_mach * 8));
-            CK(dcp.alloc((size_t)nmax * 8));
-            CK(cudaMemcpyAsync(ds.d(), samples, (size_t)n_cos * n_mach * 8, cudaMemcpyHostToDevice, s));
-            CK(cudaMemcpyAsync(dcp.d(), cp.data(), (size_t)nmax * 8, cudaMemcpyHostToDevice, s));
-            CK(scvx_launch_prefilter(ds.d(), n_cos, n_mach, dt.d(), d.coef[which], dcp.d(), s));
-            c->launches += 2;
-            CK(cudaStreamSynchronize(s));
-        }
-        CK(cudaStreamSynchronize(s));
+        if (int rc = upload_table(c, d, &d.coef[which], samples, n_cos, n_mach, prefiltered)) return rc;
         d.n1 = n_cos; d.n2 = n_mach; d.x0 = cos0; d.dx = dcos; d.y0 = mach0; d.dy = dmach;
     }
     return 0;
@@ -655,6 +793,7 @@ int scvx_dispersed_setup_batch(scvx_ctx* c, const scvx_dim_problem* base, const 
         memset(&tmpl, 0, sizeof(tmpl));
         tmpl.aero_kind = base->aero_kind;
         c->hP.assign((size_t)B, tmpl);
+        c->hP_values = false;
         c->any_aero = base->aero_kind == SCVX_AERO_TABLE;
     }
     return 0;
@@ -779,11 +918,19 @@ int scvx_last_kernel_ms(scvx_ctx* c, double* ms) {
     return 0;
 }
 
+int scvx_compact_record_doubles(int layout) {
+    if (layout == SCVX_COMPACT_FULL) return SCVX_COMPACT_DOUBLES;
+    if (layout == SCVX_COMPACT_NO_Z) return SCVX_COMPACT_NO_Z_DOUBLES;
+    return fail(SCVX_ERR_ARG, "unknown compact layout %d", layout);
+}
+
 int scvx_linearize_batch_compact(scvx_ctx* c, const double* X, const double* U, const double* sigma, double base_dt,
-                                 int npts, int mode, int n_nodes, int B, double* out_compact, double* out_tlb) {
+                                 int npts, int mode, int n_nodes, int B, int layout, double* out_compact, double* out_tlb) {
     try {
         if (!out_compact) return fail(SCVX_ERR_ARG, "out_compact is null");
-        return run(c, false, X, U, sigma, base_dt, npts, mode, n_nodes, B, nullptr, nullptr, out_tlb, nullptr, out_compact);
+        const int rec = scvx_compact_record_doubles(layout);
+        if (rec < 0) return rec;
+        return run(c, false, X, U, sigma, base_dt, npts, mode, n_nodes, B, nullptr, nullptr, out_tlb, nullptr, out_compact, rec);
     } catch (...) { return fail(SCVX_ERR_STATE, "unexpected C++ exception"); }
 }
 
@@ -795,15 +942,19 @@ int scvx_compact_layout(int32_t* index) {
     return n == SCVX_COMPACT_DATA ? 0 : fail(SCVX_ERR_STATE, "compact layout has %d entries", n);
 }
 
-int64_t scvx_expand_compact(const double* compact, const double* X, int n_nodes, int B, double* out_blocks,
-                            double* out_lin_err, int n_threads) {
+int64_t scvx_expand_compact(const double* compact, int layout, const double* X, const double* U, const double* sigma,
+                            int n_nodes, int B, double* out_blocks, double* out_lin_err, int n_threads) {
     if (!compact) return fail(SCVX_ERR_ARG, "compact is null");
     if (n_nodes < 2 || B < 0) return fail(SCVX_ERR_ARG, "bad n_nodes / B");
+    const int rec_n = scvx_compact_record_doubles(layout);
+    if (rec_n < 0) return rec_n;
+    const bool no_z = layout == SCVX_COMPACT_NO_Z;
     if (out_lin_err && !X) return fail(SCVX_ERR_ARG, "out_lin_err needs X");
+    if (no_z && out_blocks && (!X || !U || !sigma)) return fail(SCVX_ERR_ARG, "layout NO_Z needs X, U and sigma to re-form z");
     if (is_device_ptr(compact) || is_device_ptr(out_blocks) || is_device_ptr(out_lin_err))
         return fail(SCVX_ERR_ARG, "scvx_expand_compact works on host memory");
     try {
-        const int ni = n_nodes - 1;
+        const int ni = n_nodes - 1, n_data = rec_n - 1;
         const long total = (long)ni * B;
         // template block: the structural constants; the data entries are overwritten per interval
         double tmpl[SCVX_BLOCK_DOUBLES];
@@ -816,15 +967,29 @@ int64_t scvx_expand_compact(const double* compact, const double* X, int n_nodes,
         auto work = [&](long w0, long w1) {
             int64_t bad = 0;
             for (long w = w0; w < w1; ++w) {
-                const double* rec = compact + (size_t)w * SCVX_COMPACT_DOUBLES;
-                if (rec[SCVX_COMPACT_DATA] != 0.0) ++bad;
+                const double* rec = compact + (size_t)w * rec_n;
+                if (rec[n_data] != 0.0) ++bad;
+                const long b = w / ni, i = w - b * ni;
                 if (out_blocks) {
                     double* blk = out_blocks + (size_t)w * SCVX_BLOCK_DOUBLES;
                     memcpy(blk, tmpl, sizeof(tmpl));
-                    for (int k = 0; k < SCVX_COMPACT_DATA; ++k) blk[idx[k]] = rec[k];
+                    for (int k = 0; k < n_data; ++k) blk[idx[k]] = rec[k];
+                    if (no_z) {
+                        // z = endpoint - D * inp, inp = [x_i; u_i; u_{i+1}; sigma]   (old_dynamics.jl:139, 150-153)
+                        const double* x = X + ((size_t)b * n_nodes + i) * 14;
+                        const double* u = U + ((size_t)b * n_nodes + i) * 3;
+                        double inp[21];
+                        for (int k = 0; k < 14; ++k) inp[k] = x[k];
+                        for (int k = 0; k < 6; ++k) inp[14 + k] = u[k];
+                        inp[20] = sigma[b];
+                        for (int r = 0; r < 14; ++r) {
+                            double acc = blk[r];
+                            for (int cc = 0; cc < 21; ++cc) acc -= blk[14 * (1 + cc) + r] * inp[cc];
+                            blk[14 * 22 + r] = acc;
+                        }
+                    }
                 }
                 if (out_lin_err) {
-                    const long b = w / ni, i = w - b * ni;
                     const double* xn = X + ((size_t)b * n_nodes + i + 1) * 14;       // x_{n+1} (rocketland.jl:130, 256)
                     double* e = out_lin_err + (size_t)w * 14;
                     for (int r = 0; r < 14; ++r) e[r] = rec[r] - xn[r];

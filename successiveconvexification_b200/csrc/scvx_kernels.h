@@ -4,6 +4,9 @@
 #include "scvx_common.cuh"
 
 cudaError_t scvx_launch_dualwarp(const ScvxBatch& bt, const ScvxTables& tb, cudaStream_t s);
+cudaError_t scvx_launch_fin_force(const ScvxTables& lift_tb, const ScvxTables& drag_tb, const double* mach, const double* defl,
+                                  int n, double* out_lift, double* out_drag, cudaStream_t s);
+cudaError_t scvx_launch_dualwarp_fins(const ScvxBatch& bt, const ScvxTables& tb, cudaStream_t s);
 cudaError_t scvx_launch_predict(const ScvxBatch& bt, const ScvxTables& tb, cudaStream_t s);
 cudaError_t scvx_launch_prefilter(const double* d_samples, int n1, int n2, double* d_tmp, double* d_coef,
                                   const double* d_cp, cudaStream_t s);
@@ -17,12 +20,14 @@ cudaError_t scvx_launch_socp_values(const double* blocks, const double* lin_err,
 cudaError_t scvx_launch_dispersed_setup(const scvx_dim_problem& base, const double* rIi, const double* vIi, const double* mwet,
                                         int B, double* X, double* U, double* sigma, double* scales, scvx_probinfo* P0,
                                         scvx_probinfo* P1, cudaStream_t s);
-cudaError_t scvx_launch_compact_pack(const double* blocks, long n_intervals, double* out, int sm_count, cudaStream_t s);
+cudaError_t scvx_launch_compact_pack(const double* blocks, long n_intervals, int record_doubles, double* out, int sm_count,
+                                     cudaStream_t s);
 
 // STAGED path (scvx_kernels_staged.cu): value kernel + persistent tangent kernel, chunked over a scratch buffer.
 cudaError_t scvx_staged_init();          // kernel attributes of the current device (once per context and device)
 size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals);
 int scvx_staged_chunk_intervals(int sm_count);
-cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, void* scratch,
-                               int chunk_intervals, int sm_count, cudaStream_t s, int* launches);
+// shared_params != nullptr: every trajectory uses this one record; it travels in the kernel arguments (constant bank)
+cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, const scvx_probinfo* shared_params,
+                               void* scratch, int chunk_intervals, int sm_count, cudaStream_t s, int* launches);
 

@@ -70,6 +70,48 @@ linearize_dualwarp_kernel(ScvxBatch bt, ScvxTables tb) {
     }
 }
 
+// SURVEY.md §8f-4 variant (fin forces + aero torque): control_dim = 5, inp = [x(14); u_k(5); u_{k+1}(5); sigma] (25),
+// lane L < 25 carries d/d inp[L]; block 14 x 27 = [endpoint | D (25) | z].  bt.U is 5 x n_nodes x B here.
+__global__ void __launch_bounds__(128)
+linearize_dualwarp_fins_kernel(ScvxBatch bt, ScvxTables tb) {
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int ni = bt.n_nodes - 1;
+    const long total = (long)ni * bt.B;
+    if (warp >= total) return;
+    const int b = (int)(warp / ni), i = (int)(warp % ni);
+    const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
+    const double* xin = bt.X + ((size_t)b * bt.n_nodes + i) * 14;
+    const double* uin = bt.U + ((size_t)b * bt.n_nodes + i) * 5;
+    D1 st[14], um[5], up[5];
+#pragma unroll
+    for (int r = 0; r < 14; ++r) st[r] = D1(xin[r], lane == r ? 1.0 : 0.0);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        um[c] = D1(uin[c], lane == 14 + c ? 1.0 : 0.0);
+        up[c] = D1(uin[5 + c], lane == 19 + c ? 1.0 : 0.0);
+    }
+    const D1 sg(bt.sigma[b], lane == 24 ? 1.0 : 0.0);
+    double my_inp = 0.0;
+    if (lane < 14) my_inp = xin[lane];
+    else if (lane < 24) my_inp = uin[lane - 14];
+    else if (lane == 24) my_inp = bt.sigma[b];
+    rk4_fins_t<D1>(P, tb, st, um, up, sg, bt.dt, bt.npts, bt.mode);
+    double* blk = bt.out_blocks + (size_t)warp * (14 * 27);
+#pragma unroll
+    for (int r = 0; r < 14; ++r) {
+        if (lane < 25) blk[14 * (1 + lane) + r] = st[r].d;
+        double t = st[r].d * my_inp;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) {
+            blk[r] = st[r].v;
+            blk[14 * 26 + r] = st[r].v - t;
+            if (bt.out_lin_err) bt.out_lin_err[(size_t)warp * 14 + r] = st[r].v - xin[14 + r];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 predict_kernel(ScvxBatch bt, ScvxTables tb) {
     const long w = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -205,6 +247,31 @@ cudaError_t scvx_launch_dualwarp(const ScvxBatch& bt, const ScvxTables& tb, cuda
     if (total <= 0) return cudaSuccess;
     const long blocks = (total + 3) / 4;
     linearize_dualwarp_kernel<<<(unsigned)blocks, 128, 0, s>>>(bt, tb);
+    return cudaGetLastError();
+}
+
+// fin-force table lookup: both splines at n (mach, deflection) pairs
+__global__ void __launch_bounds__(128) fin_force_kernel(ScvxTables lift_tb, ScvxTables drag_tb, const double* __restrict__ mach,
+                                                        const double* __restrict__ defl, int n, double* __restrict__ out_lift,
+                                                        double* __restrict__ out_drag) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double m = mach[t], d = defl[t];
+    if (out_lift) out_lift[t] = spline_eval<double>(lift_tb.drag, lift_tb, m, d);
+    if (out_drag) out_drag[t] = spline_eval<double>(drag_tb.drag, drag_tb, m, d);
+}
+
+cudaError_t scvx_launch_fin_force(const ScvxTables& lift_tb, const ScvxTables& drag_tb, const double* mach, const double* defl,
+                                  int n, double* out_lift, double* out_drag, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    fin_force_kernel<<<(n + 127) / 128, 128, 0, s>>>(lift_tb, drag_tb, mach, defl, n, out_lift, out_drag);
+    return cudaGetLastError();
+}
+
+cudaError_t scvx_launch_dualwarp_fins(const ScvxBatch& bt, const ScvxTables& tb, cudaStream_t s) {
+    const long total = (long)(bt.n_nodes - 1) * bt.B;
+    if (total <= 0) return cudaSuccess;
+    linearize_dualwarp_fins_kernel<<<(unsigned)((total + 3) / 4), 128, 0, s>>>(bt, tb);
     return cudaGetLastError();
 }
 

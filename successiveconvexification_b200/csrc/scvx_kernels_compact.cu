@@ -10,7 +10,8 @@
 
 namespace {
 
-__global__ void __launch_bounds__(256) compact_pack_kernel(const double* __restrict__ blocks, long n_int,
+// n_data = 229 (all data entries) or 215 (without the z column, which is the last run of slots); record = n_data + 1.
+__global__ void __launch_bounds__(256) compact_pack_kernel(const double* __restrict__ blocks, long n_int, int n_data,
                                                            double* __restrict__ out) {
     __shared__ short src[SCVX_COMPACT_DATA + 3];
     if (threadIdx.x < 23) {                      // one thread per block column fills its run of slots
@@ -25,12 +26,12 @@ __global__ void __launch_bounds__(256) compact_pack_kernel(const double* __restr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (long itv = (long)blockIdx.x * 8 + warp; itv < n_int; itv += (long)gridDim.x * 8) {
         const double* blk = blocks + itv * SCVX_BLOCK_DOUBLES;
-        double* rec = out + itv * SCVX_COMPACT_DOUBLES;
+        double* rec = out + itv * (n_data + 1);
         bool bad = false;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int slot = lane + 32 * k;
-            if (slot < SCVX_COMPACT_DATA) {
+            if (slot < n_data) {
                 const double v = __ldg(blk + src[slot]);
                 bad |= !isfinite(v);
                 rec[slot] = v;
@@ -40,17 +41,18 @@ __global__ void __launch_bounds__(256) compact_pack_kernel(const double* __restr
         // but the flag is cheap to make exact: scan the 93 non-data entries as well (same sectors, already in L1)
         for (int o = lane; o < SCVX_BLOCK_DOUBLES; o += 32) bad |= !isfinite(__ldg(blk + o));
         bad = __any_sync(0xffffffffu, bad);
-        if (lane == 0) rec[SCVX_COMPACT_DATA] = bad ? 1.0 : 0.0;
+        if (lane == 0) rec[n_data] = bad ? 1.0 : 0.0;
     }
 }
 
 }  // namespace
 
-cudaError_t scvx_launch_compact_pack(const double* blocks, long n_intervals, double* out, int sm_count, cudaStream_t s) {
+cudaError_t scvx_launch_compact_pack(const double* blocks, long n_intervals, int record_doubles, double* out, int sm_count,
+                                     cudaStream_t s) {
     if (n_intervals <= 0) return cudaSuccess;
     long grid = (n_intervals + 7) / 8;
     const long cap = (long)sm_count * 8;         // 8 resident blocks of 256 threads per SM
     if (grid > cap) grid = cap;
-    compact_pack_kernel<<<(unsigned)grid, 256, 0, s>>>(blocks, n_intervals, out);
+    compact_pack_kernel<<<(unsigned)grid, 256, 0, s>>>(blocks, n_intervals, record_doubles - 1, out);
     return cudaGetLastError();
 }

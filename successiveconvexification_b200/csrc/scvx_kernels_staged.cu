@@ -41,10 +41,35 @@ namespace {
 // SCVX_A_PARK: the step-start state x and the rk4 accumulator (28 doubles) also live in lane-private shared memory, so
 // that the kernel fits 168 registers and a third block per SM (3 warps per scheduler hide the dependent-issue latency of
 // the serial value chain better than 2).
+#ifndef SCVX_A_SMEM_TABLES
+#define SCVX_A_SMEM_TABLES 0
+#endif
+// SCVX_A_SMEM_TABLES (the A/B BASELINE.json's north_star asks for: "the aero tables are staged into shared memory"):
+//   0  spline coefficients read through the read-only path (ld.global.nc), L1 resident — the default;
+//   1  drag table (92 KB) staged in shared memory by every block; one block of 256 threads per SM;
+//   2  drag + lift tables (184 KB) staged; one block of 224 threads per SM (what fits beside the light-column state).
+// Result (profiles/r2_smem_tables_*.txt): see there.
+constexpr int VT = SCVX_A_SMEM_TABLES == 0 ? 128 : (SCVX_A_SMEM_TABLES == 1 ? 256 : 224);     // threads per block
+constexpr int VALUE_MINBLOCKS = SCVX_A_SMEM_TABLES ? 1 : SCVX_A_MINBLOCKS;
 constexpr int VALUE_SMEM_DOUBLES = 24 + (SCVX_A_PARK ? 28 : 0);
-constexpr size_t LIGHT_SMEM_BYTES = VALUE_SMEM_DOUBLES * 128 * sizeof(double);
-__global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(StagedArgs a) {
-    extern __shared__ double light_smem[];            // [24][128] doubles
+constexpr size_t LIGHT_SMEM_BYTES = VALUE_SMEM_DOUBLES * VT * sizeof(double);
+template <bool SP>
+__global__ void __launch_bounds__(VT, VALUE_MINBLOCKS) stage_value_kernel(const __grid_constant__ StagedArgs a) {
+    extern __shared__ double light_smem[];            // [24][VT] doubles (+ the staged tables)
+    ScvxTables tbl = a.tb;
+#if SCVX_A_SMEM_TABLES
+    {
+        const int ncoef = (a.tb.n1 + 2) * (a.tb.n2 + 2);
+        double* sd = light_smem + VALUE_SMEM_DOUBLES * VT;
+        for (int k = threadIdx.x; k < ncoef; k += VT) sd[k] = __ldg(a.tb.drag + k);
+        tbl.drag = sd;
+#if SCVX_A_SMEM_TABLES == 2
+        for (int k = threadIdx.x; k < ncoef; k += VT) sd[ncoef + k] = __ldg(a.tb.lift + k);
+        tbl.lift = sd + ncoef;
+#endif
+        __syncthreads();
+    }
+#endif
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n_groups * GROUP) return;
     const ScvxBatch& bt = a.bt;
@@ -52,7 +77,7 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
     const bool live = t < a.count;
     const int w = a.first + (live ? t : a.count - 1);          // padded lanes recompute the last interval
     const int b = (int)(w / ni), i = (int)(w % ni);
-    const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
+    const scvx_probinfo& P = SP ? a.Pc : bt.P[bt.n_params == 1 ? 0 : b];
     const double* xin = bt.X + ((size_t)b * bt.n_nodes + i) * 14;
     const double* uin = bt.U + ((size_t)b * bt.n_nodes + i) * 3;
     const double sigma = bt.sigma[b];
@@ -75,22 +100,22 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const double s0 = (c + 1 == r) ? 1.0 : 0.0;
-                L[(c * 12 + 0 + r) * 128] = s0; L[(c * 12 + 3 + r) * 128] = 0.0;
-                L[(c * 12 + 6 + r) * 128] = s0; L[(c * 12 + 9 + r) * 128] = 0.0;
+                L[(c * 12 + 0 + r) * VT] = s0; L[(c * 12 + 3 + r) * VT] = 0.0;
+                L[(c * 12 + 6 + r) * VT] = s0; L[(c * 12 + 9 + r) * VT] = 0.0;
             }
     }
     double pca = 0.0;
 #if SCVX_A_PARK
-    double* PX = L + 24 * 128;            // step-start state [14][128]
-    double* PA = L + 38 * 128;            // rk4 accumulator  [14][128]
+    double* PX = L + 24 * VT;            // step-start state [14][128]
+    double* PA = L + 38 * VT;            // rk4 accumulator  [14][128]
 #pragma unroll
-    for (int r = 0; r < 14; ++r) PX[r * 128] = x[r];
+    for (int r = 0; r < 14; ++r) PX[r * VT] = x[r];
 #endif
     for (int it = 0; it < bt.npts; ++it) {
         double y[14];
 #if SCVX_A_PARK
 #pragma unroll
-        for (int r = 0; r < 14; ++r) { y[r] = PX[r * 128]; PA[r * 128] = 0.0; }
+        for (int r = 0; r < 14; ++r) { y[r] = PX[r * VT]; PA[r * VT] = 0.0; }
 #else
         double acc[14];
 #pragma unroll
@@ -102,7 +127,7 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
             double uc[3], f[14], Fv[3][3], Fb[3][3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) uc[c] = (1.0 - pc) * um[c] + pc * up[c];
-            rhs_value<true>(P, a.tb, y, uc, f, Fv, Fb);
+            rhs_value<true, SCVX_A_SMEM_TABLES, SP>(P, tbl, y, uc, f, Fv, Fb);
             // record: m, v, q, w, u, f_m, f_v, f_q, f_w [, dF/dv, dF/db]
             double* rp = rec + (size_t)(it * 4 + st) * ((size_t)a.rec_n * GROUP);
             if (a.rec_n == REC_AERO) {
@@ -134,19 +159,19 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
                     for (int c = 0; c < 3; ++c) Jvv[r][c] = smv * Fv[r][c];
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    double* Lc = L + c * 12 * 128;
-                    const double y0 = Lc[6 * 128], y1 = Lc[7 * 128], y2 = Lc[8 * 128];
+                    double* Lc = L + c * 12 * VT;
+                    const double y0 = Lc[6 * VT], y1 = Lc[7 * VT], y2 = Lc[8 * VT];
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
                         const double yr = (r == 0) ? y0 : (r == 1 ? y1 : y2);
-                        Lc[(9 + r) * 128] = fma(csg, yr, Lc[(9 + r) * 128]);
+                        Lc[(9 + r) * VT] = fma(csg, yr, Lc[(9 + r) * VT]);
                         const double K = fma(Jvv[r][0], y0, fma(Jvv[r][1], y1, Jvv[r][2] * y2));
                         if (st != 3) {
-                            Lc[(3 + r) * 128] = fma(wgt, K, Lc[(3 + r) * 128]);
-                            Lc[(6 + r) * 128] = fma(cy, K, Lc[r * 128]);
+                            Lc[(3 + r) * VT] = fma(wgt, K, Lc[(3 + r) * VT]);
+                            Lc[(6 + r) * VT] = fma(cy, K, Lc[r * VT]);
                         } else {
-                            const double sn = fma(h * (1.0 / 6.0), Lc[(3 + r) * 128] + K, Lc[r * 128]);
-                            Lc[r * 128] = sn; Lc[(6 + r) * 128] = sn; Lc[(3 + r) * 128] = 0.0;
+                            const double sn = fma(h * (1.0 / 6.0), Lc[(3 + r) * VT] + K, Lc[r * VT]);
+                            Lc[r * VT] = sn; Lc[(6 + r) * VT] = sn; Lc[(3 + r) * VT] = 0.0;
                         }
                     }
                 }
@@ -155,8 +180,8 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
 #pragma unroll
             for (int r = 0; r < 14; ++r) {
                 const double k = f[r] * sigma;
-                PA[r * 128] = fma(wgt, k, PA[r * 128]);
-                y[r] = fma(cy, k, PX[r * 128]);
+                PA[r * VT] = fma(wgt, k, PA[r * VT]);
+                y[r] = fma(cy, k, PX[r * VT]);
             }
 #else
 #pragma unroll
@@ -170,7 +195,7 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
         pca += pcs;
 #if SCVX_A_PARK
 #pragma unroll
-        for (int r = 0; r < 14; ++r) PX[r * 128] = fma(h * (1.0 / 6.0), PA[r * 128], PX[r * 128]);
+        for (int r = 0; r < 14; ++r) PX[r * VT] = fma(h * (1.0 / 6.0), PA[r * VT], PX[r * VT]);
 #else
 #pragma unroll
         for (int r = 0; r < 14; ++r) x[r] = fma(h * (1.0 / 6.0), acc[r], x[r]);
@@ -178,7 +203,7 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
     }
 #if SCVX_A_PARK
 #pragma unroll
-    for (int r = 0; r < 14; ++r) x[r] = PX[r * 128];
+    for (int r = 0; r < 14; ++r) x[r] = PX[r * VT];
 #endif
     if (!live) return;
     double* blk = bt.out_blocks + (size_t)w * SCVX_BLOCK_DOUBLES;
@@ -197,11 +222,11 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
 #pragma unroll
             for (int r = 0; r < 14; ++r) col[r] = 0.0;
             if (c >= 5) {
-                const double* Lc = L + (c - 5) * 12 * 128;
+                const double* Lc = L + (c - 5) * 12 * VT;
                 const double xc = xin[c];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    col[1 + r] = Lc[(9 + r) * 128]; col[4 + r] = Lc[r * 128];
+                    col[1 + r] = Lc[(9 + r) * VT]; col[4 + r] = Lc[r * VT];
                     z[1 + r] = fma(-col[1 + r], xc, z[1 + r]); z[4 + r] = fma(-col[4 + r], xc, z[4 + r]);
                 }
             } else {
@@ -230,7 +255,7 @@ __global__ void __launch_bounds__(128, SCVX_A_MINBLOCKS) stage_value_kernel(Stag
             const double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
             double* o = bt.out_tlb + ((size_t)b * bt.n_nodes + i + k) * 4;
             *reinterpret_cast<double2*>(o) = make_double2(-(u[0] / nu), -(u[1] / nu));
-            *reinterpret_cast<double2*>(o + 2) = make_double2(-(u[2] / nu), __ldg(&P.Tmin) - nu);
+            *reinterpret_cast<double2*>(o + 2) = make_double2(-(u[2] / nu), ldp<SP>(&P.Tmin) - nu);
         }
     }
 }
@@ -266,7 +291,8 @@ struct __align__(16) StepSmem {
     uint64_t recfull[2][4];                  // [half][stage]: one waiting warp per barrier (it observes every phase)
 };
 
-__global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(StagedArgs a) {
+template <bool SP>
+__global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __grid_constant__ StagedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StepSmem& sm = *reinterpret_cast<StepSmem*>(smem_raw);
     const ScvxBatch& bt = a.bt;
@@ -323,12 +349,12 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(StagedArgs 
         const int g = blockIdx.x + it * gridDim.x;
         int t = g * GROUP + lane; if (t >= a.count) t = a.count - 1;
         const int b = (a.first + t) / ni;
-        const scvx_probinfo& P = bt.P[bt.n_params == 1 ? 0 : b];
+        const scvx_probinfo& P = SP ? a.Pc : bt.P[bt.n_params == 1 ? 0 : b];
         const double sigma = __ldg(bt.sigma + b);
         const int half = n & 1, use = n >> 1;
         mbar_wait(&sm.recfull[half][kq], (uint32_t)(use & 1));      // this warp is the only waiter of recfull[half][kq]
         if (use > 0) mbar_wait(&sm.empty_step[half], (uint32_t)((use - 1) & 1));
-        produce_lean(P, a.rec_n == REC_AERO, sigma, stage_scale, sm.recbuf[kq] + lane, &sm.ring[half * 4 + kq][lane][0]);
+        produce_lean<SP>(P, a.rec_n == REC_AERO, sigma, stage_scale, sm.recbuf[kq] + lane, &sm.ring[half * 4 + kq][lane][0]);
         mbar_arrive(&sm.full_step[half]);
         __syncwarp();                                    // every lane has finished reading recbuf[kq]
         if (lane == 0 && n + 1 < total_steps) issue_record(n + 1);
@@ -438,28 +464,42 @@ size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals) {
 
 // chunk = whole waves of both kernels: the value kernel keeps 2 x 128 threads per SM resident (255 registers), the
 // tangent kernel 32 intervals per pass: 768 intervals per SM = 3 waves / 24 passes.
-int scvx_staged_chunk_intervals(int sm_count) { return sm_count * 768; }
+int scvx_staged_chunk_intervals(int sm_count) { return sm_count * (SCVX_A_SMEM_TABLES == 2 ? 896 : 768); }
 
 cudaError_t scvx_staged_init() {
-    cudaError_t e = cudaFuncSetAttribute(stage_value_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIGHT_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(tangent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
+    const int vs = SCVX_A_SMEM_TABLES ? 232448 : (int)LIGHT_SMEM_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(stage_value_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, vs);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stage_value_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vs);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tangent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tangent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
+    return e;
 }
 
-cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, void* scratch,
-                               int chunk_intervals, int sm_count, cudaStream_t s, int* launches) {
+cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, const scvx_probinfo* shared_params,
+                               void* scratch, int chunk_intervals, int sm_count, cudaStream_t s, int* launches) {
     const long total = (long)(bt.n_nodes - 1) * bt.B;
     const size_t smem = sizeof(StepSmem);
     for (long first = 0; first < total; first += chunk_intervals) {
         StagedArgs a;
         a.bt = bt; a.tb = tb; a.rec = (double*)scratch; a.first = (int)first;
+        if (shared_params) a.Pc = *shared_params;
         a.rec_n = any_aero ? REC_AERO : REC_EXO;
         a.count = (int)((total - first < chunk_intervals) ? (total - first) : chunk_intervals);
         a.n_groups = (a.count + GROUP - 1) / GROUP;
         const int threads = a.n_groups * GROUP;
-        stage_value_kernel<<<(threads + 127) / 128, 128, LIGHT_SMEM_BYTES, s>>>(a);
+        size_t vsmem = LIGHT_SMEM_BYTES;
+        if (SCVX_A_SMEM_TABLES) {
+            vsmem += (size_t)SCVX_A_SMEM_TABLES * (tb.n1 + 2) * (tb.n2 + 2) * sizeof(double);
+            if (vsmem > 232448 || !tb.drag || !tb.lift) return cudaErrorInvalidConfiguration;     // A/B build: tables must fit
+        }
         const int grid = a.n_groups < sm_count ? a.n_groups : sm_count;
-        tangent_kernel<<<grid, TANGENT_THREADS, smem, s>>>(a);
+        if (shared_params) {
+            stage_value_kernel<true><<<(threads + VT - 1) / VT, VT, vsmem, s>>>(a);
+            tangent_kernel<true><<<grid, TANGENT_THREADS, smem, s>>>(a);
+        } else {
+            stage_value_kernel<false><<<(threads + VT - 1) / VT, VT, vsmem, s>>>(a);
+            tangent_kernel<false><<<grid, TANGENT_THREADS, smem, s>>>(a);
+        }
         if (launches) *launches += 2;
     }
     return cudaGetLastError();

@@ -27,6 +27,8 @@ constexpr int J_SIG = 75;        // 1  sigma (unscaled: the r-row quadrature use
 struct StagedArgs {
     ScvxBatch bt;
     ScvxTables tb;
+    scvx_probinfo Pc;            // the parameter record itself when all trajectories share one (kernel-argument space:
+                                 // its fields become constant-bank operands, no loads; kernels instantiated with SP = true)
     double* rec;                 // stage records of this chunk
     int rec_n;                   // entries per stage record (REC_EXO or REC_AERO)
     int first;                   // first interval (global index) of this chunk (total intervals < 2^31)
@@ -34,11 +36,23 @@ struct StagedArgs {
     int n_groups;                // ceil(count / 32)
 };
 
+// Parameter access.  SP = the record is shared by every trajectory and sits in the kernel arguments (constant bank):
+// plain reads, which the compiler folds into instruction operands.  Otherwise one record per trajectory in global
+// memory, read through the read-only path.
+template <bool SP> __device__ __forceinline__ double ldp(const double* p) {
+    if constexpr (SP) return *p; else return __ldg(p);
+}
+template <bool SP> __device__ __forceinline__ int ldpi(const int32_t* p) {
+    if constexpr (SP) return *p; else return __ldg(p);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Kernel A: value trajectory + stage records.
 // ------------------------------------------------------------------------------------------------
 // spline value and gradient w.r.t. the physical coordinates (gradient 0 when strictly outside: Flat extrapolation);
 // one pass over the 16 coefficients serves all three.
+// SMEM: the coefficient array lives in shared memory (plain loads) instead of global memory (read-only path).
+template <bool SMEM = false>
 __device__ __forceinline__ void spline_val_grad(const double* __restrict__ coef, const ScvxTables& t, double x, double y,
                                                 double& val, double& gx, double& gy) {
     const int L1 = t.n1 + 2;
@@ -60,7 +74,9 @@ __device__ __forceinline__ void spline_val_grad(const double* __restrict__ coef,
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
         const double* p = base + (size_t)b * L1;
-        const double c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2), c3 = __ldg(p + 3);
+        double c0, c1, c2, c3;
+        if constexpr (SMEM) { c0 = p[0]; c1 = p[1]; c2 = p[2]; c3 = p[3]; }
+        else { c0 = __ldg(p); c1 = __ldg(p + 1); c2 = __ldg(p + 2); c3 = __ldg(p + 3); }
         const double rv = wx[0] * c0 + wx[1] * c1 + wx[2] * c2 + wx[3] * c3;
         const double rg = gxw[0] * c0 + gxw[1] * c1 + gxw[2] * c2 + gxw[3] * c3;
         av = fma(wy[b], rv, av);
@@ -72,6 +88,8 @@ __device__ __forceinline__ void spline_val_grad(const double* __restrict__ coef,
 
 // Jacobian of the aerodynamic force F(b, v) (aerodynamics.jl:38-58) w.r.t. v and b = C(q) e1: exact derivative
 // of the executed branch (|dp| >= 0.95 drag only; clamp active only strictly outside [-1,1]).
+// TS = number of tables staged in shared memory: 0 none, 1 drag, 2 drag + lift (tb.drag / tb.lift then point there).
+template <int TS = 0, bool SP = false>
 __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const ScvxTables& tb, const double b[3],
                                                const double v[3], double F[3], double Fv[3][3], double Fb[3][3]) {
     const double vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
@@ -84,7 +102,7 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
     const double car = dp * inb;
     double ca = car, mc = 1.0;
     if (car > 1.0) { ca = 1.0; mc = 0.0; } else if (car < -1.0) { ca = -1.0; mc = 0.0; }
-    const double isos = 1.0 / __ldg(&P.sos);
+    const double isos = 1.0 / ldp<SP>(&P.sos);
     const double mach = nv * isos;
     // d(ca)/dv, d(ca)/db ; d(mach)/dv
     double cav[3], cab[3], mv[3];
@@ -94,9 +112,9 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
         cab[k] = mc * (vh[k] - car * b[k] * inb) * inb;
         mv[k] = vh[k] * isos;
     }
-    const double fs = __ldg(&P.force_scalar);
+    const double fs = ldp<SP>(&P.force_scalar);
     double drag, gx, gy;
-    spline_val_grad(tb.drag, tb, ca, mach, drag, gx, gy);
+    spline_val_grad<(TS >= 1)>(tb.drag, tb, ca, mach, drag, gx, gy);
     drag *= fs; gx *= fs; gy *= fs;
     double dv[3], db[3];
 #pragma unroll
@@ -113,7 +131,7 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
     }
     if (fabs(dp) >= 0.95) return;
     double lift;
-    spline_val_grad(tb.lift, tb, ca, mach, lift, gx, gy);
+    spline_val_grad<(TS >= 2)>(tb.lift, tb, ca, mach, lift, gx, gy);
     lift *= fs; gx *= fs; gy *= fs;
     double lv[3], lb[3];
 #pragma unroll
@@ -149,7 +167,7 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
 
 // unscaled f(x,u) (dx_static without the `.* mult`, dynamics.jl:54-77) together with the Jacobians of the
 // aerodynamic force w.r.t. v and b = C(q) e1 (zero for the exo-atmospheric variant).
-template <bool JAC>
+template <bool JAC, int TS = 0, bool SP = false>
 __device__ __forceinline__ void rhs_value(const scvx_probinfo& P, const ScvxTables& tb, const double x[14],
                                           const double u[3], double f[14], double Fv[3][3], double Fb[3][3]) {
     const double q0 = x[7], q1 = x[8], q2 = x[9], q3 = x[10];
@@ -159,9 +177,9 @@ __device__ __forceinline__ void rhs_value(const scvx_probinfo& P, const ScvxTabl
     const double c10 = 2.0 * (p1 + p2), c11 = 1.0 - 2.0 * (q1 * q1 + q3 * q3), c12 = 2.0 * (p5 - p6);
     const double c20 = 2.0 * (p3 - p4), c21 = 2.0 * (p5 + p6), c22 = 1.0 - 2.0 * (q1 * q1 + q2 * q2);
     double F[3] = { 0.0, 0.0, 0.0 };
-    if (__ldg(&P.aero_kind) == SCVX_AERO_TABLE) {
+    if (ldpi<SP>(&P.aero_kind) == SCVX_AERO_TABLE) {
         const double bv[3] = { c00, c10, c20 };
-        if constexpr (JAC) aero_force_jac(P, tb, bv, x + 4, F, Fv, Fb);
+        if constexpr (JAC) aero_force_jac<TS, SP>(P, tb, bv, x + 4, F, Fv, Fb);
         else aero_force_t<double>(P, tb, bv, x + 4, F);
     } else if constexpr (JAC) {
 #pragma unroll
@@ -170,24 +188,24 @@ __device__ __forceinline__ void rhs_value(const scvx_probinfo& P, const ScvxTabl
             for (int c = 0; c < 3; ++c) { Fv[r][c] = 0.0; Fb[r][c] = 0.0; }
     }
     const double im = 1.0 / x[0];
-    f[0] = -__ldg(&P.a) * sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    f[0] = -ldp<SP>(&P.a) * sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
     f[1] = x[4]; f[2] = x[5]; f[3] = x[6];
-    f[4] = (c00 * u[0] + c01 * u[1] + c02 * u[2] + F[0]) * im - __ldg(&P.g0);
+    f[4] = (c00 * u[0] + c01 * u[1] + c02 * u[2] + F[0]) * im - ldp<SP>(&P.g0);
     f[5] = (c10 * u[0] + c11 * u[1] + c12 * u[2] + F[1]) * im;
     f[6] = (c20 * u[0] + c21 * u[1] + c22 * u[2] + F[2]) * im;
     f[7]  = 0.5 * (-(w0 * q1) - w1 * q2 - w2 * q3);
     f[8]  = 0.5 * (w0 * q0 + w2 * q2 - w1 * q3);
     f[9]  = 0.5 * (w1 * q0 - w2 * q1 + w0 * q3);
     f[10] = 0.5 * (w2 * q0 + w1 * q1 - w0 * q2);
-    const double h0 = __ldg(&P.jB[0]) * w0 + __ldg(&P.jB[3]) * w1 + __ldg(&P.jB[6]) * w2;
-    const double h1 = __ldg(&P.jB[1]) * w0 + __ldg(&P.jB[4]) * w1 + __ldg(&P.jB[7]) * w2;
-    const double h2 = __ldg(&P.jB[2]) * w0 + __ldg(&P.jB[5]) * w1 + __ldg(&P.jB[8]) * w2;
-    const double m0 = (__ldg(&P.rTB[1]) * u[2] - __ldg(&P.rTB[2]) * u[1]) - (w1 * h2 - w2 * h1);
-    const double m1 = (__ldg(&P.rTB[2]) * u[0] - __ldg(&P.rTB[0]) * u[2]) - (w2 * h0 - w0 * h2);
-    const double m2 = (__ldg(&P.rTB[0]) * u[1] - __ldg(&P.rTB[1]) * u[0]) - (w0 * h1 - w1 * h0);
-    f[11] = __ldg(&P.jBi[0]) * m0 + __ldg(&P.jBi[3]) * m1 + __ldg(&P.jBi[6]) * m2;
-    f[12] = __ldg(&P.jBi[1]) * m0 + __ldg(&P.jBi[4]) * m1 + __ldg(&P.jBi[7]) * m2;
-    f[13] = __ldg(&P.jBi[2]) * m0 + __ldg(&P.jBi[5]) * m1 + __ldg(&P.jBi[8]) * m2;
+    const double h0 = ldp<SP>(&P.jB[0]) * w0 + ldp<SP>(&P.jB[3]) * w1 + ldp<SP>(&P.jB[6]) * w2;
+    const double h1 = ldp<SP>(&P.jB[1]) * w0 + ldp<SP>(&P.jB[4]) * w1 + ldp<SP>(&P.jB[7]) * w2;
+    const double h2 = ldp<SP>(&P.jB[2]) * w0 + ldp<SP>(&P.jB[5]) * w1 + ldp<SP>(&P.jB[8]) * w2;
+    const double m0 = (ldp<SP>(&P.rTB[1]) * u[2] - ldp<SP>(&P.rTB[2]) * u[1]) - (w1 * h2 - w2 * h1);
+    const double m1 = (ldp<SP>(&P.rTB[2]) * u[0] - ldp<SP>(&P.rTB[0]) * u[2]) - (w2 * h0 - w0 * h2);
+    const double m2 = (ldp<SP>(&P.rTB[0]) * u[1] - ldp<SP>(&P.rTB[1]) * u[0]) - (w0 * h1 - w1 * h0);
+    f[11] = ldp<SP>(&P.jBi[0]) * m0 + ldp<SP>(&P.jBi[3]) * m1 + ldp<SP>(&P.jBi[6]) * m2;
+    f[12] = ldp<SP>(&P.jBi[1]) * m0 + ldp<SP>(&P.jBi[4]) * m1 + ldp<SP>(&P.jBi[7]) * m2;
+    f[13] = ldp<SP>(&P.jBi[2]) * m0 + ldp<SP>(&P.jBi[5]) * m1 + ldp<SP>(&P.jBi[8]) * m2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -238,6 +256,7 @@ __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpre
 // out: this lane's NJ-double Jacobian record in the ring (the caller has waited for the slot).  The record is formed
 // and stored block by block, so only a few values are live at any time; every block that enters a stage increment
 // carries sigma * scale (scale = the stage's rk4 factor, see consume_stage8), the quadrature entries (v, sigma) do not.
+template <bool SP = false>
 __device__ __forceinline__ void produce_lean(const scvx_probinfo& P, bool aero_rec, double sigma, double scale,
                                              const double* __restrict__ rec, double* __restrict__ out) {
     const double ss = sigma * scale;
@@ -260,7 +279,7 @@ __device__ __forceinline__ void produce_lean(const scvx_probinfo& P, bool aero_r
         {
             double jB[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) jB[k] = __ldg(&P.jB[k]);
+            for (int k = 0; k < 9; ++k) jB[k] = ldp<SP>(&P.jB[k]);
             const double L0 = jB[0] * w0 + jB[3] * w1 + jB[6] * w2;
             const double L1 = jB[1] * w0 + jB[4] * w1 + jB[7] * w2;
             const double L2 = jB[2] * w0 + jB[5] * w1 + jB[8] * w2;
@@ -274,7 +293,7 @@ __device__ __forceinline__ void produce_lean(const scvx_probinfo& P, bool aero_r
         double Jw[9];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            const double b0 = __ldg(&P.jBi[r]), b1 = __ldg(&P.jBi[r + 3]), b2 = __ldg(&P.jBi[r + 6]);
+            const double b0 = ldp<SP>(&P.jBi[r]), b1 = ldp<SP>(&P.jBi[r + 3]), b2 = ldp<SP>(&P.jBi[r + 6]);
 #pragma unroll
             for (int c = 0; c < 3; ++c) Jw[3 * r + c] = -ss * (b0 * M[0][c] + b1 * M[1][c] + b2 * M[2][c]);
         }
@@ -286,7 +305,7 @@ __device__ __forceinline__ void produce_lean(const scvx_probinfo& P, bool aero_r
     {
         const double q0 = rec[4 * GROUP], q1 = rec[5 * GROUP], q2 = rec[6 * GROUP], q3 = rec[7 * GROUP];
         const double u0 = rec[11 * GROUP], u1 = rec[12 * GROUP], u2 = rec[13 * GROUP];
-        const double Pg0 = __ldg(&P.g0);
+        const double Pg0 = ldp<SP>(&P.g0);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             double j0, j1, j2, j3;
@@ -321,12 +340,12 @@ __device__ __forceinline__ void produce_lean(const scvx_probinfo& P, bool aero_r
         const double c10 = 2.0 * (q1 * q2 + q0 * q3), c11 = 1.0 - 2.0 * (q1 * q1 + q3 * q3), c12 = 2.0 * (q2 * q3 - q0 * q1);
         const double c20 = 2.0 * (q1 * q3 - q0 * q2), c21 = 2.0 * (q2 * q3 + q0 * q1), c22 = 1.0 - 2.0 * (q1 * q1 + q2 * q2);
         const double nu = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
-        const double gm = -ss * __ldg(&P.a) / nu;
-        const double r0 = __ldg(&P.rTB[0]), r1 = __ldg(&P.rTB[1]), r2 = __ldg(&P.rTB[2]);
+        const double gm = -ss * ldp<SP>(&P.a) / nu;
+        const double r0 = ldp<SP>(&P.rTB[0]), r1 = ldp<SP>(&P.rTB[1]), r2 = ldp<SP>(&P.rTB[2]);
         double* G = out + J_G;
         double bi[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) bi[k] = __ldg(&P.jBi[k]);
+        for (int k = 0; k < 9; ++k) bi[k] = ldp<SP>(&P.jBi[k]);
         // jBi * (rTB x e_j): rTB x e0 = (0, r2, -r1); x e1 = (-r2, 0, r0); x e2 = (r1, -r0, 0)
         st2(G + 0, gm * u0, sm * c00); st2(G + 2, sm * c10, sm * c20);
         st2(G + 4, ss * (bi[3] * r2 - bi[6] * r1), ss * (bi[4] * r2 - bi[7] * r1));

@@ -117,9 +117,9 @@ class DeviceContext:
         _lib.check(self._lib.scvx_last_kernel_ms(self._h, ctypes.byref(ms)))
         return ms.value
 
-    def linearize_compact_ptr(self, X, U, sigma, base_dt, npts, mode, n_nodes, B, out_compact, out_tlb=0):
+    def linearize_compact_ptr(self, X, U, sigma, base_dt, npts, mode, n_nodes, B, out_compact, out_tlb=0, layout=0):
         _lib.check(self._lib.scvx_linearize_batch_compact(self._h, X, U, sigma, base_dt, npts, mode, n_nodes, B,
-                                                          out_compact, out_tlb or None))
+                                                          int(layout), out_compact, out_tlb or None))
 
     # ---- raw pointer calls (host or device addresses)
     def linearize_ptr(self, X, U, sigma, base_dt, npts, mode, n_nodes, B, out_blocks, out_lin_err=0, out_tlb=0):
@@ -144,6 +144,28 @@ class DeviceContext:
     def socp_values_ptr(self, blocks, lin_err, tlb, n_nodes, B, out_vals, out_rhs=0):
         _lib.check(self._lib.scvx_socp_values_batch(self._h, blocks, lin_err or None, tlb, n_nodes, B, out_vals,
                                                     out_rhs or None))
+
+    def linearize_fins_ptr(self, X, U5, sigma, base_dt, npts, mode, n_nodes, B, out_blocks, out_lin_err=0):
+        _lib.check(self._lib.scvx_linearize_batch_fins(self._h, X, U5, sigma, base_dt, npts, mode, n_nodes, B, out_blocks,
+                                                       out_lin_err or None))
+
+    def set_fin_tables(self, lift, drag, mach0, dmach, defl0, ddefl):
+        """Stage the fin-force tables (`aerodynamics.load_fin_table`): (n_mach, n_defl) column-major lift and drag."""
+        for which, t in ((0, lift), (1, drag)):
+            a = np.asfortranarray(t, dtype=np.float64)
+            _lib.check(self._lib.scvx_set_fin_table(self._h, which, a.ctypes.data, a.shape[0], a.shape[1], float(mach0),
+                                                    float(dmach), float(defl0), float(ddefl), 0))
+
+    def fin_force(self, mach, deflection):
+        """Fin lift / drag increments at (mach, deflection) pairs from the staged tables (cubic B-spline, Flat ends)."""
+        m = np.ascontiguousarray(mach, dtype=np.float64).reshape(-1)
+        d = np.ascontiguousarray(deflection, dtype=np.float64).reshape(-1)
+        if m.shape != d.shape:
+            raise ValueError("mach and deflection must have the same length")
+        lift, drag = np.empty_like(m), np.empty_like(m)
+        _lib.check(self._lib.scvx_fin_force_batch(self._h, m.ctypes.data, d.ctypes.data, m.size, lift.ctypes.data,
+                                                  drag.ctypes.data))
+        return lift, drag
 
     def predict_ptr(self, X, U, sigma, base_dt, npts, mode, n_nodes, B, out):
         _lib.check(self._lib.scvx_predict_batch(self._h, X, U, sigma, base_dt, npts, mode, n_nodes, B, out))
@@ -204,6 +226,14 @@ def linearize_batch(cache: IntegratorCache, X, U, sigma, base_dt: float, npts: i
 
 
 COMPACT_DOUBLES, COMPACT_DATA = 230, 229      # include/scvx_b200.h
+COMPACT_FULL, COMPACT_NO_Z = 0, 1
+
+
+def compact_record_doubles(layout: int = COMPACT_FULL) -> int:
+    n = _lib.load().scvx_compact_record_doubles(int(layout))
+    if n < 0:
+        _lib.check(n)
+    return n
 
 
 def compact_layout() -> np.ndarray:
@@ -214,10 +244,11 @@ def compact_layout() -> np.ndarray:
 
 
 def linearize_batch_compact(cache: IntegratorCache, X, U, sigma, base_dt: float, npts: int = 10, mode: int = MODE_LITERAL,
-                            tlb: bool = True):
+                            tlb: bool = True, layout: int = COMPACT_FULL):
     """`linearize_batch` with compact result records: only the 229 data entries of every 14x23 block (+ a per-interval
-    non-finite flag) cross PCIe.  -> compact (B, n_int, 230), tlb (B, n_nodes, 4) | None.  `expand_compact` restores the
-    dense blocks and lin_err on the host."""
+    non-finite flag) cross PCIe; layout COMPACT_NO_Z also drops the z column (215 + 1).
+    -> compact (B, n_int, 230 | 216), tlb (B, n_nodes, 4) | None.  `expand_compact` restores the dense blocks and lin_err
+    on the host."""
     ctx = _ctx(cache)
     X = np.ascontiguousarray(X, dtype=np.float64)
     U = np.ascontiguousarray(U, dtype=np.float64)
@@ -226,26 +257,55 @@ def linearize_batch_compact(cache: IntegratorCache, X, U, sigma, base_dt: float,
         raise ValueError("expected X (B, n_nodes, 14), U (B, n_nodes, 3), sigma (B,)")
     B, n_nodes, _ = X.shape
     ni = max(n_nodes - 1, 0)
-    comp = np.empty((B, ni, COMPACT_DOUBLES))
+    comp = np.empty((B, ni, compact_record_doubles(layout)))
     tl = np.empty((B, n_nodes, 4)) if tlb else None
     ctx.linearize_compact_ptr(X.ctypes.data, U.ctypes.data, sigma.ctypes.data, float(base_dt), int(npts), int(mode),
-                              n_nodes, B, comp.ctypes.data, tl.ctypes.data if tlb else 0)
+                              n_nodes, B, comp.ctypes.data, tl.ctypes.data if tlb else 0, layout)
     return comp, tl
 
 
-def expand_compact(compact, X, lin_err: bool = True, n_threads: int = 0):
-    """Host-side expander (`scvx_expand_compact`): compact (B, n_int, 230) + X (B, n_nodes, 14) ->
+def expand_compact(compact, X, U=None, sigma=None, lin_err: bool = True, n_threads: int = 0):
+    """Host-side expander (`scvx_expand_compact`): compact (B, n_int, 230 | 216) + X (B, n_nodes, 14) [+ U, sigma for the
+    NO_Z layout, whose z column is re-formed on the host] ->
     blocks (B, n_int, 23, 14), lin_err (B, n_int, 14) | None, number of intervals flagged non-finite."""
     compact = np.ascontiguousarray(compact, dtype=np.float64)
     X = np.ascontiguousarray(X, dtype=np.float64)
-    B, ni, _ = compact.shape
+    B, ni, rec = compact.shape
+    layout = {COMPACT_DOUBLES: COMPACT_FULL, 216: COMPACT_NO_Z}[rec]
+    U = None if U is None else np.ascontiguousarray(U, dtype=np.float64)
+    sigma = None if sigma is None else np.ascontiguousarray(sigma, dtype=np.float64).reshape(-1)
     blocks = np.empty((B, ni, ACC_WIDTH, STATE_DIM))
     err = np.empty((B, ni, STATE_DIM)) if lin_err else None
-    n = _lib.load().scvx_expand_compact(compact.ctypes.data, X.ctypes.data, ni + 1, B, blocks.ctypes.data,
+    n = _lib.load().scvx_expand_compact(compact.ctypes.data, layout, X.ctypes.data,
+                                        U.ctypes.data if U is not None else None,
+                                        sigma.ctypes.data if sigma is not None else None, ni + 1, B, blocks.ctypes.data,
                                         err.ctypes.data if lin_err else None, int(n_threads))
     if n < 0:
         _lib.check(int(n))
     return blocks, err, int(n)
+
+
+FINS_CONTROL_DIM, FINS_INP_DIM, FINS_ACC_WIDTH = 5, 25, 27      # control_dim 3 -> 5: inp 14 + 2*5 + 1, acc_width 14 + 2*5 + 3
+
+
+def linearize_batch_fins(cache: IntegratorCache, X, U5, sigma, base_dt: float, npts: int = 10, mode: int = MODE_LITERAL,
+                         lin_err: bool = True):
+    """SURVEY.md §8f-4 variant: the fin-force (`ff = u[4]*fd1 + u[5]*fd2`) and aero-torque terms the reference carries as
+    comments (dynamics.jl:60-63, 66, 69; torque of aerodynamics.jl:45, 49-56), control_dim = 5.  NO REFERENCE CONSUMER.
+    X (B, n_nodes, 14), U5 (B, n_nodes, 5) -> blocks (B, n_int, 27, 14) = [endpoint | D (25 columns) | z], lin_err."""
+    ctx = _ctx(cache)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    U5 = np.ascontiguousarray(U5, dtype=np.float64)
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64).reshape(-1)
+    if X.ndim != 3 or X.shape[2] != 14 or U5.shape != (X.shape[0], X.shape[1], 5) or sigma.shape[0] != X.shape[0]:
+        raise ValueError("expected X (B, n_nodes, 14), U5 (B, n_nodes, 5), sigma (B,)")
+    B, n_nodes, _ = X.shape
+    ni = max(n_nodes - 1, 0)
+    blocks = np.empty((B, ni, FINS_ACC_WIDTH, STATE_DIM))
+    err = np.empty((B, ni, STATE_DIM)) if lin_err else None
+    ctx.linearize_fins_ptr(X.ctypes.data, U5.ctypes.data, sigma.ctypes.data, float(base_dt), int(npts), int(mode), n_nodes,
+                           B, blocks.ctypes.data, err.ctypes.data if lin_err else 0)
+    return blocks, err
 
 
 def predict_batch(cache: IntegratorCache, X, U, sigma, base_dt: float, npts: int = 10, mode: int = MODE_LITERAL):

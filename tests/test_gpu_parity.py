@@ -616,6 +616,13 @@ def test_compact_expands_to_dense_bit_for_bit(dyn, cache_aero, prob_aero, mode, 
     ctx.linearize_compact_ptr(dX.data_ptr(), dU.data_ptr(), dS.data_ptr(), 1 / (K + 1), 10, mode, K + 1, B, dC.data_ptr())
     torch.cuda.synchronize()
     assert np.array_equal(dC.cpu().numpy(), comp)
+    # layout NO_Z: 216-double records; everything but the z column is the same bytes, z is re-formed on the host
+    c216, _ = dyn.linearize_batch_compact(cache_aero, X, U, sigma, 1 / (K + 1), 10, mode, tlb=False, layout=dyn.COMPACT_NO_Z)
+    assert c216.shape == (B, K, 216) and np.array_equal(c216[..., :215], comp[..., :215]) and not c216[..., 215].any()
+    zb, ze, _ = dyn.expand_compact(c216, X, U, sigma)
+    assert np.array_equal(zb[:, :, :22], blocks[:, :, :22]) and np.array_equal(ze, err)
+    scale = np.abs(blocks[:, :, :22]).max(axis=(2, 3), keepdims=True)
+    assert (np.abs(zb[:, :, 22:] - blocks[:, :, 22:]) <= 1e-12 * scale).all()
     ctx.use_library_stream()                               # scvx_set_stream(ctx, NULL) = back to the library's own stream
     comp2, _ = dyn.linearize_batch_compact(cache_aero, X[:7], U[:7], sigma[:7], 1 / (K + 1), 10, mode, tlb=False)
     assert np.array_equal(comp2, comp[:7])
@@ -643,3 +650,87 @@ def test_pinned_host_memory_round_trip():
     a = np.zeros(1 << 17)
     _lib.check(lib.scvx_host_register(a.ctypes.data, a.nbytes))
     _lib.check(lib.scvx_host_unregister(a.ctypes.data))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fin forces + aero torque (control_dim = 5) and the fin-force tables.  NO REFERENCE CONSUMER: parity is
+# against the oracle's extension, which restores the reference's commented-out expressions (dynamics.jl:60-63, 66, 69).
+# ---------------------------------------------------------------------------------------------------------------
+def _fins_batch(prob, K, B, seed):
+    from successiveconvexification_b200 import workloads
+    X, U, sigma, P = workloads.monte_carlo_batch(prob, K, B, seed, sigma_range=(0.8, 1.5))
+    rng = np.random.default_rng(seed + 1)
+    U5 = np.concatenate([U, rng.normal(0.0, 0.002, (B, K + 1, 2))], axis=-1)
+    return X, np.ascontiguousarray(U5), U, sigma, P
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fins_and_aero_torque_variant_vs_oracle_extension(dyn, cache_aero, prob_aero, oracle_tables, mode):
+    X, U5, U, sigma, P = _fins_batch(prob_aero, 12, 40, 333)
+    blocks, err = dyn.linearize_batch_fins(cache_aero, X, U5, sigma, 1 / 13, 10, mode)
+    ref, rerr = _oracle().linearize_batch_fins(P, oracle_tables, X, U5, sigma, 1 / 13, 10, mode)
+    assert blocks.shape == ref.shape == (40, 12, 27, 14) and np.isfinite(blocks).all()
+    for sl in (slice(0, 1), slice(1, 15), slice(15, 20), slice(20, 25), slice(25, 26)):      # endpoint, A, B-, B+, Sigma
+        g, r = blocks[:, :, sl, :], ref[:, :, sl, :]
+        scale = np.abs(r).max(axis=(2, 3), keepdims=True)
+        assert (np.abs(g - r) / np.maximum(np.abs(r), 1e-4 * scale)).max() <= 1e-10
+    zs = np.abs(ref[:, :, :26]).max(axis=(2, 3))
+    assert (np.abs(blocks[:, :, 26] - ref[:, :, 26]).max(axis=2) <= 1e-12 * zs).all()
+    assert np.abs(err - rerr).max() <= 1e-12 * max(1.0, np.abs(rerr).max())
+    # the torque couples wdot to q and v: the zero pattern the 3-control path relies on is gone
+    assert np.abs(blocks[:, :, 1 + 7:1 + 11, 11:14]).max() > 0.0
+    # nothing depends on position, as before
+    expect = np.zeros((3, 14)); expect[[0, 1, 2], [1, 2, 3]] = 1.0
+    assert np.array_equal(blocks[:, :, 2:5, :], np.broadcast_to(expect, (40, 12, 3, 14)))
+    # device pointers give the same bytes
+    import torch
+    ctx = cache_aero.sim_prob
+    dX, dU, dS = (torch.from_numpy(a).cuda() for a in (X, U5, sigma))
+    dO = torch.empty((40, 12, 27, 14), dtype=torch.float64, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.linearize_fins_ptr(dX.data_ptr(), dU.data_ptr(), dS.data_ptr(), 1 / 13, 10, mode, 13, 40, dO.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(dO.cpu().numpy(), blocks)
+
+
+def test_fins_variant_reduces_to_the_three_control_path(dyn, prob_aero, cache_aero):
+    """With zero fin commands and a zero torque table the 5-control variant is the 3-control model: shared entries of
+    the blocks agree with the DUALWARP kernel of the standard path (same arithmetic, bit for bit in the value)."""
+    from successiveconvexification_b200.defns import AeroTable, AtmosphericData
+    aero = prob_aero.aero
+    zero = AeroTable(np.zeros_like(aero.trq_itrp.samples), aero.trq_itrp.cos0, aero.trq_itrp.dcos, aero.trq_itrp.mach0,
+                     aero.trq_itrp.dmach)
+    prob0 = prob_aero.replace(aero=AtmosphericData(aero.drag_itrp, aero.lift_itrp, zero, aero.force_scalar, aero.length_scalar))
+    cache0 = dyn.make_cache(prob0)
+    X, U5, U, sigma, _ = _fins_batch(prob_aero, 6, 9, 71)
+    U5[..., 3:] = 0.0
+    b5, _ = dyn.linearize_batch_fins(cache0, X, U5, sigma, 1 / 7, 10, 1)
+    cache_aero.sim_prob.set_kernel(1)
+    b3, _, _ = dyn.linearize_batch(cache_aero, X, U, sigma, 1 / 7, 10, 1)
+    cache_aero.sim_prob.set_kernel(0)
+    assert np.abs(b5[:, :, 0] - b3[:, :, 0]).max() <= 1e-15                                 # endpoint
+    cols5 = list(range(1, 15)) + [15, 16, 17, 20, 21, 22, 25]                                # A, B-[0:3], B+[0:3], Sigma
+    assert np.abs(b5[:, :, cols5] - b3[:, :, 1:22]).max() <= 1e-12 * np.abs(b3[:, :, 1:22]).max()
+
+
+def test_fin_force_tables_staged_and_evaluated(dyn, cache_aero):
+    """Fin-force tables at the size of aero/fin.csv (60 Mach x 901 deflections), device prefilter + lookup kernel against
+    the oracle's spline (same Interpolations.jl semantics as the aero tables)."""
+    orc = _oracle()
+    mach = 0.01 + 0.025 * np.arange(60)
+    defl = 0.1 * np.arange(901)
+    lift = np.asfortranarray(1e-3 * np.sin(2.0 * mach)[:, None] * np.sin(np.deg2rad(defl))[None, :] * (1 + 0.1 * mach[:, None] ** 2))
+    drag = np.asfortranarray(2e-4 * (1 - np.cos(np.deg2rad(defl)))[None, :] * (0.5 + mach[:, None]))
+    ctx = cache_aero.sim_prob
+    ctx.set_fin_tables(lift, drag, 0.01, 0.025, 0.0, 0.1)
+    rng = np.random.default_rng(4)
+    m = rng.uniform(-0.1, 1.7, 500); d = rng.uniform(-5.0, 95.0, 500)                      # incl. Flat extrapolation
+    gl, gd = ctx.fin_force(m, d)
+    geom = np.array([60, 901, 0.01, 0.025, 0.0, 0.1])
+    cl, cd = orc.prefilter(lift), orc.prefilter(drag)
+    rl = np.array([orc.spline_eval(cl, geom, a, b)[0] for a, b in zip(m, d)])
+    rd = np.array([orc.spline_eval(cd, geom, a, b)[0] for a, b in zip(m, d)])
+    assert np.abs(gl - rl).max() <= 1e-13 * np.abs(rl).max() and np.abs(gd - rd).max() <= 1e-13 * np.abs(rd).max()
+    # exact interpolation at grid points
+    gl2, _ = ctx.fin_force(mach[[0, 7, 59]], defl[[0, 450, 900]])
+    assert np.abs(gl2 - lift[[0, 7, 59], [0, 450, 900]]).max() <= 1e-15

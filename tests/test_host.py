@@ -130,3 +130,16 @@ def test_socp_entry_points_reject_bad_arguments():
     from successiveconvexification_b200 import rocketland, _lib
     with pytest.raises(_lib.ScvxError):
         rocketland.socp_dims(1)
+
+
+def test_fin_table_loader(tmp_path):
+    """aero/fin.csv layout (aero/AeroTable.jl:94-112): header lift,drag,mach,aoa; Mach varies fastest."""
+    from successiveconvexification_b200 import aerodynamics
+    mach = 0.01 + 0.025 * np.arange(4)
+    defl = 0.1 * np.arange(3)
+    rows = [(10 * j + i, 100 * j + i, mach[i], defl[j]) for j in range(3) for i in range(4)]
+    p = tmp_path / "fin.csv"
+    p.write_text("lift,drag,mach,aoa\n" + "\n".join(",".join(repr(float(v)) for v in r) for r in rows) + "\n")
+    lift, drag, axes = aerodynamics.load_fin_table(p, n_mach=4, n_defl=3)
+    assert lift.shape == (4, 3) and lift[2, 1] == 12.0 and drag[3, 2] == 203.0
+    assert axes == pytest.approx((0.01, 0.025, 0.0, 0.1))

@@ -243,3 +243,34 @@ def test_binary128_evaluation_and_branch_signatures(prob_aero, oracle_tables):
     same = (a == b).reshape(-1)
     assert parity_metric_per_interval(txt64, txtq).max() <= 1e-10
     assert parity_metric_per_interval(lit64, litq)[same].max() > 1e-10     # no FP64 implementation holds 1e-10 here
+
+
+def test_fins_extension_is_consistent(prob_aero, oracle_tables):
+    """SURVEY.md §8f-4 oracle extension (no reference consumer): (a) with zero fin commands and a zero torque table it is
+    the 3-control model; (b) its forward-mode Jacobian agrees with central differences of its own endpoint map."""
+    import copy
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, 4, 5, 21, sigma_range=(0.8, 1.5))
+    U5 = np.concatenate([U, np.zeros(U.shape[:2] + (2,))], axis=-1)
+    tb0 = copy.copy(oracle_tables)
+    tb0.trq = np.zeros_like(oracle_tables.trq)
+    b5, _ = oracle.linearize_batch_fins(P, tb0, X, U5, sigma, 0.2, 10, 1)
+    b3, _, _, _ = oracle.linearize_batch(P, oracle_tables, X, U, sigma, 0.2, 10, 1)
+    cols5 = list(range(1, 15)) + [15, 16, 17, 20, 21, 22, 25]
+    assert np.abs(b5[:, :, 0] - b3[:, :, 0]).max() <= 1e-15
+    assert np.abs(b5[:, :, cols5] - b3[:, :, 1:22]).max() <= 1e-13 * np.abs(b3[:, :, 1:22]).max()
+    # (b) central differences, with fins and torque active
+    rng = np.random.default_rng(3)
+    U5 = np.concatenate([U, rng.normal(0, 0.002, U.shape[:2] + (2,))], axis=-1)
+    base, _ = oracle.linearize_batch_fins(P, oracle_tables, X[:1, :2], U5[:1, :2], sigma[:1], 0.2, 10, 1)
+    D = base[0, 0, 1:26]                                   # rows = columns of D
+    inp = np.concatenate([X[0, 0], U5[0, 0], U5[0, 1], sigma[:1]])
+    for j in (0, 5, 8, 12, 17, 18, 23, 24):
+        h = 1e-6 * max(1.0, abs(inp[j]))
+        ends = []
+        for sgn in (+1, -1):
+            v = inp.copy(); v[j] += sgn * h
+            Xp = np.stack([v[:14], X[0, 1]])[None]; Up = np.stack([v[14:19], v[19:24]])[None]
+            e, _ = oracle.linearize_batch_fins(P, oracle_tables, Xp, Up, v[24:25], 0.2, 10, 1)
+            ends.append(e[0, 0, 0])
+        fd = (ends[0] - ends[1]) / (2 * h)
+        assert np.abs(fd - D[j]).max() <= 1e-6 * max(1.0, np.abs(D[j]).max()), j
