@@ -315,59 +315,62 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
     const int my_groups = (a.n_groups > (int)blockIdx.x) ? (a.n_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int total_steps = my_groups * npts;          // global step counter n = pass * npts + local step
 
-    int colA = -1, colB = -1, gcol = 3;
-    if (l8 < 3) { colA = 14 + l8; colB = 17 + l8; gcol = l8; }
-    else if (l8 == 3) { colA = 20; colB = 0; }          // sigma column | light column d/dm
-    else if (l8 == 4) { colA = 11; colB = 12; }
-    else if (l8 == 5) { colA = 13; colB = 7; }
-    else if (l8 == 6) { colA = 8; colB = 9; }
-    else { colA = 10; colB = 4; }                        // q3 column | light column d/dv0
+    // slot A: control-type columns (B-0..2, B+0..2, Sigma, light d/dm); slot B: state-type columns (w0..2, q0..3, light
+    // d/dv0) — see consume_stage8
+    const int colA = (l8 < 7) ? 14 + l8 : 0;
+    const int colB = (l8 < 3) ? 11 + l8 : (l8 < 7 ? 4 + l8 : 4);
+    const int gcol = (l8 < 3) ? l8 : (l8 < 6 ? l8 - 3 : 3);
 
     const int kq = warp & 3;                            // stage (within a step) this warp produces
     // rk4 factor folded into the Jacobian blocks of that stage (consume_stage8): Y_{i+1} = S + c_i K_i, h/6 for the last
     const double stage_scale = (kq == 3) ? h6 : (kq == 2 ? sstep : 0.5 * sstep);
     const double kappa = (bt.mode == SCVX_MODE_LITERAL) ? h * (1.0 / 3.0) : (1.0 / 3.0);
-    auto issue_record = [&](int n) {                    // one lane: TMA the record of (global step n, stage kq)
-        const int it = n / npts, ls = n - it * npts;
-        const int g = blockIdx.x + it * gridDim.x;
-        const uint32_t bytes = (uint32_t)a.rec_n * GROUP * 8;
-        const double* src = a.rec + ((size_t)g * nst + 4 * ls + kq) * ((size_t)a.rec_n * GROUP);
-        fence_proxy_async();
-        mbar_expect_tx(&sm.recfull[n & 1][kq], bytes);
-        bulk_g2s(sm.recbuf[kq], src, bytes, &sm.recfull[n & 1][kq]);
-    };
-    auto record_src = [&](int n) -> const double* {
-        const int it = n / npts, ls = n - it * npts;
+    const uint32_t rec_bytes = (uint32_t)a.rec_n * GROUP * 8;
+    // stage record of (pass it, local step ls, stage kq); (it, ls) are tracked incrementally — no integer divisions in the
+    // producer loop
+    auto record_src = [&](int it, int ls) -> const double* {
         const int g = blockIdx.x + it * gridDim.x;
         return a.rec + ((size_t)g * nst + 4 * ls + kq) * ((size_t)a.rec_n * GROUP);
     };
-    auto produce = [&](int n) {                         // whole warp (lane = interval): stage kq of global step n
-        // the record buffer is single (shared memory is full), so the TMA of step n+1 can only be issued once this
-        // step's record has been read: pull it into L2 now, the copy then costs an L2 hit instead of a DRAM round trip
-        if (lane == 0 && n + 1 < total_steps) bulk_prefetch_l2(record_src(n + 1), (uint32_t)a.rec_n * GROUP * 8);
-        const int it = n / npts;
-        const int g = blockIdx.x + it * gridDim.x;
-        int t = g * GROUP + lane; if (t >= a.count) t = a.count - 1;
-        const int b = (a.first + t) / ni;
-        const scvx_probinfo& P = SP ? a.Pc : bt.P[bt.n_params == 1 ? 0 : b];
-        const double sigma = __ldg(bt.sigma + b);
-        const int half = n & 1, use = n >> 1;
-        mbar_wait(&sm.recfull[half][kq], (uint32_t)(use & 1));      // this warp is the only waiter of recfull[half][kq]
-        if (use > 0) mbar_wait(&sm.empty_step[half], (uint32_t)((use - 1) & 1));
-        produce_lean<SP>(P, a.rec_n == REC_AERO, sigma, stage_scale, sm.recbuf[kq] + lane, &sm.ring[half * 4 + kq][lane][0]);
-        mbar_arrive(&sm.full_step[half]);
-        __syncwarp();                                    // every lane has finished reading recbuf[kq]
-        if (lane == 0 && n + 1 < total_steps) issue_record(n + 1);
+    auto issue_record = [&](int n, int it, int ls) {    // one lane: TMA the record of global step n = it * npts + ls
+        fence_proxy_async();
+        mbar_expect_tx(&sm.recfull[n & 1][kq], rec_bytes);
+        bulk_g2s(sm.recbuf[kq], record_src(it, ls), rec_bytes, &sm.recfull[n & 1][kq]);
     };
 
     // dedicated producer warps: warp NWARP + kq forms stage kq of every step, as far ahead as the ring allows
     if (warp >= NWARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
         if (total_steps > 0) {
-            if (lane == 0) issue_record(0);
+            if (lane == 0) issue_record(0, 0, 0);
             __syncwarp();
+            int n = 0;
 #pragma unroll 1
-            for (int n = 0; n < total_steps; ++n) produce(n);
+            for (int it = 0; it < my_groups; ++it) {
+                // whole warp, lane = interval: this pass's interval, its trajectory and parameters (once per pass)
+                const int g = blockIdx.x + it * gridDim.x;
+                int t = g * GROUP + lane; if (t >= a.count) t = a.count - 1;
+                const int b = (a.first + t) / ni;
+                const scvx_probinfo& P = SP ? a.Pc : bt.P[bt.n_params == 1 ? 0 : b];
+                const double sigma = __ldg(bt.sigma + b);
+#pragma unroll 1
+                for (int ls = 0; ls < npts; ++ls, ++n) {
+                    const bool more = n + 1 < total_steps;
+                    const int nit = (ls + 1 < npts) ? it : it + 1, nls = (ls + 1 < npts) ? ls + 1 : 0;
+                    // the record buffer is single (shared memory is full), so the TMA of step n+1 can only be issued once
+                    // this step's record has been read: pull it into L2 now, the copy then costs an L2 hit instead of a
+                    // DRAM round trip
+                    if (lane == 0 && more) bulk_prefetch_l2(record_src(nit, nls), rec_bytes);
+                    const int half = n & 1, use = n >> 1;
+                    mbar_wait(&sm.recfull[half][kq], (uint32_t)(use & 1));      // this warp is the only waiter of recfull[half][kq]
+                    if (use > 0) mbar_wait(&sm.empty_step[half], (uint32_t)((use - 1) & 1));
+                    produce_lean<SP>(P, a.Kw, a.Tw, a.rec_n == REC_AERO, sigma, stage_scale, sm.recbuf[kq] + lane,
+                                     &sm.ring[half * 4 + kq][lane][0]);
+                    mbar_arrive(&sm.full_step[half]);
+                    __syncwarp();                        // every lane has finished reading recbuf[kq]
+                    if (lane == 0 && more) issue_record(n + 1, nit, nls);
+                }
+            }
         }
         return;
     }
@@ -380,8 +383,8 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
 #pragma unroll
         for (int r = 0; r < 11; ++r) {
             // identity part of S(0) = [I | 0]; local rows 0 m, 1..3 v, 4..7 q, 8..10 w <-> inp columns 0, 4..6, 7..10, 11..13
-            FA.S[r] = (colA == r + 3 && r >= 1) ? 1.0 : 0.0;
-            FB.S[r] = ((colB == r + 3 && r >= 1) || (colB == 0 && r == 0)) ? 1.0 : 0.0;
+            FA.S[r] = (colA == 0 && r == 0) ? 1.0 : 0.0;        // control columns start at zero; d/dm starts at e_m
+            FB.S[r] = (colB == r + 3 && r >= 1) ? 1.0 : 0.0;    // state columns start at their unit vector
             FA.A[r] = 0.0; FB.A[r] = 0.0;
             FA.Y[r] = FA.S[r]; FB.Y[r] = FB.S[r];
         }
@@ -482,7 +485,29 @@ cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool a
     for (long first = 0; first < total; first += chunk_intervals) {
         StagedArgs a;
         a.bt = bt; a.tb = tb; a.rec = (double*)scratch; a.first = (int)first;
-        if (shared_params) a.Pc = *shared_params;
+        if (shared_params) {
+            a.Pc = *shared_params;
+            const double* bi = a.Pc.jBi;
+            const double r0 = a.Pc.rTB[0], r1 = a.Pc.rTB[1], r2 = a.Pc.rTB[2];
+            a.Kw[0] = bi[3] * r2 - bi[6] * r1; a.Kw[1] = bi[4] * r2 - bi[7] * r1; a.Kw[2] = bi[5] * r2 - bi[8] * r1;
+            a.Kw[3] = bi[6] * r0 - bi[0] * r2; a.Kw[4] = bi[7] * r0 - bi[1] * r2; a.Kw[5] = bi[8] * r0 - bi[2] * r2;
+            a.Kw[6] = bi[0] * r1 - bi[3] * r0; a.Kw[7] = bi[1] * r1 - bi[4] * r0; a.Kw[8] = bi[2] * r1 - bi[5] * r0;
+            const double* jB = a.Pc.jB;
+            for (int k = 0; k < 3; ++k) {                  // Tw_k = -jBi ([e_k]x jB - [jB e_k]x), row-major 3 x 3
+                double w[3] = { 0.0, 0.0, 0.0 }, M[3][3];
+                w[k] = 1.0;
+                const double L[3] = { jB[0] * w[0] + jB[3] * w[1] + jB[6] * w[2], jB[1] * w[0] + jB[4] * w[1] + jB[7] * w[2],
+                                      jB[2] * w[0] + jB[5] * w[1] + jB[8] * w[2] };
+                for (int c = 0; c < 3; ++c) {
+                    const double a0 = jB[3 * c], a1 = jB[3 * c + 1], a2 = jB[3 * c + 2];
+                    M[0][c] = w[1] * a2 - w[2] * a1; M[1][c] = w[2] * a0 - w[0] * a2; M[2][c] = w[0] * a1 - w[1] * a0;
+                }
+                M[0][1] += L[2]; M[0][2] -= L[1]; M[1][0] -= L[2]; M[1][2] += L[0]; M[2][0] += L[1]; M[2][1] -= L[0];
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c)
+                        a.Tw[9 * k + 3 * r + c] = -(bi[r] * M[0][c] + bi[r + 3] * M[1][c] + bi[r + 6] * M[2][c]);
+            }
+        }
         a.rec_n = any_aero ? REC_AERO : REC_EXO;
         a.count = (int)((total - first < chunk_intervals) ? (total - first) : chunk_intervals);
         a.n_groups = (a.count + GROUP - 1) / GROUP;

@@ -29,6 +29,8 @@ struct StagedArgs {
     ScvxTables tb;
     scvx_probinfo Pc;            // the parameter record itself when all trajectories share one (kernel-argument space:
                                  // its fields become constant-bank operands, no loads; kernels instantiated with SP = true)
+    double Kw[9];                // with Pc: jBi * [rTB]x, the d(wdot)/du block (column-major 3 x 3), formed once on the host
+    double Tw[27];               // with Pc: d(wdot)/dw = sum_k w_k Tw[9k + 3r + c], Tw_k = -jBi ([e_k]x jB - [jB e_k]x)
     double* rec;                 // stage records of this chunk
     int rec_n;                   // entries per stage record (REC_EXO or REC_AERO)
     int first;                   // first interval (global index) of this chunk (total intervals < 2^31)
@@ -257,8 +259,9 @@ __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpre
 // and stored block by block, so only a few values are live at any time; every block that enters a stage increment
 // carries sigma * scale (scale = the stage's rk4 factor, see consume_stage8), the quadrature entries (v, sigma) do not.
 template <bool SP = false>
-__device__ __forceinline__ void produce_lean(const scvx_probinfo& P, bool aero_rec, double sigma, double scale,
-                                             const double* __restrict__ rec, double* __restrict__ out) {
+__device__ __forceinline__ void produce_lean(const scvx_probinfo& P, const double* __restrict__ Kw,
+                                             const double* __restrict__ Tw, bool aero_rec, double sigma,
+                                             double scale, const double* __restrict__ rec, double* __restrict__ out) {
     const double ss = sigma * scale;
     const double hs = 0.5 * ss;
     const double sm = ss / rec[0];
@@ -272,68 +275,79 @@ __device__ __forceinline__ void produce_lean(const scvx_probinfo& P, bool aero_r
         st2(out + J_FRQ + 4, scale * f1, scale * f2); st2(out + J_FRQ + 6, scale * f3, sigma);
         st2(out + J_FRQ + 8, 0.0, 0.0);
     }
-    // ---- rotational block: Jww = -ss * jBi * ([w]x jB - [jB w]x), and hw
+    // ---- rotational block: Jww = -ss * jBi * ([w]x jB - [jB w]x), and hw.  The block is linear in w; with a shared
+    // parameter record its three constant 3 x 3 factors come from the kernel arguments (27 FMAs instead of 54 operations).
     {
         const double w0 = rec[8 * GROUP], w1 = rec[9 * GROUP], w2 = rec[10 * GROUP];
-        double M[3][3];
-        {
-            double jB[9];
+        if constexpr (SP) {
+            const double s0 = ss * w0, s1 = ss * w1, s2 = ss * w2;
+            auto jw = [&](int k) { return fma(s2, Tw[18 + k], fma(s1, Tw[9 + k], s0 * Tw[k])); };
+            st2(out + J_WW + 0, jw(0), jw(1)); st2(out + J_WW + 2, jw(2), jw(3)); st2(out + J_WW + 4, jw(4), jw(5));
+            st2(out + J_WW + 6, jw(6), jw(7)); st2(out + J_WW + 8, jw(8), hs * w0);
+        } else {
+            double Jw[9];
+            double M[3][3];
+            {
+                double jB[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) jB[k] = ldp<SP>(&P.jB[k]);
-            const double L0 = jB[0] * w0 + jB[3] * w1 + jB[6] * w2;
-            const double L1 = jB[1] * w0 + jB[4] * w1 + jB[7] * w2;
-            const double L2 = jB[2] * w0 + jB[5] * w1 + jB[8] * w2;
+                for (int k = 0; k < 9; ++k) jB[k] = ldp<SP>(&P.jB[k]);
+                const double L0 = jB[0] * w0 + jB[3] * w1 + jB[6] * w2;
+                const double L1 = jB[1] * w0 + jB[4] * w1 + jB[7] * w2;
+                const double L2 = jB[2] * w0 + jB[5] * w1 + jB[8] * w2;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const double a0 = jB[3 * c], a1 = jB[3 * c + 1], a2 = jB[3 * c + 2];
-                M[0][c] = w1 * a2 - w2 * a1; M[1][c] = w2 * a0 - w0 * a2; M[2][c] = w0 * a1 - w1 * a0;
+                for (int c = 0; c < 3; ++c) {
+                    const double a0 = jB[3 * c], a1 = jB[3 * c + 1], a2 = jB[3 * c + 2];
+                    M[0][c] = w1 * a2 - w2 * a1; M[1][c] = w2 * a0 - w0 * a2; M[2][c] = w0 * a1 - w1 * a0;
+                }
+                M[0][1] += L2; M[0][2] -= L1; M[1][0] -= L2; M[1][2] += L0; M[2][0] += L1; M[2][1] -= L0;
             }
-            M[0][1] += L2; M[0][2] -= L1; M[1][0] -= L2; M[1][2] += L0; M[2][0] += L1; M[2][1] -= L0;
-        }
-        double Jw[9];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const double b0 = ldp<SP>(&P.jBi[r]), b1 = ldp<SP>(&P.jBi[r + 3]), b2 = ldp<SP>(&P.jBi[r + 6]);
+            for (int r = 0; r < 3; ++r) {
+                const double b0 = ldp<SP>(&P.jBi[r]), b1 = ldp<SP>(&P.jBi[r + 3]), b2 = ldp<SP>(&P.jBi[r + 6]);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) Jw[3 * r + c] = -ss * (b0 * M[0][c] + b1 * M[1][c] + b2 * M[2][c]);
+                for (int c = 0; c < 3; ++c) Jw[3 * r + c] = -ss * (b0 * M[0][c] + b1 * M[1][c] + b2 * M[2][c]);
+            }
+            st2(out + J_WW + 0, Jw[0], Jw[1]); st2(out + J_WW + 2, Jw[2], Jw[3]); st2(out + J_WW + 4, Jw[4], Jw[5]);
+            st2(out + J_WW + 6, Jw[6], Jw[7]); st2(out + J_WW + 8, Jw[8], hs * w0);
         }
-        st2(out + J_WW + 0, Jw[0], Jw[1]); st2(out + J_WW + 2, Jw[2], Jw[3]); st2(out + J_WW + 4, Jw[4], Jw[5]);
-        st2(out + J_WW + 6, Jw[6], Jw[7]); st2(out + J_WW + 8, Jw[8], hs * w0);
         st2(out + J_HW + 1, hs * w1, hs * w2);
     }
-    // ---- v rows: [d/dm, d/dv (3), d/dq (4)] per row
+    // ---- v rows: [d/dm, d/dv (3), d/dq (4)] per row.  The factor 2 of d(C u)/dq and of db/dq is folded into sm2 = 2 sm;
+    // the structurally zero entries of db/dq (row 0: {0, 0, -4 q2, -4 q3}) are not multiplied out.
     {
         const double q0 = rec[4 * GROUP], q1 = rec[5 * GROUP], q2 = rec[6 * GROUP], q3 = rec[7 * GROUP];
         const double u0 = rec[11 * GROUP], u1 = rec[12 * GROUP], u2 = rec[13 * GROUP];
         const double Pg0 = ldp<SP>(&P.g0);
+        const double sm2 = sm + sm;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
+            // half of d(C u)_r / dq
             double j0, j1, j2, j3;
             if (r == 0) {
-                j0 = 2.0 * (q2 * u2 - q3 * u1);             j1 = 2.0 * (q2 * u1 + q3 * u2);
-                j2 = 2.0 * (q1 * u1 + q0 * u2) - 4.0 * q2 * u0; j3 = 2.0 * (q1 * u2 - q0 * u1) - 4.0 * q3 * u0;
+                j0 = q2 * u2 - q3 * u1;                     j1 = q2 * u1 + q3 * u2;
+                j2 = fma(-2.0 * q2, u0, q1 * u1 + q0 * u2); j3 = fma(-2.0 * q3, u0, q1 * u2 - q0 * u1);
             } else if (r == 1) {
-                j0 = 2.0 * (q3 * u0 - q1 * u2);             j1 = 2.0 * (q2 * u0 - q0 * u2) - 4.0 * q1 * u1;
-                j2 = 2.0 * (q1 * u0 + q3 * u2);             j3 = 2.0 * (q0 * u0 + q2 * u2) - 4.0 * q3 * u1;
+                j0 = q3 * u0 - q1 * u2;                     j1 = fma(-2.0 * q1, u1, q2 * u0 - q0 * u2);
+                j2 = q1 * u0 + q3 * u2;                     j3 = fma(-2.0 * q3, u1, q0 * u0 + q2 * u2);
             } else {
-                j0 = 2.0 * (q1 * u1 - q2 * u0);             j1 = 2.0 * (q3 * u0 + q0 * u1) - 4.0 * q1 * u2;
-                j2 = 2.0 * (q3 * u1 - q0 * u0) - 4.0 * q2 * u2; j3 = 2.0 * (q1 * u0 + q2 * u1);
+                j0 = q1 * u1 - q2 * u0;                     j1 = fma(-2.0 * q1, u2, q3 * u0 + q0 * u1);
+                j2 = fma(-2.0 * q2, u2, q3 * u1 - q0 * u0); j3 = q1 * u0 + q2 * u1;
             }
             double vv0 = 0.0, vv1 = 0.0, vv2 = 0.0;
             if (aero_rec) {
                 const double b0 = rec[(34 + 3 * r) * GROUP], b1 = rec[(35 + 3 * r) * GROUP], b2 = rec[(36 + 3 * r) * GROUP];
-                // db/dq rows: {0, 0, -4 q2, -4 q3}, {2 q3, 2 q2, 2 q1, 2 q0}, {-2 q2, 2 q3, -2 q0, 2 q1}
-                j0 += b0 * 0.0 + b1 * (2.0 * q3) + b2 * (-2.0 * q2);
-                j1 += b0 * 0.0 + b1 * (2.0 * q2) + b2 * (2.0 * q3);
-                j2 += b0 * (-4.0 * q2) + b1 * (2.0 * q1) + b2 * (-2.0 * q0);
-                j3 += b0 * (-4.0 * q3) + b1 * (2.0 * q0) + b2 * (2.0 * q1);
+                // half of dF_r/db * db/dq, db/dq rows: {0, 0, -4 q2, -4 q3}, {2 q3, 2 q2, 2 q1, 2 q0}, {-2 q2, 2 q3, -2 q0, 2 q1}
+                j0 = fma(b1, q3, fma(-b2, q2, j0));
+                j1 = fma(b1, q2, fma(b2, q3, j1));
+                j2 = fma(-2.0 * b0, q2, fma(b1, q1, fma(-b2, q0, j2)));
+                j3 = fma(-2.0 * b0, q3, fma(b1, q0, fma(b2, q1, j3)));
                 vv0 = sm * rec[(25 + 3 * r) * GROUP]; vv1 = sm * rec[(26 + 3 * r) * GROUP]; vv2 = sm * rec[(27 + 3 * r) * GROUP];
             }
             const double fvr = rec[(15 + r) * GROUP];
             st2(out + J_V + 8 * r + 0, -sm * (fvr + (r == 0 ? Pg0 : 0.0)), vv0);
             st2(out + J_V + 8 * r + 2, vv1, vv2);
-            st2(out + J_V + 8 * r + 4, sm * j0, sm * j1);
-            st2(out + J_V + 8 * r + 6, sm * j2, sm * j3);
+            st2(out + J_V + 8 * r + 4, sm2 * j0, sm2 * j1);
+            st2(out + J_V + 8 * r + 6, sm2 * j2, sm2 * j3);
         }
         // ---- direct (control / sigma) columns G[col][row], rows m, v0..2, w0..2 (7 per column)
         const double c00 = 1.0 - 2.0 * (q2 * q2 + q3 * q3), c01 = 2.0 * (q1 * q2 - q0 * q3), c02 = 2.0 * (q1 * q3 + q0 * q2);
@@ -343,19 +357,29 @@ __device__ __forceinline__ void produce_lean(const scvx_probinfo& P, bool aero_r
         const double gm = -ss * ldp<SP>(&P.a) / nu;
         const double r0 = ldp<SP>(&P.rTB[0]), r1 = ldp<SP>(&P.rTB[1]), r2 = ldp<SP>(&P.rTB[2]);
         double* G = out + J_G;
-        double bi[9];
+        // jBi * (rTB x e_j): rTB x e0 = (0, r2, -r1); x e1 = (-r2, 0, r0); x e2 = (r1, -r0, 0) — constant per parameter
+        // record: taken from the kernel arguments when the record is shared (SP), formed here otherwise
+        double kw[9];
+        if constexpr (SP) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) bi[k] = ldp<SP>(&P.jBi[k]);
-        // jBi * (rTB x e_j): rTB x e0 = (0, r2, -r1); x e1 = (-r2, 0, r0); x e2 = (r1, -r0, 0)
+            for (int k = 0; k < 9; ++k) kw[k] = Kw[k];
+        } else {
+            double bi[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) bi[k] = ldp<SP>(&P.jBi[k]);
+            kw[0] = bi[3] * r2 - bi[6] * r1; kw[1] = bi[4] * r2 - bi[7] * r1; kw[2] = bi[5] * r2 - bi[8] * r1;
+            kw[3] = bi[6] * r0 - bi[0] * r2; kw[4] = bi[7] * r0 - bi[1] * r2; kw[5] = bi[8] * r0 - bi[2] * r2;
+            kw[6] = bi[0] * r1 - bi[3] * r0; kw[7] = bi[1] * r1 - bi[4] * r0; kw[8] = bi[2] * r1 - bi[5] * r0;
+        }
         st2(G + 0, gm * u0, sm * c00); st2(G + 2, sm * c10, sm * c20);
-        st2(G + 4, ss * (bi[3] * r2 - bi[6] * r1), ss * (bi[4] * r2 - bi[7] * r1));
-        st2(G + 6, ss * (bi[5] * r2 - bi[8] * r1), gm * u1);
+        st2(G + 4, ss * kw[0], ss * kw[1]);
+        st2(G + 6, ss * kw[2], gm * u1);
         st2(G + 8, sm * c01, sm * c11);
-        st2(G + 10, sm * c21, ss * (bi[6] * r0 - bi[0] * r2));
-        st2(G + 12, ss * (bi[7] * r0 - bi[1] * r2), ss * (bi[8] * r0 - bi[2] * r2));
+        st2(G + 10, sm * c21, ss * kw[3]);
+        st2(G + 12, ss * kw[4], ss * kw[5]);
         st2(G + 14, gm * u2, sm * c02); st2(G + 16, sm * c12, sm * c22);
-        st2(G + 18, ss * (bi[0] * r1 - bi[3] * r0), ss * (bi[1] * r1 - bi[4] * r0));
-        st2(G + 20, ss * (bi[2] * r1 - bi[5] * r0), scale * rec[14 * GROUP]);
+        st2(G + 18, ss * kw[6], ss * kw[7]);
+        st2(G + 20, ss * kw[8], scale * rec[14 * GROUP]);
         st2(G + 22, scale * rec[15 * GROUP], scale * rec[16 * GROUP]);
         st2(G + 24, scale * rec[17 * GROUP], scale * rec[22 * GROUP]);
         st2(G + 26, scale * rec[23 * GROUP], scale * rec[24 * GROUP]);
@@ -375,6 +399,11 @@ struct FullCol {
 // Rows are processed in cascade order (r, v, m, q, w): a row block is overwritten only after every block that
 // reads its old stage value has been formed.
 //
+// Slot roles.  Slot A of every lane carries a CONTROL-type column (B- / B+ / Sigma, or the light column d/dm): the only
+// columns with a direct term alpha * G and a non-zero mass row.  Slot B carries a STATE-type column (d/dw, d/dq, or the
+// light column d/dv0): mdot does not depend on the state, so its mass row is identically zero and it has no direct
+// term — the code of slot B omits the J_vm * Y_m products, the G terms and the whole m row (11 of 163 FMAs per stage).
+//
 // Stage-tangent form of rk4.  The producer scales the Jacobian blocks of stage i by c_i (the factor of
 // Y_{i+1} = S + c_i K_i; h/6 for the final stage), so a row's chain of FMAs started FROM S yields the next stage
 // tangent directly (no separate K, no multiply to start the chain).  With T = Y_2 + 2 Y_3 + Y_4 and kappa = h/(3 s)
@@ -386,8 +415,10 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
                                                const int l8, const double pc, const double tw, const double cr,
                                                const double kappa, uint64_t* empty_bar, const int lane) {
     constexpr bool last = LAST;
-    const double alA = (l8 < 3) ? 1.0 - pc : (l8 == 3 ? 1.0 : 0.0), alB = (l8 < 3) ? pc : 0.0;
-    const double dsA = (l8 == 3) ? 1.0 : 0.0;
+    // slot A: lanes 0..2 B- (alpha = 1 - pc), 3..5 B+ (alpha = pc), 6 Sigma (direct term = the f column, alpha = 1),
+    // 7 the light column d/dm (no direct term)
+    const double alA = (l8 < 3) ? 1.0 - pc : (l8 < 6 ? pc : (l8 == 6 ? 1.0 : 0.0));
+    const double dsA = (l8 == 6) ? 1.0 : 0.0;
     const double* Gc = J + J_G + 7 * gcol;
     auto init = [&](const FullCol& F, const int idx) -> double {
         if constexpr (!last) return F.S[idx];
@@ -419,17 +450,17 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
             const double gg = Gc[1 + row];
             kA[row] = fma(c01.x, FA.Y[0], fma(c01.y, FA.Y[1], fma(c23.x, FA.Y[2], fma(c23.y, FA.Y[3],
                       fma(qa.x, FA.Y[4], fma(qa.y, FA.Y[5], fma(qb.x, FA.Y[6], fma(qb.y, FA.Y[7], fma(alA, gg, init(FA, 1 + row))))))))));
-            kB[row] = fma(c01.x, FB.Y[0], fma(c01.y, FB.Y[1], fma(c23.x, FB.Y[2], fma(c23.y, FB.Y[3],
-                      fma(qa.x, FB.Y[4], fma(qa.y, FB.Y[5], fma(qb.x, FB.Y[6], fma(qb.y, FB.Y[7], fma(alB, gg, init(FB, 1 + row))))))))));
+            kB[row] = fma(c01.y, FB.Y[1], fma(c23.x, FB.Y[2], fma(c23.y, FB.Y[3],
+                      fma(qa.x, FB.Y[4], fma(qa.y, FB.Y[5], fma(qb.x, FB.Y[6], fma(qb.y, FB.Y[7], init(FB, 1 + row))))))));
         }
 #pragma unroll
         for (int r = 0; r < 3; ++r) { fin(FA, 1 + r, kA[r]); fin(FB, 1 + r, kB[r]); }
     }
-    // ---- m row: alpha * G_m
+    // ---- m row: alpha * G_m (slot A only: the mass row of a state-type column is identically zero)
     {
         const double gmv = Gc[0];
-        const double a0 = fma(alA, gmv, init(FA, 0)), b0 = fma(alB, gmv, init(FB, 0));
-        fin(FA, 0, a0); fin(FB, 0, b0);
+        const double a0 = fma(alA, gmv, init(FA, 0));
+        fin(FA, 0, a0);
     }
     // ---- q rows: Omega(hw) Y_q + Omega(Y_w) hq + dsigma * f_q   (only slot A can hold the sigma column)
     {
@@ -460,9 +491,9 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
         kA[0] = fma(j01.x, FA.Y[8], fma(j01.y, FA.Y[9], fma(j23.x, FA.Y[10], fma(alA, g0, init(FA, 8)))));
         kA[1] = fma(j23.y, FA.Y[8], fma(j45.x, FA.Y[9], fma(j45.y, FA.Y[10], fma(alA, g1, init(FA, 9)))));
         kA[2] = fma(j67.x, FA.Y[8], fma(j67.y, FA.Y[9], fma(j8, FA.Y[10], fma(alA, g2, init(FA, 10)))));
-        kB[0] = fma(j01.x, FB.Y[8], fma(j01.y, FB.Y[9], fma(j23.x, FB.Y[10], fma(alB, g0, init(FB, 8)))));
-        kB[1] = fma(j23.y, FB.Y[8], fma(j45.x, FB.Y[9], fma(j45.y, FB.Y[10], fma(alB, g1, init(FB, 9)))));
-        kB[2] = fma(j67.x, FB.Y[8], fma(j67.y, FB.Y[9], fma(j8, FB.Y[10], fma(alB, g2, init(FB, 10)))));
+        kB[0] = fma(j01.x, FB.Y[8], fma(j01.y, FB.Y[9], fma(j23.x, FB.Y[10], init(FB, 8))));
+        kB[1] = fma(j23.y, FB.Y[8], fma(j45.x, FB.Y[9], fma(j45.y, FB.Y[10], init(FB, 9))));
+        kB[2] = fma(j67.x, FB.Y[8], fma(j67.y, FB.Y[9], fma(j8, FB.Y[10], init(FB, 10))));
         // all reads of the ring slot are done: hand it back (per-stage hand-over only; the step-synchronised kernel
         // passes a null barrier and releases a whole step at once)
         if (empty_bar != nullptr) {
