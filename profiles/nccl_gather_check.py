@@ -17,10 +17,11 @@ X, U, sigma, _ = workloads.monte_carlo_batch(prob, K, B, 7, sigma_range=(0.8, 1.
 b0, b1 = sharding.shard_range(B, rank, world)
 blocks, err, tlb = dynamics.linearize_batch(cache, X[b0:b1], U[b0:b1], sigma[b0:b1], 1 / (K + 1))
 full = sharding.gather_shards(torch.from_numpy(blocks).to(dev))
+rooted = sharding.gather_to_root(torch.from_numpy(blocks).to(dev), dst=0)        # send/recv into one result on rank 0
 ok, chk = sharding.reduce_status(bool(np.isfinite(blocks).all()), float(blocks[:, :, 0, :].sum()), dev)
 if rank == 0:
     ref, _, _ = dynamics.linearize_batch(cache, X, U, sigma, 1 / (K + 1))
-    same = np.array_equal(full.cpu().numpy(), ref)
+    same = np.array_equal(full.cpu().numpy(), ref) and np.array_equal(rooted.cpu().numpy(), ref)
     print(f"ranks {world}: gathered {tuple(full.shape)} identical to the single-GPU result: {same}; status ok {ok}; "
           f"checksum {chk:.12e} vs {ref[:, :, 0, :].sum():.12e}")
     assert same and ok

@@ -128,25 +128,22 @@ __global__ void __launch_bounds__(VT, VALUE_MINBLOCKS) stage_value_kernel(const 
 #pragma unroll
             for (int c = 0; c < 3; ++c) uc[c] = (1.0 - pc) * um[c] + pc * up[c];
             rhs_value<true, SCVX_A_SMEM_TABLES, SP>(P, tbl, y, uc, f, Fv, Fb);
-            // record: m, v, q, w, u, f_m, f_v, f_q, f_w [, dF/dv, dF/db]
+            // record: m, v, q, w, f_v [, dF/dv, dF/db]  (u, f_m, f_q, f_w are re-formed by the producers)
             double* rp = rec + (size_t)(it * 4 + st) * ((size_t)a.rec_n * GROUP);
             if (a.rec_n == REC_AERO) {
 #pragma unroll
                 for (int r = 0; r < 3; ++r)
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        rp[(25 + 3 * r + c) * GROUP] = Fv[r][c];
-                        rp[(34 + 3 * r + c) * GROUP] = Fb[r][c];
+                        rp[(R_AV + 3 * r + c) * GROUP] = Fv[r][c];
+                        rp[(R_AB + 3 * r + c) * GROUP] = Fb[r][c];
                     }
             }
             rp[0 * GROUP] = y[0];
 #pragma unroll
             for (int r = 0; r < 10; ++r) rp[(1 + r) * GROUP] = y[4 + r];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) rp[(11 + c) * GROUP] = uc[c];
-            rp[14 * GROUP] = f[0];
-#pragma unroll
-            for (int r = 0; r < 10; ++r) rp[(15 + r) * GROUP] = f[4 + r];
+            for (int c = 0; c < 3; ++c) rp[(R_FV + c) * GROUP] = f[4 + c];
             const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
             const double cy = (st == 2) ? s : 0.5 * s;
             {
@@ -286,6 +283,7 @@ static_assert(PRODUCER_REGS == 88, "register split");
 struct __align__(16) StepSmem {
     double ring[8][GROUP][NJ];               // [half * 4 + stage][interval][entry]
     double recbuf[4][REC_MAX * GROUP];       // stage records of the step being produced (TMA destination)
+    double unode[4][6][GROUP];               // per producer warp: node controls u-(3), u+(3) of the pass's 32 intervals
     uint64_t full_step[2];
     uint64_t empty_step[2];
     uint64_t recfull[2][4];                  // [half][stage]: one waiting warp per barrier (it observes every phase)
@@ -320,6 +318,9 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
     const int colA = (l8 < 7) ? 14 + l8 : 0;
     const int colB = (l8 < 3) ? 11 + l8 : (l8 < 7 ? 4 + l8 : 4);
     const int gcol = (l8 < 3) ? l8 : (l8 < 6 ? l8 - 3 : 3);
+    // FOH weight of slot A's direct term: alpha = cA0 + cA1 * pc  (B-: 1 - pc, B+: pc, Sigma: 1, d/dm: 0)
+    const double cA0 = (l8 < 3 || l8 == 6) ? 1.0 : 0.0, cA1 = (l8 < 3) ? -1.0 : (l8 < 6 ? 1.0 : 0.0);
+    const double dsA = (l8 == 6) ? 1.0 : 0.0;
 
     const int kq = warp & 3;                            // stage (within a step) this warp produces
     // rk4 factor folded into the Jacobian blocks of that stage (consume_stage8): Y_{i+1} = S + c_i K_i, h/6 for the last
@@ -353,6 +354,14 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
                 const int b = (a.first + t) / ni;
                 const scvx_probinfo& P = SP ? a.Pc : bt.P[bt.n_params == 1 ? 0 : b];
                 const double sigma = __ldg(bt.sigma + b);
+                {   // the interval's node controls (the stage control is their FOH blend, re-formed per record)
+                    const int ii = (a.first + t) - b * ni;
+                    const double* uin = bt.U + ((size_t)b * bt.n_nodes + ii) * 3;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) sm.unode[kq][c][lane] = __ldg(uin + c);
+                    __syncwarp();
+                }
+                double pca = 0.0;
 #pragma unroll 1
                 for (int ls = 0; ls < npts; ++ls, ++n) {
                     const bool more = n + 1 < total_steps;
@@ -364,8 +373,10 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
                     const int half = n & 1, use = n >> 1;
                     mbar_wait(&sm.recfull[half][kq], (uint32_t)(use & 1));      // this warp is the only waiter of recfull[half][kq]
                     if (use > 0) mbar_wait(&sm.empty_step[half], (uint32_t)((use - 1) & 1));
+                    const double pc = (kq == 0) ? pca : (kq == 3 ? pca + pcs : pca + 0.5 * pcs);     // as the value kernel
+                    pca += pcs;
                     produce_lean<SP>(P, a.Kw, a.Tw, a.rec_n == REC_AERO, sigma, stage_scale, sm.recbuf[kq] + lane,
-                                     &sm.ring[half * 4 + kq][lane][0]);
+                                     &sm.unode[kq][0][lane], pc, &sm.ring[half * 4 + kq][lane][0]);
                     mbar_arrive(&sm.full_step[half]);
                     __syncwarp();                        // every lane has finished reading recbuf[kq]
                     if (lane == 0 && more) issue_record(n + 1, nit, nls);
@@ -414,10 +425,10 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
 #pragma unroll 1
             for (int k = 0; k < 3; ++k) {
                 const double pc = (k == 0) ? pca : pca + 0.5 * pcs;
-                consume_stage8<false>(FA, FB, J0 + k * (GROUP * NJ), gcol, l8, pc, k == 1 ? 2.0 : 1.0,
+                consume_stage8<false>(FA, FB, J0 + k * (GROUP * NJ), gcol, fma(cA1, pc, cA0), dsA, k == 1 ? 2.0 : 1.0,
                                       k == 0 ? h6 : 2.0 * h6, kappa, nullptr, lane);
             }
-            consume_stage8<true>(FA, FB, J0 + 3 * (GROUP * NJ), gcol, l8, pca + pcs, 1.0, h6, kappa, nullptr, lane);
+            consume_stage8<true>(FA, FB, J0 + 3 * (GROUP * NJ), gcol, fma(cA1, pca + pcs, cA0), dsA, 1.0, h6, kappa, nullptr, lane);
             __syncwarp();
             mbar_arrive_lane0(&sm.empty_step[half], lane);           // the four slabs of this step are free again
             pca += pcs;
@@ -473,6 +484,15 @@ cudaError_t scvx_staged_init() {
     const int vs = SCVX_A_SMEM_TABLES ? 232448 : (int)LIGHT_SMEM_BYTES;
     cudaError_t e = cudaFuncSetAttribute(stage_value_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, vs);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(stage_value_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vs);
+#ifndef SCVX_A_CARVEOUT
+#define SCVX_A_CARVEOUT 0
+#endif
+    // the value kernel needs 2 x 24.5 KB of shared memory per SM; the driver's default carve-out for it is 102 KB.  A smaller
+    // one leaves more of the 256 KB to L1, where the spline coefficients live (A/B: profiles/r2_value_carveout.txt)
+    if (SCVX_A_CARVEOUT > 0 && !SCVX_A_SMEM_TABLES) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(stage_value_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, SCVX_A_CARVEOUT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(stage_value_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, SCVX_A_CARVEOUT);
+    }
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tangent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tangent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
     return e;

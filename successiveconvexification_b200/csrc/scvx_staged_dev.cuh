@@ -7,8 +7,14 @@
 namespace {
 
 
-constexpr int REC_EXO = 25;      // stage record entries: m, v(3), q(4), w(3), u(3), f_m, f_v(3), f_q(4), f_w(3)
-constexpr int REC_AERO = 43;     // + dF_aero/dv (9, row-major) + dF_aero/db (9), b = C(q) e1
+// Stage record (value kernel -> producers).  The value kernel is bound by the HBM WRITE rate of these records (round 2:
+// 1.62 GB per chunk in 0.42 ms = 3.9 TB/s), so the record holds only what cannot be re-formed cheaply: the stage state,
+// f_v (it contains the aero force) and the aero Jacobians.  The stage control (FOH of the interval's two node controls,
+// which the producers keep in shared memory), f_m = -a |u|, f_q = Omega(w) q / 2 and f_w = jBi (rTB x u - w x jB w) are
+// re-formed by the producers (~45 FP64 operations per record).
+constexpr int REC_EXO = 14;      // stage record entries: m, v(3), q(4), w(3), f_v(3)
+constexpr int REC_AERO = 32;     // + dF_aero/dv (9, row-major) + dF_aero/db (9), b = C(q) e1
+constexpr int R_FV = 11, R_AV = 14, R_AB = 23;
 constexpr int REC_MAX = REC_AERO;
 constexpr int NJ = 78;           // Jacobian record entries per interval per stage (2 x odd: conflict-free STS.128)
 constexpr int GROUP = 32;        // intervals per CTA pass
@@ -261,62 +267,35 @@ __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpre
 template <bool SP = false>
 __device__ __forceinline__ void produce_lean(const scvx_probinfo& P, const double* __restrict__ Kw,
                                              const double* __restrict__ Tw, bool aero_rec, double sigma,
-                                             double scale, const double* __restrict__ rec, double* __restrict__ out) {
+                                             double scale, const double* __restrict__ rec, const double* __restrict__ unode,
+                                             double pc, double* __restrict__ out) {
     const double ss = sigma * scale;
     const double hs = 0.5 * ss;
     const double sm = ss / rec[0];
-    // ---- quadrature entries, hw, hq
+    // ---- quadrature entries, hw, hq; f_q = Omega(w) q / 2 is re-formed here (dynamics.jl:46-52, 68)
     {
         const double q0 = rec[4 * GROUP], q1 = rec[5 * GROUP], q2 = rec[6 * GROUP], q3 = rec[7 * GROUP];
         st2(out + J_HQ + 0, hs * q0, hs * q1); st2(out + J_HQ + 2, hs * q2, hs * q3);
         const double v0 = rec[1 * GROUP], v1 = rec[2 * GROUP], v2 = rec[3 * GROUP];
-        const double f0 = rec[18 * GROUP], f1 = rec[19 * GROUP], f2 = rec[20 * GROUP], f3 = rec[21 * GROUP];
-        st2(out + J_FRQ + 0, v0, v1); st2(out + J_FRQ + 2, v2, scale * f0);
-        st2(out + J_FRQ + 4, scale * f1, scale * f2); st2(out + J_FRQ + 6, scale * f3, sigma);
-        st2(out + J_FRQ + 8, 0.0, 0.0);
-    }
-    // ---- rotational block: Jww = -ss * jBi * ([w]x jB - [jB w]x), and hw.  The block is linear in w; with a shared
-    // parameter record its three constant 3 x 3 factors come from the kernel arguments (27 FMAs instead of 54 operations).
-    {
         const double w0 = rec[8 * GROUP], w1 = rec[9 * GROUP], w2 = rec[10 * GROUP];
-        if constexpr (SP) {
-            const double s0 = ss * w0, s1 = ss * w1, s2 = ss * w2;
-            auto jw = [&](int k) { return fma(s2, Tw[18 + k], fma(s1, Tw[9 + k], s0 * Tw[k])); };
-            st2(out + J_WW + 0, jw(0), jw(1)); st2(out + J_WW + 2, jw(2), jw(3)); st2(out + J_WW + 4, jw(4), jw(5));
-            st2(out + J_WW + 6, jw(6), jw(7)); st2(out + J_WW + 8, jw(8), hs * w0);
-        } else {
-            double Jw[9];
-            double M[3][3];
-            {
-                double jB[9];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) jB[k] = ldp<SP>(&P.jB[k]);
-                const double L0 = jB[0] * w0 + jB[3] * w1 + jB[6] * w2;
-                const double L1 = jB[1] * w0 + jB[4] * w1 + jB[7] * w2;
-                const double L2 = jB[2] * w0 + jB[5] * w1 + jB[8] * w2;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const double a0 = jB[3 * c], a1 = jB[3 * c + 1], a2 = jB[3 * c + 2];
-                    M[0][c] = w1 * a2 - w2 * a1; M[1][c] = w2 * a0 - w0 * a2; M[2][c] = w0 * a1 - w1 * a0;
-                }
-                M[0][1] += L2; M[0][2] -= L1; M[1][0] -= L2; M[1][2] += L0; M[2][0] += L1; M[2][1] -= L0;
-            }
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const double b0 = ldp<SP>(&P.jBi[r]), b1 = ldp<SP>(&P.jBi[r + 3]), b2 = ldp<SP>(&P.jBi[r + 6]);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) Jw[3 * r + c] = -ss * (b0 * M[0][c] + b1 * M[1][c] + b2 * M[2][c]);
-            }
-            st2(out + J_WW + 0, Jw[0], Jw[1]); st2(out + J_WW + 2, Jw[2], Jw[3]); st2(out + J_WW + 4, Jw[4], Jw[5]);
-            st2(out + J_WW + 6, Jw[6], Jw[7]); st2(out + J_WW + 8, Jw[8], hs * w0);
-        }
-        st2(out + J_HW + 1, hs * w1, hs * w2);
+        const double hc = 0.5 * scale;
+        const double f0 = hc * (-(w0 * q1) - w1 * q2 - w2 * q3);
+        const double f1 = hc * (w0 * q0 + w2 * q2 - w1 * q3);
+        const double f2 = hc * (w1 * q0 - w2 * q1 + w0 * q3);
+        const double f3 = hc * (w2 * q0 + w1 * q1 - w0 * q2);
+        st2(out + J_FRQ + 0, v0, v1); st2(out + J_FRQ + 2, v2, f0);
+        st2(out + J_FRQ + 4, f1, f2); st2(out + J_FRQ + 6, f3, sigma);
+        st2(out + J_FRQ + 8, 0.0, 0.0);
     }
     // ---- v rows: [d/dm, d/dv (3), d/dq (4)] per row.  The factor 2 of d(C u)/dq and of db/dq is folded into sm2 = 2 sm;
     // the structurally zero entries of db/dq (row 0: {0, 0, -4 q2, -4 q3}) are not multiplied out.
     {
         const double q0 = rec[4 * GROUP], q1 = rec[5 * GROUP], q2 = rec[6 * GROUP], q3 = rec[7 * GROUP];
-        const double u0 = rec[11 * GROUP], u1 = rec[12 * GROUP], u2 = rec[13 * GROUP];
+        // stage control: current_control (dynamics.jl:108-110) of the interval's node controls (unode: u-(3), u+(3), stride GROUP)
+        const double opc = 1.0 - pc;
+        const double u0 = opc * unode[0 * GROUP] + pc * unode[3 * GROUP];
+        const double u1 = opc * unode[1 * GROUP] + pc * unode[4 * GROUP];
+        const double u2 = opc * unode[2 * GROUP] + pc * unode[5 * GROUP];
         const double Pg0 = ldp<SP>(&P.g0);
         const double sm2 = sm + sm;
 #pragma unroll
@@ -335,15 +314,15 @@ __device__ __forceinline__ void produce_lean(const scvx_probinfo& P, const doubl
             }
             double vv0 = 0.0, vv1 = 0.0, vv2 = 0.0;
             if (aero_rec) {
-                const double b0 = rec[(34 + 3 * r) * GROUP], b1 = rec[(35 + 3 * r) * GROUP], b2 = rec[(36 + 3 * r) * GROUP];
+                const double b0 = rec[(R_AB + 3 * r) * GROUP], b1 = rec[(R_AB + 1 + 3 * r) * GROUP], b2 = rec[(R_AB + 2 + 3 * r) * GROUP];
                 // half of dF_r/db * db/dq, db/dq rows: {0, 0, -4 q2, -4 q3}, {2 q3, 2 q2, 2 q1, 2 q0}, {-2 q2, 2 q3, -2 q0, 2 q1}
                 j0 = fma(b1, q3, fma(-b2, q2, j0));
                 j1 = fma(b1, q2, fma(b2, q3, j1));
                 j2 = fma(-2.0 * b0, q2, fma(b1, q1, fma(-b2, q0, j2)));
                 j3 = fma(-2.0 * b0, q3, fma(b1, q0, fma(b2, q1, j3)));
-                vv0 = sm * rec[(25 + 3 * r) * GROUP]; vv1 = sm * rec[(26 + 3 * r) * GROUP]; vv2 = sm * rec[(27 + 3 * r) * GROUP];
+                vv0 = sm * rec[(R_AV + 3 * r) * GROUP]; vv1 = sm * rec[(R_AV + 1 + 3 * r) * GROUP]; vv2 = sm * rec[(R_AV + 2 + 3 * r) * GROUP];
             }
-            const double fvr = rec[(15 + r) * GROUP];
+            const double fvr = rec[(R_FV + r) * GROUP];
             st2(out + J_V + 8 * r + 0, -sm * (fvr + (r == 0 ? Pg0 : 0.0)), vv0);
             st2(out + J_V + 8 * r + 2, vv1, vv2);
             st2(out + J_V + 8 * r + 4, sm2 * j0, sm2 * j1);
@@ -379,10 +358,63 @@ __device__ __forceinline__ void produce_lean(const scvx_probinfo& P, const doubl
         st2(G + 12, ss * kw[4], ss * kw[5]);
         st2(G + 14, gm * u2, sm * c02); st2(G + 16, sm * c12, sm * c22);
         st2(G + 18, ss * kw[6], ss * kw[7]);
-        st2(G + 20, ss * kw[8], scale * rec[14 * GROUP]);
-        st2(G + 22, scale * rec[15 * GROUP], scale * rec[16 * GROUP]);
-        st2(G + 24, scale * rec[17 * GROUP], scale * rec[22 * GROUP]);
-        st2(G + 26, scale * rec[23 * GROUP], scale * rec[24 * GROUP]);
+        // ---- rotational block: Jww = -ss * jBi * ([w]x jB - [jB w]x), and hw.  The block is linear in w; with a shared
+        // parameter record its three constant 3 x 3 factors come from the kernel arguments (27 FMAs instead of 54 operations).
+        double fwq[3];
+        {
+            const double w0 = rec[8 * GROUP], w1 = rec[9 * GROUP], w2 = rec[10 * GROUP];
+            // fwq = -jBi (w x jB w), the rate-dependent part of f_w (the producer adds jBi (rTB x u) below).  d(wdot)/dw is
+            // linear in w and  (d(wdot)/dw) w = -2 jBi (w x jB w),  so fwq = (Jww / ss) w / 2
+            if constexpr (SP) {
+                const double s0 = ss * w0, s1 = ss * w1, s2 = ss * w2;
+                auto jw = [&](int k) { return fma(s2, Tw[18 + k], fma(s1, Tw[9 + k], s0 * Tw[k])); };
+                const double j0 = jw(0), j1 = jw(1), j2 = jw(2), j3 = jw(3), j4 = jw(4), j5 = jw(5), j6 = jw(6), j7 = jw(7), j8 = jw(8);
+                st2(out + J_WW + 0, j0, j1); st2(out + J_WW + 2, j2, j3); st2(out + J_WW + 4, j4, j5);
+                st2(out + J_WW + 6, j6, j7); st2(out + J_WW + 8, j8, hs * w0);
+                const double hi = 0.5 / ss;
+                fwq[0] = hi * fma(j2, w2, fma(j1, w1, j0 * w0));
+                fwq[1] = hi * fma(j5, w2, fma(j4, w1, j3 * w0));
+                fwq[2] = hi * fma(j8, w2, fma(j7, w1, j6 * w0));
+            } else {
+                double Jw[9];
+                double M[3][3];
+                {
+                    double jB[9];
+    #pragma unroll
+                    for (int k = 0; k < 9; ++k) jB[k] = ldp<SP>(&P.jB[k]);
+                    const double L0 = jB[0] * w0 + jB[3] * w1 + jB[6] * w2;
+                    const double L1 = jB[1] * w0 + jB[4] * w1 + jB[7] * w2;
+                    const double L2 = jB[2] * w0 + jB[5] * w1 + jB[8] * w2;
+    #pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const double a0 = jB[3 * c], a1 = jB[3 * c + 1], a2 = jB[3 * c + 2];
+                        M[0][c] = w1 * a2 - w2 * a1; M[1][c] = w2 * a0 - w0 * a2; M[2][c] = w0 * a1 - w1 * a0;
+                    }
+                    M[0][1] += L2; M[0][2] -= L1; M[1][0] -= L2; M[1][2] += L0; M[2][0] += L1; M[2][1] -= L0;
+                }
+    #pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double b0 = ldp<SP>(&P.jBi[r]), b1 = ldp<SP>(&P.jBi[r + 3]), b2 = ldp<SP>(&P.jBi[r + 6]);
+    #pragma unroll
+                    for (int c = 0; c < 3; ++c) Jw[3 * r + c] = -ss * (b0 * M[0][c] + b1 * M[1][c] + b2 * M[2][c]);
+                }
+                st2(out + J_WW + 0, Jw[0], Jw[1]); st2(out + J_WW + 2, Jw[2], Jw[3]); st2(out + J_WW + 4, Jw[4], Jw[5]);
+                st2(out + J_WW + 6, Jw[6], Jw[7]); st2(out + J_WW + 8, Jw[8], hs * w0);
+                const double hi = 0.5 / ss;
+                fwq[0] = hi * fma(Jw[2], w2, fma(Jw[1], w1, Jw[0] * w0));
+                fwq[1] = hi * fma(Jw[5], w2, fma(Jw[4], w1, Jw[3] * w0));
+                fwq[2] = hi * fma(Jw[8], w2, fma(Jw[7], w1, Jw[6] * w0));
+            }
+            st2(out + J_HW + 1, hs * w1, hs * w2);
+        }
+        // sigma column (the unscaled rhs): f_m = -a |u|, f_v from the record, f_w = jBi (rTB x u) + fwq
+        const double fw0 = fma(kw[6], u2, fma(kw[3], u1, fma(kw[0], u0, fwq[0])));
+        const double fw1 = fma(kw[7], u2, fma(kw[4], u1, fma(kw[1], u0, fwq[1])));
+        const double fw2 = fma(kw[8], u2, fma(kw[5], u1, fma(kw[2], u0, fwq[2])));
+        st2(G + 20, ss * kw[8], -(scale * ldp<SP>(&P.a)) * nu);
+        st2(G + 22, scale * rec[R_FV * GROUP], scale * rec[(R_FV + 1) * GROUP]);
+        st2(G + 24, scale * rec[(R_FV + 2) * GROUP], scale * fw0);
+        st2(G + 26, scale * fw1, scale * fw2);
     }
 }
 
@@ -412,13 +444,11 @@ struct FullCol {
 // 11 % fewer FP64 instructions per stage than forming K, acc += w K, Y = S + c K.
 template <bool LAST>
 __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const double* __restrict__ J, const int gcol,
-                                               const int l8, const double pc, const double tw, const double cr,
+                                               const double alA, const double dsA, const double tw, const double cr,
                                                const double kappa, uint64_t* empty_bar, const int lane) {
     constexpr bool last = LAST;
-    // slot A: lanes 0..2 B- (alpha = 1 - pc), 3..5 B+ (alpha = pc), 6 Sigma (direct term = the f column, alpha = 1),
-    // 7 the light column d/dm (no direct term)
-    const double alA = (l8 < 3) ? 1.0 - pc : (l8 < 6 ? pc : (l8 == 6 ? 1.0 : 0.0));
-    const double dsA = (l8 == 6) ? 1.0 : 0.0;
+    // slot A: lanes 0..2 B- (alA = 1 - pc), 3..5 B+ (alA = pc), 6 Sigma (direct term = the f column, alA = 1, dsA = 1),
+    // 7 the light column d/dm (no direct term): alA = cA0 + cA1 * pc with per-lane constants, formed by the caller
     const double* Gc = J + J_G + 7 * gcol;
     auto init = [&](const FullCol& F, const int idx) -> double {
         if constexpr (!last) return F.S[idx];

@@ -67,3 +67,18 @@ def test_fails_loudly_without_gpu():
     from successiveconvexification_b200.dynamics import DeviceContext
     with pytest.raises(_lib.ScvxError, match="no CPU fallback"):
         DeviceContext()
+
+
+def test_julia_shim_overrides_sit_inside_the_module():
+    """The replaced `Dynamics.*` methods use LinPoint / LinRes / IntegratorCache unqualified; master.jl exports them from
+    RocketlandDefns but never brings them into Main, so the definitions must sit inside `module SCvxB200` (which does
+    `using ..RocketlandDefns` and `import ..Dynamics`).  The shim has never run under Julia; this pins its structure."""
+    shim = open(os.path.join(ROOT, "julia", "SCvxB200.jl")).read()
+    start, end = shim.index("module SCvxB200"), shim.rindex("end # module")
+    assert shim[end:].strip() == "end # module"
+    assert "using ..RocketlandDefns" in shim[start:end] and "import ..Dynamics" in shim[start:end]
+    for name in ("linearize_dynamics", "predict_state", "simulate_zygote", "sensitivity_zygote"):
+        assert start < shim.index(f"function Dynamics.{name}(") < end
+    code = "\n".join(l.split("#")[0] for l in shim[start:end].splitlines())
+    assert "SCvxB200." not in code                      # no self-qualified names inside the module
+    assert "live_mode" in code and "MODE_TEXTBOOK" in code
