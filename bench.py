@@ -388,6 +388,22 @@ def main():
     else:
         ok = finite
     elapsed_ms = float(t.item())
+    # result collection over NCCL: not part of the timed step — a slab of every rank's blocks is sent to rank 0
+    # (sharding.gather_to_root: send/recv into one result tensor, no padding, nothing on the other ranks) and checked there
+    gather = None
+    if world > 1:
+        slab = dOut[:64].contiguous()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        g0.record()
+        rooted = sharding.gather_to_root(slab, dst=0)
+        g1.record()
+        torch.cuda.synchronize()
+        if rank == 0:
+            same = bool(torch.equal(rooted[:64], slab)) and rooted.shape[0] == 64 * world and bool(torch.isfinite(rooted).all())
+            gather = {"call": "sharding.gather_to_root (NCCL send/recv)", "trajectories_per_rank": 64,
+                      "bytes_collected": int(rooted.nbytes), "ms": g0.elapsed_time(g1), "ok": same}
+            del rooted
     total_intervals = B * ni * world
     value = total_intervals * args.steps / (elapsed_ms * 1e-3)
 
@@ -536,7 +552,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "parity": parity, "assembly": assembly, "extra": extra, "results_finite": ok,
+            "cpu_baseline": cpu, "parity": parity, "assembly": assembly, "extra": extra, "gather": gather, "results_finite": ok,
             "kernel": args.kernel}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)

@@ -1,4 +1,4 @@
-"""Static SASS instruction evidence per kernel (cuobjdump -sass of the built library) -> profiles/r1_sass_evidence.txt."""
+"""Static SASS instruction evidence per kernel (cuobjdump -sass of the built library) -> profiles/r2_sass_evidence.txt."""
 import collections, os, re, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "successiveconvexification_b200", "libscvx_b200.so")
@@ -17,5 +17,5 @@ for m in re.finditer(r"Function : (\S+)\n(.*?)(?=\n\s*Function :|\Z)", txt, re.S
         if k.startswith(('UBLKCP', 'UBLKPF', 'USETMAXREG', 'SYNCS')) or k in ('LDS.128', 'STS.128', 'LDG.E.64.CONSTANT'):
             agg[k] += v
     out.append(f"\n{short}\n  total {sum(ops.values())}  " + "  ".join(f"{k}={v}" for k, v in sorted(agg.items())))
-open(os.path.join(ROOT, "profiles", "r1_sass_evidence.txt"), "w").write("\n".join(out) + "\n")
+open(os.path.join(ROOT, "profiles", "r2_sass_evidence.txt"), "w").write("\n".join(out) + "\n")
 print("\n".join(out))
