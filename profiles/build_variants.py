@@ -14,6 +14,7 @@ VARIANTS = {
     "mb3": ["-DSCVX_A_MINBLOCKS=3"],
     "mb3_park": ["-DSCVX_A_MINBLOCKS=3", "-DSCVX_A_PARK=1"],
     "mb4_park": ["-DSCVX_A_MINBLOCKS=4", "-DSCVX_A_PARK=1"],
+    "lean_lift": ["-DSCVX_A_LEAN_LIFT=1"],
     "carve25": ["-DSCVX_A_CARVEOUT=25"],
     "carve15": ["-DSCVX_A_CARVEOUT=15"],
     "smem_drag": ["-DSCVX_A_SMEM_TABLES=1"],

@@ -12,6 +12,9 @@ namespace {
 // f_v (it contains the aero force) and the aero Jacobians.  The stage control (FOH of the interval's two node controls,
 // which the producers keep in shared memory), f_m = -a |u|, f_q = Omega(w) q / 2 and f_w = jBi (rTB x u - w x jB w) are
 // re-formed by the producers (~45 FP64 operations per record).
+#ifndef SCVX_A_LEAN_LIFT
+#define SCVX_A_LEAN_LIFT 1     // leaner lift-branch Jacobian algebra: -44 FP64 operations, +0.55 % (A/B: profiles/r2_ab_lean_lift.txt)
+#endif
 constexpr int REC_EXO = 14;      // stage record entries: m, v(3), q(4), w(3), f_v(3)
 constexpr int REC_AERO = 32;     // + dF_aero/dv (9, row-major) + dF_aero/db (9), b = C(q) e1
 constexpr int R_FV = 11, R_AV = 14, R_AB = 23;
@@ -148,6 +151,35 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
     const double l[3] = { v[0] * bvdot - b[0] * vv, v[1] * bvdot - b[1] * vv, v[2] * bvdot - b[2] * vv };
     const double inl = rsqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
     const double lh[3] = { l[0] * inl, l[1] * inl, l[2] * inl };
+#if SCVX_A_LEAN_LIFT
+    // dl/dv = Lv = (v.b) I + v b^T - 2 b v^T ;  dl/db = Lb = v v^T - (v.v) I ;  d(lh)/d. = (I - lh lh^T) L. / |l|, so
+    //   dF/dv += lh lv^T + ln (Lv - lh (lh^T Lv)),   dF/db += lh lb^T + ln (Lb - lh (lh^T Lb)),   ln = lift / |l|.
+    // The projections are formed from two scalars instead of from the 3 x 3 matrices:
+    //   lh^T Lv = (v.b) lh^T + (lh.v) b^T - 2 (lh.b) v^T ,   lh^T Lb = (lh.v) v^T - (v.v) lh^T
+    const double ln = lift * inl;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) F[r] = fma(ln, l[r], F[r]);
+    const double lhv = lh[0] * v[0] + lh[1] * v[1] + lh[2] * v[2];
+    const double lhb = lh[0] * b[0] + lh[1] * b[1] + lh[2] * b[2];
+    double pjv[3], pjb[3], lnv[3], lnb2[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double pv = fma(bvdot, lh[c], fma(lhv, b[c], -2.0 * lhb * v[c]));
+        const double pb = fma(lhv, v[c], -vv * lh[c]);
+        pjv[c] = fma(-ln, pv, lv[c]);
+        pjb[c] = fma(-ln, pb, lb[c]);
+        lnv[c] = ln * v[c];
+        lnb2[c] = -2.0 * ln * b[c];
+    }
+    const double dgv = ln * bvdot, dgb = -ln * vv;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Fv[r][c] += fma(lh[r], pjv[c], fma(lnv[r], b[c], fma(lnb2[r], v[c], r == c ? dgv : 0.0)));
+            Fb[r][c] += fma(lh[r], pjb[c], fma(lnv[r], v[c], r == c ? dgb : 0.0));
+        }
+#else
     // dl/dv = (v.b) I + v b^T - 2 b v^T ;  dl/db = v v^T - (v.v) I
     double Lv[3][3], Lb[3][3];
 #pragma unroll
@@ -171,6 +203,7 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
             Fb[r][c] += lh[r] * lb[c] + ln * (Lb[r][c] - lh[r] * pb);
         }
     }
+#endif
 }
 
 // unscaled f(x,u) (dx_static without the `.* mult`, dynamics.jl:54-77) together with the Jacobians of the
