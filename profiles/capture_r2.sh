@@ -5,6 +5,7 @@ set -u
 O=gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q > $O/r2_pytest_gpu.log 2>&1; echo "pytest exit $?" >> $O/r2_pytest_gpu.log
 tail -3 $O/r2_pytest_gpu.log
+python __graft_entry__.py --smoke > $O/r2_smoke.log 2>&1; tail -1 $O/r2_smoke.log
 python bench.py > $O/r2_bench.json 2> $O/r2_bench.err; echo "bench exit $?"
 python bench.py --impl reference --steps 3 --warmup 1 > $O/r2_bench_reference.json 2>> $O/r2_bench.err
 python bench.py --mode 1 --no-cpu --no-extra > $O/r2_bench_textbook.json 2>> $O/r2_bench.err
