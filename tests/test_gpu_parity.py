@@ -737,3 +737,24 @@ def test_fin_force_tables_staged_and_evaluated(dyn, cache_aero):
     # exact interpolation at grid points
     gl2, _ = ctx.fin_force(mach[[0, 7, 59]], defl[[0, 450, 900]])
     assert np.abs(gl2 - lift[[0, 7, 59], [0, 450, 900]]).max() <= 1e-15
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_mixed_aero_kinds_in_one_batch(dyn, prob_aero, oracle_tables, kernel):
+    """Per-trajectory records may mix ExoatmosphericData and AtmosphericData problems in one call (the stage records
+    then carry zero aero blocks for the exo trajectories)."""
+    from successiveconvexification_b200 import workloads
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, 9, 10, 99, sweep=True, sigma_range=(0.8, 1.5))
+    P = P.copy()
+    P["aero_kind"][::2] = 0
+    cache = dyn.make_cache(prob_aero)
+    ptr, n, keep = workloads.as_c_params(P)
+    cache.sim_prob.set_params_raw(ptr, n)
+    cache.sim_prob.set_kernel(kernel)
+    for mode in (0, 1):
+        blocks, err, tlb = dyn.linearize_batch(cache, X, U, sigma, 0.1, 10, mode)
+        ref, rerr, rtlb, _ = _oracle().linearize_batch(P, oracle_tables, X, U, sigma, 0.1, 10, mode)
+        assert_parity(blocks, ref)
+        assert np.abs(tlb - rtlb).max() <= 1e-15
+    # an exo trajectory's v-v block of A has no aero coupling: d(vdot)/dv = 0 -> D[v, v] = I exactly
+    assert np.array_equal(blocks[0, :, 5:8, 4:7], np.broadcast_to(np.eye(3), (9, 3, 3)))
