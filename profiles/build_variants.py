@@ -11,6 +11,7 @@ from successiveconvexification_b200.csrc import build as b
 
 VARIANTS = {
     "base": [],
+    "tables_global": ["-DSCVX_A_SMEM_TABLES=0"],
     "mb3": ["-DSCVX_A_MINBLOCKS=3"],
     "mb3_park": ["-DSCVX_A_MINBLOCKS=3", "-DSCVX_A_PARK=1"],
     "mb4_park": ["-DSCVX_A_MINBLOCKS=4", "-DSCVX_A_PARK=1"],
@@ -19,6 +20,7 @@ VARIANTS = {
     "carve15": ["-DSCVX_A_CARVEOUT=15"],
     "smem_drag": ["-DSCVX_A_SMEM_TABLES=1"],
     "smem_both": ["-DSCVX_A_SMEM_TABLES=2"],
+    "smem_window": ["-DSCVX_A_SMEM_TABLES=3"],
 }
 
 

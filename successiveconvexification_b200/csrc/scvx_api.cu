@@ -129,6 +129,7 @@ int dev_index_of(const scvx_ctx* c, const void* p);
 ScvxTables tables_of(const Dev& d) {
     ScvxTables t;
     t.drag = d.coef[SCVX_TABLE_DRAG]; t.lift = d.coef[SCVX_TABLE_LIFT]; t.trq = d.coef[SCVX_TABLE_TORQUE];
+    t.wdrag = nullptr; t.wlift = nullptr; t.wi0 = 0; t.wj0 = 0;
     t.n1 = d.n1; t.n2 = d.n2; t.x0 = d.x0; t.inv_dx = 1.0 / d.dx; t.y0 = d.y0; t.inv_dy = 1.0 / d.dy;
     return t;
 }
@@ -510,6 +511,7 @@ int scvx_fin_force_batch(scvx_ctx* c, const double* mach, const double* deflecti
     if ((out_lift && !d.fin[0]) || (out_drag && !d.fin[1])) return fail(SCVX_ERR_STATE, "fin table not uploaded (scvx_set_fin_table)");
     ScvxTables lt, dt;
     lt.drag = d.fin[0]; lt.lift = nullptr; lt.trq = nullptr; lt.n1 = d.fn1; lt.n2 = d.fn2;
+    lt.wdrag = nullptr; lt.wlift = nullptr; lt.wi0 = 0; lt.wj0 = 0;
     lt.x0 = d.fx0; lt.inv_dx = 1.0 / d.fdx; lt.y0 = d.fy0; lt.inv_dy = 1.0 / d.fdy;
     dt = lt; dt.drag = d.fin[1];
     if (dev) {

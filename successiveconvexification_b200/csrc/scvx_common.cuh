@@ -22,6 +22,11 @@ struct ScvxTables {
     const double* drag;
     const double* lift;
     const double* trq;    // torque table: only the fins variant reads it
+    // shared-memory window of the drag / lift coefficients (value kernel of the STAGED path): WIN_I x WIN_J padded
+    // coefficients starting at (wi0, wj0); nullptr / unused elsewhere
+    const double* wdrag;
+    const double* wlift;
+    int wi0, wj0;
     int n1, n2;           // n_cos, n_mach
     double x0, inv_dx;    // cos axis:  index coordinate = (x - x0) * inv_dx + 1
     double y0, inv_dy;    // mach axis

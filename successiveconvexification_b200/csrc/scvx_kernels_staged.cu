@@ -42,36 +42,43 @@ namespace {
 // that the kernel fits 168 registers and a third block per SM (3 warps per scheduler hide the dependent-issue latency of
 // the serial value chain better than 2).
 #ifndef SCVX_A_SMEM_TABLES
-#define SCVX_A_SMEM_TABLES 0
+#define SCVX_A_SMEM_TABLES 1
 #endif
-// SCVX_A_SMEM_TABLES (the A/B BASELINE.json's north_star asks for: "the aero tables are staged into shared memory"):
-//   0  spline coefficients read through the read-only path (ld.global.nc), L1 resident — the default;
-//   1  drag table (92 KB) staged in shared memory by every block; one block of 256 threads per SM;
-//   2  drag + lift tables (184 KB) staged; one block of 224 threads per SM (what fits beside the light-column state).
-// Result (profiles/r2_smem_tables_*.txt): see there.
-constexpr int VT = SCVX_A_SMEM_TABLES == 0 ? 128 : (SCVX_A_SMEM_TABLES == 1 ? 256 : 224);     // threads per block
-constexpr int VALUE_MINBLOCKS = SCVX_A_SMEM_TABLES ? 1 : SCVX_A_MINBLOCKS;
+// Table staging of the value kernel, template parameter TS (BASELINE.json's north_star: "the aero tables are staged into
+// shared memory"; A/Bs in profiles/r2_smem_tables_variants.txt, r2_smem_tables_small_record.txt, r2_smem_window_variant.txt):
+//   0  spline coefficients read through the read-only path (ld.global.nc), L1 resident; two blocks of 128 threads per SM.
+//      Always available: the fallback when the tables do not fit, and the path of exo-atmospheric batches;
+//   1  DRAG table (92 KB: every stage reads it) staged in shared memory by every block, one block of 256 threads per SM,
+//      the lift table (one branch only) through L1: +0.8 % — the default (SCVX_A_SMEM_TABLES) when the table fits;
+//   2  drag + lift tables (184 KB) staged; one block of 224 threads per SM (what fits beside the light-column state): -1.7 %;
+//   3  a WIN_I x WIN_J WINDOW of both tables around the block's starting (cos aoa, Mach) cells (18 KB per block; two blocks
+//      of 128 threads per SM as in 0), 4 x 4 patches outside the window from global memory: -6.8 % (generic loads, spills).
+__host__ __device__ constexpr int value_threads(int ts) { return (ts == 1) ? 256 : (ts == 2 ? 224 : 128); }
+__host__ __device__ constexpr int value_minblocks(int ts) { return (ts == 1 || ts == 2) ? 1 : SCVX_A_MINBLOCKS; }
 constexpr int VALUE_SMEM_DOUBLES = 24 + (SCVX_A_PARK ? 28 : 0);
-constexpr size_t LIGHT_SMEM_BYTES = VALUE_SMEM_DOUBLES * VT * sizeof(double);
-template <bool SP>
-__global__ void __launch_bounds__(VT, VALUE_MINBLOCKS) stage_value_kernel(const __grid_constant__ StagedArgs a) {
+__host__ __device__ constexpr size_t value_smem_bytes(int ts) {
+    return (size_t)VALUE_SMEM_DOUBLES * value_threads(ts) * sizeof(double) + (ts == 3 ? 2 * WIN_I * WIN_J * sizeof(double) : 0);
+}
+template <bool SP, int TS>
+__global__ void __launch_bounds__(value_threads(TS), value_minblocks(TS)) stage_value_kernel(const __grid_constant__ StagedArgs a) {
+    constexpr int VT = value_threads(TS);
     extern __shared__ double light_smem[];            // [24][VT] doubles (+ the staged tables)
     ScvxTables tbl = a.tb;
-#if SCVX_A_SMEM_TABLES
-    {
+    if constexpr (TS == 1 || TS == 2) {
         const int ncoef = (a.tb.n1 + 2) * (a.tb.n2 + 2);
         double* sd = light_smem + VALUE_SMEM_DOUBLES * VT;
         for (int k = threadIdx.x; k < ncoef; k += VT) sd[k] = __ldg(a.tb.drag + k);
         tbl.drag = sd;
-#if SCVX_A_SMEM_TABLES == 2
-        for (int k = threadIdx.x; k < ncoef; k += VT) sd[ncoef + k] = __ldg(a.tb.lift + k);
-        tbl.lift = sd + ncoef;
-#endif
+        if constexpr (TS == 2) {
+            for (int k = threadIdx.x; k < ncoef; k += VT) sd[ncoef + k] = __ldg(a.tb.lift + k);
+            tbl.lift = sd + ncoef;
+        }
         __syncthreads();
     }
-#endif
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n_groups * GROUP) return;
+    if constexpr (TS != 3) {
+        if (t >= a.n_groups * GROUP) return;
+    }
     const ScvxBatch& bt = a.bt;
     const int ni = bt.n_nodes - 1;
     const bool live = t < a.count;
@@ -86,6 +93,41 @@ __global__ void __launch_bounds__(VT, VALUE_MINBLOCKS) stage_value_kernel(const 
     for (int r = 0; r < 14; ++r) x[r] = xin[r];
 #pragma unroll
     for (int c = 0; c < 3; ++c) { um[c] = uin[c]; up[c] = uin[3 + c]; }
+    if constexpr (TS == 3) {
+        // window of the spline coefficients around the block's starting (cos aoa, Mach) cells
+        __shared__ int wmm[4];                               // min i, max i, min j, max j over the block
+        if (threadIdx.x == 0) { wmm[0] = 1 << 30; wmm[1] = -1; wmm[2] = 1 << 30; wmm[3] = -1; }
+        __syncthreads();
+        if (a.tb.drag != nullptr && ldpi<SP>(&P.aero_kind) == SCVX_AERO_TABLE) {
+            const double q0 = x[7], q1 = x[8], q2 = x[9], q3 = x[10];
+            const double b0 = 1.0 - 2.0 * (q2 * q2 + q3 * q3), b1 = 2.0 * (q1 * q2 + q0 * q3), b2 = 2.0 * (q1 * q3 - q0 * q2);
+            const double vv = x[4] * x[4] + x[5] * x[5] + x[6] * x[6], nv = sqrt(vv);
+            double ca = (b0 * x[4] + b1 * x[5] + b2 * x[6]) / (nv * sqrt(b0 * b0 + b1 * b1 + b2 * b2));
+            ca = fmin(fmax(ca, -1.0), 1.0);
+            const double mach = nv / ldp<SP>(&P.sos);
+            double xi = (ca - a.tb.x0) * a.tb.inv_dx + 1.0, yi = (mach - a.tb.y0) * a.tb.inv_dy + 1.0;
+            xi = fmin(fmax(xi, 1.0), (double)a.tb.n1); yi = fmin(fmax(yi, 1.0), (double)a.tb.n2);
+            const int ci = (xi == xi) ? (int)xi : 1, cj = (yi == yi) ? (int)yi : 1;
+            atomicMin(&wmm[0], ci); atomicMax(&wmm[1], ci); atomicMin(&wmm[2], cj); atomicMax(&wmm[3], cj);
+        }
+        __syncthreads();
+        const int L1 = a.tb.n1 + 2, L2 = a.tb.n2 + 2;
+        int wi0 = -(1 << 29), wj0 = -(1 << 29);              // "no window": no patch is ever inside
+        double* wd = light_smem + VALUE_SMEM_DOUBLES * VT;
+        if (wmm[1] >= 0 && L1 >= WIN_I && L2 >= WIN_J) {
+            wi0 = min(max((wmm[0] + wmm[1]) / 2 - WIN_I / 2, 0), L1 - WIN_I);
+            wj0 = min(max((wmm[2] + wmm[3]) / 2 - WIN_J / 2, 0), L2 - WIN_J);
+            for (int k = threadIdx.x; k < WIN_I * WIN_J; k += VT) {
+                const int li = k % WIN_I, lj = k / WIN_I;
+                const size_t g = (size_t)(wi0 + li) + (size_t)(wj0 + lj) * L1;
+                wd[k] = __ldg(a.tb.drag + g);
+                wd[WIN_I * WIN_J + k] = __ldg(a.tb.lift + g);
+            }
+        }
+        __syncthreads();
+        tbl.wdrag = wd; tbl.wlift = wd + WIN_I * WIN_J; tbl.wi0 = wi0; tbl.wj0 = wj0;
+        if (t >= a.n_groups * GROUP) return;
+    }
 
     const int nst = 4 * bt.npts;
     double* rec = a.rec + ((size_t)(t >> 5) * nst) * ((size_t)a.rec_n * GROUP) + (t & 31);
@@ -127,7 +169,7 @@ __global__ void __launch_bounds__(VT, VALUE_MINBLOCKS) stage_value_kernel(const 
             double uc[3], f[14], Fv[3][3], Fb[3][3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) uc[c] = (1.0 - pc) * um[c] + pc * up[c];
-            rhs_value<true, SCVX_A_SMEM_TABLES, SP>(P, tbl, y, uc, f, Fv, Fb);
+            rhs_value<true, TS, SP>(P, tbl, y, uc, f, Fv, Fb);
             // record: m, v, q, w, f_v [, dF/dv, dF/db]  (u, f_m, f_q, f_w are re-formed by the producers)
             double* rp = rec + (size_t)(it * 4 + st) * ((size_t)a.rec_n * GROUP);
             if (a.rec_n == REC_AERO) {
@@ -480,22 +522,39 @@ size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals) {
 // tangent kernel 32 intervals per pass: 768 intervals per SM = 3 waves / 24 passes.
 int scvx_staged_chunk_intervals(int sm_count) { return sm_count * (SCVX_A_SMEM_TABLES == 2 ? 896 : 768); }
 
+// the table-staging mode a launch uses: the compiled preference if the tables fit beside the light-column state, else 0
+static int value_table_mode(const ScvxTables& tb, bool any_aero) {
+    const int pref = SCVX_A_SMEM_TABLES;
+    if (pref == 0 || !any_aero || !tb.drag || !tb.lift) return 0;
+    if (pref == 3) return 3;
+    const size_t need = value_smem_bytes(pref) + (size_t)pref * (tb.n1 + 2) * (tb.n2 + 2) * sizeof(double);
+    return need <= 232448 ? pref : 0;
+}
+
+template <int TS>
+static cudaError_t value_kernel_attributes() {
+    const int vs = (TS == 1 || TS == 2) ? 232448 : (int)value_smem_bytes(TS);
+    cudaError_t e = cudaFuncSetAttribute(stage_value_kernel<false, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, vs);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stage_value_kernel<true, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, vs);
+    return e;
+}
+
 cudaError_t scvx_staged_init() {
-    const int vs = SCVX_A_SMEM_TABLES ? 232448 : (int)LIGHT_SMEM_BYTES;
-    cudaError_t e = cudaFuncSetAttribute(stage_value_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, vs);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(stage_value_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vs);
-#ifndef SCVX_A_CARVEOUT
-#define SCVX_A_CARVEOUT 0
-#endif
-    // the value kernel needs 2 x 24.5 KB of shared memory per SM; the driver's default carve-out for it is 102 KB.  A smaller
-    // one leaves more of the 256 KB to L1, where the spline coefficients live (A/B: profiles/r2_value_carveout.txt)
-    if (SCVX_A_CARVEOUT > 0 && !SCVX_A_SMEM_TABLES) {
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(stage_value_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, SCVX_A_CARVEOUT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(stage_value_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, SCVX_A_CARVEOUT);
-    }
+    cudaError_t e = value_kernel_attributes<0>();
+    if (e == cudaSuccess && SCVX_A_SMEM_TABLES != 0) e = value_kernel_attributes<SCVX_A_SMEM_TABLES>();
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tangent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tangent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
     return e;
+}
+
+template <int TS>
+static void launch_value(const StagedArgs& a, const ScvxTables& tb, bool shared, cudaStream_t s) {
+    constexpr int VT = value_threads(TS);
+    const int threads = a.n_groups * GROUP;
+    size_t vsmem = value_smem_bytes(TS);
+    if (TS == 1 || TS == 2) vsmem += (size_t)TS * (tb.n1 + 2) * (tb.n2 + 2) * sizeof(double);
+    if (shared) stage_value_kernel<true, TS><<<(threads + VT - 1) / VT, VT, vsmem, s>>>(a);
+    else stage_value_kernel<false, TS><<<(threads + VT - 1) / VT, VT, vsmem, s>>>(a);
 }
 
 cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, const scvx_probinfo* shared_params,
@@ -531,20 +590,11 @@ cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool a
         a.rec_n = any_aero ? REC_AERO : REC_EXO;
         a.count = (int)((total - first < chunk_intervals) ? (total - first) : chunk_intervals);
         a.n_groups = (a.count + GROUP - 1) / GROUP;
-        const int threads = a.n_groups * GROUP;
-        size_t vsmem = LIGHT_SMEM_BYTES;
-        if (SCVX_A_SMEM_TABLES) {
-            vsmem += (size_t)SCVX_A_SMEM_TABLES * (tb.n1 + 2) * (tb.n2 + 2) * sizeof(double);
-            if (vsmem > 232448 || !tb.drag || !tb.lift) return cudaErrorInvalidConfiguration;     // A/B build: tables must fit
-        }
         const int grid = a.n_groups < sm_count ? a.n_groups : sm_count;
-        if (shared_params) {
-            stage_value_kernel<true><<<(threads + VT - 1) / VT, VT, vsmem, s>>>(a);
-            tangent_kernel<true><<<grid, TANGENT_THREADS, smem, s>>>(a);
-        } else {
-            stage_value_kernel<false><<<(threads + VT - 1) / VT, VT, vsmem, s>>>(a);
-            tangent_kernel<false><<<grid, TANGENT_THREADS, smem, s>>>(a);
-        }
+        if (value_table_mode(tb, any_aero) != 0) launch_value<SCVX_A_SMEM_TABLES>(a, tb, shared_params != nullptr, s);
+        else launch_value<0>(a, tb, shared_params != nullptr, s);
+        if (shared_params) tangent_kernel<true><<<grid, TANGENT_THREADS, smem, s>>>(a);
+        else tangent_kernel<false><<<grid, TANGENT_THREADS, smem, s>>>(a);
         if (launches) *launches += 2;
     }
     return cudaGetLastError();

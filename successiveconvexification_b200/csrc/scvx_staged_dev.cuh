@@ -63,8 +63,12 @@ template <bool SP> __device__ __forceinline__ int ldpi(const int32_t* p) {
 // spline value and gradient w.r.t. the physical coordinates (gradient 0 when strictly outside: Flat extrapolation);
 // one pass over the 16 coefficients serves all three.
 // SMEM: the coefficient array lives in shared memory (plain loads) instead of global memory (read-only path).
-template <bool SMEM = false>
-__device__ __forceinline__ void spline_val_grad(const double* __restrict__ coef, const ScvxTables& t, double x, double y,
+// WIN: a WIN_I x WIN_J window of the coefficients around the block's starting cells is staged in shared memory
+// (`wcoef`, origin t.wi0 / t.wj0); a 4 x 4 patch inside the window is read from there, any other from global memory.
+constexpr int WIN_I = 48, WIN_J = 24;
+template <bool SMEM = false, bool WIN = false>
+__device__ __forceinline__ void spline_val_grad(const double* __restrict__ coef, const double* __restrict__ wcoef,
+                                                const ScvxTables& t, double x, double y,
                                                 double& val, double& gx, double& gy) {
     const int L1 = t.n1 + 2;
     double xi = (x - t.x0) * t.inv_dx + 1.0, yi = (y - t.y0) * t.inv_dy + 1.0;
@@ -81,12 +85,20 @@ __device__ __forceinline__ void spline_val_grad(const double* __restrict__ coef,
                            (2.0 / 3.0) - oy * oy + 0.5 * oy * oy * oy, dy * dy * dy * (1.0 / 6.0) };
     const double gyw[4] = { -0.5 * oy * oy, -2.0 * dy + 1.5 * dy * dy, 2.0 * oy - 1.5 * oy * oy, 0.5 * dy * dy };
     const double* base = coef + (i - 1) + (size_t)(j - 1) * L1;
+    int stride = L1;
+    if constexpr (WIN) {
+        const int li = i - 1 - t.wi0, lj = j - 1 - t.wj0;
+        if ((unsigned)li <= (unsigned)(WIN_I - 4) && (unsigned)lj <= (unsigned)(WIN_J - 4)) {
+            base = wcoef + li + lj * WIN_I;
+            stride = WIN_I;
+        }
+    }
     double av = 0.0, ax = 0.0, ay = 0.0;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-        const double* p = base + (size_t)b * L1;
+        const double* p = base + (size_t)b * stride;
         double c0, c1, c2, c3;
-        if constexpr (SMEM) { c0 = p[0]; c1 = p[1]; c2 = p[2]; c3 = p[3]; }
+        if constexpr (SMEM || WIN) { c0 = p[0]; c1 = p[1]; c2 = p[2]; c3 = p[3]; }      // WIN: generic loads (shared or global)
         else { c0 = __ldg(p); c1 = __ldg(p + 1); c2 = __ldg(p + 2); c3 = __ldg(p + 3); }
         const double rv = wx[0] * c0 + wx[1] * c1 + wx[2] * c2 + wx[3] * c3;
         const double rg = gxw[0] * c0 + gxw[1] * c1 + gxw[2] * c2 + gxw[3] * c3;
@@ -99,7 +111,7 @@ __device__ __forceinline__ void spline_val_grad(const double* __restrict__ coef,
 
 // Jacobian of the aerodynamic force F(b, v) (aerodynamics.jl:38-58) w.r.t. v and b = C(q) e1: exact derivative
 // of the executed branch (|dp| >= 0.95 drag only; clamp active only strictly outside [-1,1]).
-// TS = number of tables staged in shared memory: 0 none, 1 drag, 2 drag + lift (tb.drag / tb.lift then point there).
+// TS = tables staged in shared memory: 0 none, 1 drag, 2 drag + lift (tb.drag / tb.lift then point there), 3 a window of both.
 template <int TS = 0, bool SP = false>
 __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const ScvxTables& tb, const double b[3],
                                                const double v[3], double F[3], double Fv[3][3], double Fb[3][3]) {
@@ -125,7 +137,7 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
     }
     const double fs = ldp<SP>(&P.force_scalar);
     double drag, gx, gy;
-    spline_val_grad<(TS >= 1)>(tb.drag, tb, ca, mach, drag, gx, gy);
+    spline_val_grad<(TS == 1 || TS == 2), (TS == 3)>(tb.drag, tb.wdrag, tb, ca, mach, drag, gx, gy);
     drag *= fs; gx *= fs; gy *= fs;
     double dv[3], db[3];
 #pragma unroll
@@ -142,7 +154,7 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
     }
     if (fabs(dp) >= 0.95) return;
     double lift;
-    spline_val_grad<(TS >= 2)>(tb.lift, tb, ca, mach, lift, gx, gy);
+    spline_val_grad<(TS == 2), (TS == 3)>(tb.lift, tb.wlift, tb, ca, mach, lift, gx, gy);
     lift *= fs; gx *= fs; gy *= fs;
     double lv[3], lb[3];
 #pragma unroll

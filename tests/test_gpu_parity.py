@@ -758,3 +758,29 @@ def test_mixed_aero_kinds_in_one_batch(dyn, prob_aero, oracle_tables, kernel):
         assert np.abs(tlb - rtlb).max() <= 1e-15
     # an exo trajectory's v-v block of A has no aero coupling: d(vdot)/dv = 0 -> D[v, v] = I exactly
     assert np.array_equal(blocks[0, :, 5:8, 4:7], np.broadcast_to(np.eye(3), (9, 3, 3)))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_large_tables_fall_back_to_the_global_memory_path(dyn, prob_aero, kernel):
+    """The value kernel stages the drag table in shared memory when it fits (92 KB for the reference's 181 x 61 grid); a
+    finer table (301 x 121: 295 KB) does not, and the launch falls back to the global-memory path."""
+    from successiveconvexification_b200 import workloads
+    from successiveconvexification_b200.defns import AeroTable, AtmosphericData
+    n1, n2 = 301, 121
+    cos = -1.0 + 2.0 * np.arange(n1) / (n1 - 1)
+    mach = 1.5 * np.arange(n2) / (n2 - 1)
+    drag = np.asfortranarray(-(40.0 + 600.0 * mach[None, :] ** 2) * (1.2 + cos[:, None] ** 2))
+    lift = np.asfortranarray(-300.0 * mach[None, :] * np.sin(np.pi * cos[:, None]))
+    trq = np.asfortranarray(10.0 * mach[None, :] * cos[:, None])
+    geo = (-1.0, 2.0 / (n1 - 1), 0.0, 1.5 / (n2 - 1))
+    aero = AtmosphericData(AeroTable(drag, *geo), AeroTable(lift, *geo), AeroTable(trq, *geo),
+                           prob_aero.aero.force_scalar, prob_aero.aero.length_scalar)
+    prob = prob_aero.replace(aero=aero)
+    cache = dyn.make_cache(prob)
+    cache.sim_prob.set_kernel(kernel)
+    tb = _oracle().OracleTables.from_aero(aero)
+    X, U, sigma, P = workloads.monte_carlo_batch(prob, 10, 40, 5150, sigma_range=(0.8, 1.5))
+    for mode in (0, 1):
+        blocks, err, _ = dyn.linearize_batch(cache, X, U, sigma, 1 / 11, 10, mode)
+        ref, rerr, _, _ = _oracle().linearize_batch(P, tb, X, U, sigma, 1 / 11, 10, mode)
+        assert_parity(blocks, ref)
