@@ -12,6 +12,8 @@ from successiveconvexification_b200.csrc import build as b
 VARIANTS = {
     "base": [],
     "tables_global": ["-DSCVX_A_SMEM_TABLES=0"],
+    "evict_last": ["-DSCVX_A_EVICT_LAST=1"],
+    "evict_last_global": ["-DSCVX_A_EVICT_LAST=1", "-DSCVX_A_SMEM_TABLES=0"],
     "mb3": ["-DSCVX_A_MINBLOCKS=3"],
     "mb3_park": ["-DSCVX_A_MINBLOCKS=3", "-DSCVX_A_PARK=1"],
     "mb4_park": ["-DSCVX_A_MINBLOCKS=4", "-DSCVX_A_PARK=1"],

@@ -280,23 +280,28 @@ int run_impl(scvx_ctx* c, bool predict, const double* X, const double* U, const 
     chunk = std::max(1L, chunk);
     // chunk index outermost, devices innermost: every device gets its c-th chunk enqueued before any device gets its
     // (c+1)-th, so the slot-reuse waits of one device never hold back the others (all devices run concurrently)
+    // the D2H engine is the bottleneck and sits idle until the first chunk has been computed: a short first chunk (1/8)
+    // starts it early (the pipeline prologue was 3-4 % of a 12-chunk call)
+    const long first = std::max(1L, chunk / 8);
     long max_chunks = 0;
     for (int di = 0; di < nd; ++di) {
-        const long b0 = (long)B * di / nd, b1 = (long)B * (di + 1) / nd;
-        max_chunks = std::max(max_chunks, (b1 - b0 + chunk - 1) / chunk);
+        const long len = (long)B * (di + 1) / nd - (long)B * di / nd;
+        max_chunks = std::max(max_chunks, len <= chunk ? (len > 0 ? 1L : 0L) : 1 + (len - first + chunk - 1) / chunk);
     }
     for (long ci = 0; ci < max_chunks; ++ci) {
         for (int di = 0; di < nd; ++di) {
             Dev& d = c->devs[di];
             const long b0 = (long)B * di / nd, b1 = (long)B * (di + 1) / nd;
-            const long cb = b0 + ci * chunk;
+            const bool split = (b1 - b0) > chunk;
+            const long cb = (ci == 0 || !split) ? b0 + ci * chunk : b0 + first + (ci - 1) * chunk;
             if (cb >= b1) continue;
             CK(cudaSetDevice(d.id));
-            const int nb = (int)std::min(chunk, b1 - cb);
+            const int nb = (int)std::min((ci == 0 && split) ? first : chunk, b1 - cb);
+            const size_t cap_nb = (size_t)std::min(chunk, b1 - b0);      // every slot is sized for a full chunk at once
             Slot& sl = d.slot[ci % NSLOT];
             CK(cudaStreamSynchronize(sl.stream));       // previous user of this slot has drained its D2H
-            if (grow(&sl.dX, &sl.capX, (size_t)nb * n_nodes * 14) || grow(&sl.dU, &sl.capU, (size_t)nb * n_nodes * 3) ||
-                grow(&sl.dS, &sl.capS, (size_t)nb))
+            if (grow(&sl.dX, &sl.capX, cap_nb * n_nodes * 14) || grow(&sl.dU, &sl.capU, cap_nb * n_nodes * 3) ||
+                grow(&sl.dS, &sl.capS, cap_nb))
                 return SCVX_ERR_NOMEM;
             Range chunk_range("scvx:chunk h2d+kernels+d2h");
             CK(cudaMemcpyAsync(sl.dX, X + (size_t)cb * n_nodes * 14, (size_t)nb * n_nodes * 14 * 8, cudaMemcpyHostToDevice, sl.stream));
@@ -307,18 +312,18 @@ int run_impl(scvx_ctx* c, bool predict, const double* X, const double* U, const 
             bt.n_nodes = n_nodes; bt.B = nb; bt.dt = dt; bt.npts = npts; bt.mode = mode;
             bt.out_blocks = nullptr; bt.out_lin_err = nullptr; bt.out_tlb = nullptr; bt.out_endpoints = nullptr;
             if (predict) {
-                if (grow(&sl.dEnd, &sl.capEnd, (size_t)nb * ni * 14)) return SCVX_ERR_NOMEM;
+                if (grow(&sl.dEnd, &sl.capEnd, cap_nb * ni * 14)) return SCVX_ERR_NOMEM;
                 bt.out_endpoints = sl.dEnd;
                 if (int rc = launch_predict(c, d, bt, sl.stream)) return rc;
                 CK(cudaMemcpyAsync(out_end + (size_t)cb * ni * 14, sl.dEnd, (size_t)nb * ni * 14 * 8, cudaMemcpyDeviceToHost, sl.stream));
             } else {
-                if (grow(&sl.dOut, &sl.capOut, (size_t)nb * ni * SCVX_BLOCK_DOUBLES)) return SCVX_ERR_NOMEM;
+                if (grow(&sl.dOut, &sl.capOut, cap_nb * ni * SCVX_BLOCK_DOUBLES)) return SCVX_ERR_NOMEM;
                 bt.out_blocks = sl.dOut;
-                if (out_lin_err) { if (grow(&sl.dErr, &sl.capErr, (size_t)nb * ni * 14)) return SCVX_ERR_NOMEM; bt.out_lin_err = sl.dErr; }
-                if (out_tlb) { if (grow(&sl.dTlb, &sl.capTlb, (size_t)nb * n_nodes * 4)) return SCVX_ERR_NOMEM; bt.out_tlb = sl.dTlb; }
+                if (out_lin_err) { if (grow(&sl.dErr, &sl.capErr, cap_nb * ni * 14)) return SCVX_ERR_NOMEM; bt.out_lin_err = sl.dErr; }
+                if (out_tlb) { if (grow(&sl.dTlb, &sl.capTlb, cap_nb * n_nodes * 4)) return SCVX_ERR_NOMEM; bt.out_tlb = sl.dTlb; }
                 if (int rc = launch_linearize(c, d, bt, sl.stream)) return rc;
                 if (out_compact) {
-                    if (grow(&sl.dCmp, &sl.capCmp, (size_t)nb * ni * rec)) return SCVX_ERR_NOMEM;
+                    if (grow(&sl.dCmp, &sl.capCmp, cap_nb * ni * rec)) return SCVX_ERR_NOMEM;
                     CK(scvx_launch_compact_pack(sl.dOut, (long)nb * ni, rec, sl.dCmp, d.sm_count, sl.stream));
                     c->launches += 1;
                     CK(cudaMemcpyAsync(out_compact + (size_t)cb * ni * rec, sl.dCmp, (size_t)nb * ni * rec * 8,

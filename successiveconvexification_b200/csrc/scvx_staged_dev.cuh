@@ -62,6 +62,21 @@ template <bool SP> __device__ __forceinline__ int ldpi(const int32_t* p) {
 // ------------------------------------------------------------------------------------------------
 // spline value and gradient w.r.t. the physical coordinates (gradient 0 when strictly outside: Flat extrapolation);
 // one pass over the 16 coefficients serves all three.
+#ifndef SCVX_A_EVICT_LAST
+#define SCVX_A_EVICT_LAST 0
+#endif
+// spline coefficient from global memory through the read-only path; SCVX_A_EVICT_LAST marks the line evict-last in L1
+// (A/B: profiles/r2_ab_evict_last.txt)
+__device__ __forceinline__ double ld_coef(const double* p) {
+#if SCVX_A_EVICT_LAST
+    double v;
+    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 // SMEM: the coefficient array lives in shared memory (plain loads) instead of global memory (read-only path).
 // WIN: a WIN_I x WIN_J window of the coefficients around the block's starting cells is staged in shared memory
 // (`wcoef`, origin t.wi0 / t.wj0); a 4 x 4 patch inside the window is read from there, any other from global memory.
@@ -99,7 +114,7 @@ __device__ __forceinline__ void spline_val_grad(const double* __restrict__ coef,
         const double* p = base + (size_t)b * stride;
         double c0, c1, c2, c3;
         if constexpr (SMEM || WIN) { c0 = p[0]; c1 = p[1]; c2 = p[2]; c3 = p[3]; }      // WIN: generic loads (shared or global)
-        else { c0 = __ldg(p); c1 = __ldg(p + 1); c2 = __ldg(p + 2); c3 = __ldg(p + 3); }
+        else { c0 = ld_coef(p); c1 = ld_coef(p + 1); c2 = ld_coef(p + 2); c3 = ld_coef(p + 3); }
         const double rv = wx[0] * c0 + wx[1] * c1 + wx[2] * c2 + wx[3] * c3;
         const double rg = gxw[0] * c0 + gxw[1] * c1 + gxw[2] * c2 + gxw[3] * c3;
         av = fma(wy[b], rv, av);
