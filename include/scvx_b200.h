@@ -118,7 +118,7 @@ int scvx_linearize_batch(scvx_ctx* ctx, const double* X, const double* U, const 
  *                                                                                         aerodynamics.jl:45, 49-56
  * Needs aero_kind = TABLE and all three tables (drag, lift, torque).  The torque makes wdot depend on q and v, so the
  * structural zeros the STAGED kernels exploit are gone: this variant runs on the generic forward-mode kernel (one warp
- * per interval, lane L < 25 carries d/d inp[L]), exact by construction, ~7x slower than the 3-control path.
+ * per interval, lane L < 25 carries d/d inp[L]), exact by construction, about an order of magnitude slower than the STAGED path.
  *   X 14 x n_nodes x B    U5 5 x n_nodes x B    sigma B      inp = [x; u_k(5); u_{k+1}(5); sigma] (25)
  *   out_blocks 14 x 27 x (n_nodes-1) x B = [ endpoint | D (25 columns) | z ]   (acc_width = 14 + 2*5 + 3, rocketland.jl:22)
  *   out_lin_err 14 x (n_nodes-1) x B (optional).  All host or all device pointers. */
