@@ -42,14 +42,16 @@ namespace {
 // that the kernel fits 168 registers and a third block per SM (3 warps per scheduler hide the dependent-issue latency of
 // the serial value chain better than 2).
 #ifndef SCVX_A_SMEM_TABLES
-#define SCVX_A_SMEM_TABLES 1
+#define SCVX_A_SMEM_TABLES 0
 #endif
 // Table staging of the value kernel, template parameter TS (BASELINE.json's north_star: "the aero tables are staged into
 // shared memory"; A/Bs in profiles/r2_smem_tables_variants.txt, r2_smem_tables_small_record.txt, r2_smem_window_variant.txt):
 //   0  spline coefficients read through the read-only path (ld.global.nc), L1 resident; two blocks of 128 threads per SM.
-//      Always available: the fallback when the tables do not fit, and the path of exo-atmospheric batches;
+//      The default (SCVX_A_SMEM_TABLES); always compiled: the fallback when the tables do not fit, and the path of
+//      exo-atmospheric batches;
 //   1  DRAG table (92 KB: every stage reads it) staged in shared memory by every block, one block of 256 threads per SM,
-//      the lift table (one branch only) through L1: +0.8 % — the default (SCVX_A_SMEM_TABLES) when the table fits;
+//      the lift table (one branch only) through L1: +0.8 % with the LITERAL rule at sigma ~ U(1, 15), -2.6 % with the
+//      TEXTBOOK rule (one 256-thread block per SM drains less evenly than two of 128) — not the default;
 //   2  drag + lift tables (184 KB) staged; one block of 224 threads per SM (what fits beside the light-column state): -1.7 %;
 //   3  a WIN_I x WIN_J WINDOW of both tables around the block's starting (cos aoa, Mach) cells (18 KB per block; two blocks
 //      of 128 threads per SM as in 0), 4 x 4 patches outside the window from global memory: -6.8 % (generic loads, spills).
