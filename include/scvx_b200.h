@@ -84,8 +84,9 @@ int scvx_sizeof_probinfo(void);
 int scvx_create(scvx_ctx** out, const int* device_ids, int n_dev);
 void scvx_destroy(scvx_ctx* ctx);
 
-/* n == 1: parameters shared by all trajectories; n == B: one record per trajectory
- * (mass / thrust-bound sweeps).  `p` is a host pointer. */
+/* n == 1: parameters shared by all trajectories; n == B: one record per trajectory.  `p` is a host pointer.
+ * Records that differ in `a` and `Tmin` only (mass / thrust-bound sweeps) run at the speed of shared parameters; records
+ * that differ in any other field take a slower path that reads whole records from device memory (about -8 %). */
 int scvx_set_params(scvx_ctx* ctx, const scvx_probinfo* p, int n);
 
 /* Upload one aero table.  `samples` (host): n_cos x n_mach column-major exactly as the reshape at

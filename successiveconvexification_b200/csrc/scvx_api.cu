@@ -101,6 +101,7 @@ struct scvx_ctx {
     std::vector<scvx_probinfo> hP;
     bool any_aero = false;
     bool hP_values = false;      // hP holds the records' values (set by scvx_set_params), not just their count / aero kind
+    bool hP_sweep = false;       // > 1 records that differ in `a` and `Tmin` only (a mass / thrust-bound sweep)
 };
 
 namespace {
@@ -178,8 +179,10 @@ int launch_linearize(scvx_ctx* c, Dev& d, const ScvxBatch& bt, cudaStream_t s) {
     // event recorded now on that stream would also wait for its D2H copy and serialise copy and compute
     if (d.scratch_user && d.scratch_user != s) CK(cudaStreamWaitEvent(s, d.ev_scratch, 0));
     int n = 0;
-    const scvx_probinfo* shared = (bt.n_params == 1 && c->hP_values && c->hP.size() == 1) ? c->hP.data() : nullptr;
-    CK(scvx_launch_staged(bt, tb, c->any_aero, shared, d.scratch, chunk, d.sm_count, s, &n));
+    // one record for all (n_params == 1), or a sweep whose records differ in a / Tmin only (the kernels then read those
+    // two per trajectory and take the rest from record 0): the record travels in the kernel arguments
+    const scvx_probinfo* shared = (c->hP_values && (c->hP.size() == 1 ? bt.n_params == 1 : c->hP_sweep)) ? c->hP.data() : nullptr;
+    CK(scvx_launch_staged(bt, tb, c->any_aero, shared, c->hP.size() > 1, d.scratch, chunk, d.sm_count, s, &n));
     c->launches += n;
     CK(cudaEventRecord(d.ev_scratch, s));
     d.scratch_user = s;
@@ -438,6 +441,12 @@ int scvx_set_params(scvx_ctx* c, const scvx_probinfo* p, int n) {
             return fail(SCVX_ERR_ARG, "record %d: unknown aero_kind %d", i, p[i].aero_kind);
     c->hP.assign(p, p + n);
     c->hP_values = true;
+    c->hP_sweep = n > 1;
+    for (int i = 1; i < n && c->hP_sweep; ++i) {
+        scvx_probinfo r = p[i];
+        r.a = p[0].a; r.Tmin = p[0].Tmin; r._pad = p[0]._pad;
+        c->hP_sweep = std::memcmp(&r, &p[0], sizeof r) == 0;
+    }
     c->any_aero = false;
     for (int i = 0; i < n; ++i) if (p[i].aero_kind == SCVX_AERO_TABLE) c->any_aero = true;
     for (Dev& d : c->devs) {
@@ -800,7 +809,7 @@ int scvx_dispersed_setup_batch(scvx_ctx* c, const scvx_dim_problem* base, const 
         memset(&tmpl, 0, sizeof(tmpl));
         tmpl.aero_kind = base->aero_kind;
         c->hP.assign((size_t)B, tmpl);
-        c->hP_values = false;
+        c->hP_values = false; c->hP_sweep = false;
         c->any_aero = base->aero_kind == SCVX_AERO_TABLE;
     }
     return 0;

@@ -27,7 +27,9 @@ cudaError_t scvx_launch_compact_pack(const double* blocks, long n_intervals, int
 cudaError_t scvx_staged_init();          // kernel attributes of the current device (once per context and device)
 size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals);
 int scvx_staged_chunk_intervals(int sm_count);
-// shared_params != nullptr: every trajectory uses this one record; it travels in the kernel arguments (constant bank)
+// shared_params != nullptr: the record travels in the kernel arguments (constant bank).  sweep == false: every trajectory
+// uses it as is; sweep == true: the records of bt.P differ from it in `a` and `Tmin` only, which the kernels read per
+// trajectory from bt.P (mass / thrust-bound sweeps, BASELINE.json configs[3]).
 cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, const scvx_probinfo* shared_params,
-                               void* scratch, int chunk_intervals, int sm_count, cudaStream_t s, int* launches);
+                               bool sweep, void* scratch, int chunk_intervals, int sm_count, cudaStream_t s, int* launches);
 

@@ -61,7 +61,7 @@ constexpr int VALUE_SMEM_DOUBLES = 24 + (SCVX_A_PARK ? 28 : 0);
 __host__ __device__ constexpr size_t value_smem_bytes(int ts) {
     return (size_t)VALUE_SMEM_DOUBLES * value_threads(ts) * sizeof(double) + (ts == 3 ? 2 * WIN_I * WIN_J * sizeof(double) : 0);
 }
-template <bool SP, int TS>
+template <int SP, int TS>
 __global__ void __launch_bounds__(value_threads(TS), value_minblocks(TS)) stage_value_kernel(const __grid_constant__ StagedArgs a) {
     constexpr int VT = value_threads(TS);
     extern __shared__ double light_smem[];            // [24][VT] doubles (+ the staged tables)
@@ -87,6 +87,9 @@ __global__ void __launch_bounds__(value_threads(TS), value_minblocks(TS)) stage_
     const int w = a.first + (live ? t : a.count - 1);          // padded lanes recompute the last interval
     const int b = (int)(w / ni), i = (int)(w % ni);
     const scvx_probinfo& P = SP ? a.Pc : bt.P[bt.n_params == 1 ? 0 : b];
+    // SP == 2 (a mass / thrust-bound sweep): the records differ in `a` and `Tmin` only; those two come from the
+    // trajectory's own record, everything else from the shared one in the kernel arguments
+    const double pa = (SP == 2) ? __ldg(&bt.P[b].a) : ldp<SP>(&P.a);
     const double* xin = bt.X + ((size_t)b * bt.n_nodes + i) * 14;
     const double* uin = bt.U + ((size_t)b * bt.n_nodes + i) * 3;
     const double sigma = bt.sigma[b];
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(value_threads(TS), value_minblocks(TS)) stage_
             double uc[3], f[14], Fv[3][3], Fb[3][3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) uc[c] = (1.0 - pc) * um[c] + pc * up[c];
-            rhs_value<true, TS, SP>(P, tbl, y, uc, f, Fv, Fb);
+            rhs_value<true, TS, SP>(P, pa, tbl, y, uc, f, Fv, Fb);
             // record: m, v, q, w, f_v [, dF/dv, dF/db]  (u, f_m, f_q, f_w are re-formed by the producers)
             double* rp = rec + (size_t)(it * 4 + st) * ((size_t)a.rec_n * GROUP);
             if (a.rec_n == REC_AERO) {
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(value_threads(TS), value_minblocks(TS)) stage_
             const double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
             double* o = bt.out_tlb + ((size_t)b * bt.n_nodes + i + k) * 4;
             *reinterpret_cast<double2*>(o) = make_double2(-(u[0] / nu), -(u[1] / nu));
-            *reinterpret_cast<double2*>(o + 2) = make_double2(-(u[2] / nu), ldp<SP>(&P.Tmin) - nu);
+            *reinterpret_cast<double2*>(o + 2) = make_double2(-(u[2] / nu), ((SP == 2) ? __ldg(&bt.P[b].Tmin) : ldp<SP>(&P.Tmin)) - nu);
         }
     }
 }
@@ -333,7 +336,7 @@ struct __align__(16) StepSmem {
     uint64_t recfull[2][4];                  // [half][stage]: one waiting warp per barrier (it observes every phase)
 };
 
-template <bool SP>
+template <int SP>
 __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __grid_constant__ StagedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StepSmem& sm = *reinterpret_cast<StepSmem*>(smem_raw);
@@ -397,6 +400,7 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
                 int t = g * GROUP + lane; if (t >= a.count) t = a.count - 1;
                 const int b = (a.first + t) / ni;
                 const scvx_probinfo& P = SP ? a.Pc : bt.P[bt.n_params == 1 ? 0 : b];
+                const double pa = (SP == 2) ? __ldg(&bt.P[b].a) : ldp<SP>(&P.a);
                 const double sigma = __ldg(bt.sigma + b);
                 {   // the interval's node controls (the stage control is their FOH blend, re-formed per record)
                     const int ii = (a.first + t) - b * ni;
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
                     if (use > 0) mbar_wait(&sm.empty_step[half], (uint32_t)((use - 1) & 1));
                     const double pc = (kq == 0) ? pca : (kq == 3 ? pca + pcs : pca + 0.5 * pcs);     // as the value kernel
                     pca += pcs;
-                    produce_lean<SP>(P, a.Kw, a.Tw, a.rec_n == REC_AERO, sigma, stage_scale, sm.recbuf[kq] + lane,
+                    produce_lean<SP>(P, pa, a.Kw, a.Tw, a.rec_n == REC_AERO, sigma, stage_scale, sm.recbuf[kq] + lane,
                                      &sm.unode[kq][0][lane], pc, &sm.ring[half * 4 + kq][lane][0]);
                     mbar_arrive(&sm.full_step[half]);
                     __syncwarp();                        // every lane has finished reading recbuf[kq]
@@ -536,31 +540,34 @@ static int value_table_mode(const ScvxTables& tb, bool any_aero) {
 template <int TS>
 static cudaError_t value_kernel_attributes() {
     const int vs = (TS == 1 || TS == 2) ? 232448 : (int)value_smem_bytes(TS);
-    cudaError_t e = cudaFuncSetAttribute(stage_value_kernel<false, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, vs);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(stage_value_kernel<true, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, vs);
+    cudaError_t e = cudaFuncSetAttribute(stage_value_kernel<0, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, vs);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stage_value_kernel<1, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, vs);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stage_value_kernel<2, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, vs);
     return e;
 }
 
 cudaError_t scvx_staged_init() {
     cudaError_t e = value_kernel_attributes<0>();
     if (e == cudaSuccess && SCVX_A_SMEM_TABLES != 0) e = value_kernel_attributes<SCVX_A_SMEM_TABLES>();
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tangent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tangent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tangent_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tangent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tangent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
     return e;
 }
 
 template <int TS>
-static void launch_value(const StagedArgs& a, const ScvxTables& tb, bool shared, cudaStream_t s) {
+static void launch_value(const StagedArgs& a, const ScvxTables& tb, int sp, cudaStream_t s) {
     constexpr int VT = value_threads(TS);
     const int threads = a.n_groups * GROUP;
     size_t vsmem = value_smem_bytes(TS);
     if (TS == 1 || TS == 2) vsmem += (size_t)TS * (tb.n1 + 2) * (tb.n2 + 2) * sizeof(double);
-    if (shared) stage_value_kernel<true, TS><<<(threads + VT - 1) / VT, VT, vsmem, s>>>(a);
-    else stage_value_kernel<false, TS><<<(threads + VT - 1) / VT, VT, vsmem, s>>>(a);
+    if (sp == 2) stage_value_kernel<2, TS><<<(threads + VT - 1) / VT, VT, vsmem, s>>>(a);
+    else if (sp == 1) stage_value_kernel<1, TS><<<(threads + VT - 1) / VT, VT, vsmem, s>>>(a);
+    else stage_value_kernel<0, TS><<<(threads + VT - 1) / VT, VT, vsmem, s>>>(a);
 }
 
 cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, const scvx_probinfo* shared_params,
-                               void* scratch, int chunk_intervals, int sm_count, cudaStream_t s, int* launches) {
+                               bool sweep, void* scratch, int chunk_intervals, int sm_count, cudaStream_t s, int* launches) {
     const long total = (long)(bt.n_nodes - 1) * bt.B;
     const size_t smem = sizeof(StepSmem);
     for (long first = 0; first < total; first += chunk_intervals) {
@@ -593,10 +600,14 @@ cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool a
         a.count = (int)((total - first < chunk_intervals) ? (total - first) : chunk_intervals);
         a.n_groups = (a.count + GROUP - 1) / GROUP;
         const int grid = a.n_groups < sm_count ? a.n_groups : sm_count;
-        if (value_table_mode(tb, any_aero) != 0) launch_value<SCVX_A_SMEM_TABLES>(a, tb, shared_params != nullptr, s);
-        else launch_value<0>(a, tb, shared_params != nullptr, s);
-        if (shared_params) tangent_kernel<true><<<grid, TANGENT_THREADS, smem, s>>>(a);
-        else tangent_kernel<false><<<grid, TANGENT_THREADS, smem, s>>>(a);
+        // 0: one record per trajectory in global memory; 1: one shared record in the kernel arguments;
+        // 2: shared record + per-trajectory `a` / `Tmin` (the records of bt.P differ in those two fields only)
+        const int sp = !shared_params ? 0 : (sweep ? 2 : 1);
+        if (value_table_mode(tb, any_aero) != 0) launch_value<SCVX_A_SMEM_TABLES>(a, tb, sp, s);
+        else launch_value<0>(a, tb, sp, s);
+        if (sp == 2) tangent_kernel<2><<<grid, TANGENT_THREADS, smem, s>>>(a);
+        else if (sp == 1) tangent_kernel<1><<<grid, TANGENT_THREADS, smem, s>>>(a);
+        else tangent_kernel<0><<<grid, TANGENT_THREADS, smem, s>>>(a);
         if (launches) *launches += 2;
     }
     return cudaGetLastError();

@@ -50,11 +50,11 @@ struct StagedArgs {
 // Parameter access.  SP = the record is shared by every trajectory and sits in the kernel arguments (constant bank):
 // plain reads, which the compiler folds into instruction operands.  Otherwise one record per trajectory in global
 // memory, read through the read-only path.
-template <bool SP> __device__ __forceinline__ double ldp(const double* p) {
-    if constexpr (SP) return *p; else return __ldg(p);
+template <int SP> __device__ __forceinline__ double ldp(const double* p) {
+    if constexpr (SP != 0) return *p; else return __ldg(p);
 }
-template <bool SP> __device__ __forceinline__ int ldpi(const int32_t* p) {
-    if constexpr (SP) return *p; else return __ldg(p);
+template <int SP> __device__ __forceinline__ int ldpi(const int32_t* p) {
+    if constexpr (SP != 0) return *p; else return __ldg(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -127,7 +127,7 @@ __device__ __forceinline__ void spline_val_grad(const double* __restrict__ coef,
 // Jacobian of the aerodynamic force F(b, v) (aerodynamics.jl:38-58) w.r.t. v and b = C(q) e1: exact derivative
 // of the executed branch (|dp| >= 0.95 drag only; clamp active only strictly outside [-1,1]).
 // TS = tables staged in shared memory: 0 none, 1 drag, 2 drag + lift (tb.drag / tb.lift then point there), 3 a window of both.
-template <int TS = 0, bool SP = false>
+template <int TS = 0, int SP = 0>
 __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const ScvxTables& tb, const double b[3],
                                                const double v[3], double F[3], double Fv[3][3], double Fb[3][3]) {
     const double vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
@@ -235,8 +235,8 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
 
 // unscaled f(x,u) (dx_static without the `.* mult`, dynamics.jl:54-77) together with the Jacobians of the
 // aerodynamic force w.r.t. v and b = C(q) e1 (zero for the exo-atmospheric variant).
-template <bool JAC, int TS = 0, bool SP = false>
-__device__ __forceinline__ void rhs_value(const scvx_probinfo& P, const ScvxTables& tb, const double x[14],
+template <bool JAC, int TS = 0, int SP = 0>
+__device__ __forceinline__ void rhs_value(const scvx_probinfo& P, double pa, const ScvxTables& tb, const double x[14],
                                           const double u[3], double f[14], double Fv[3][3], double Fb[3][3]) {
     const double q0 = x[7], q1 = x[8], q2 = x[9], q3 = x[10];
     const double w0 = x[11], w1 = x[12], w2 = x[13];
@@ -256,7 +256,7 @@ __device__ __forceinline__ void rhs_value(const scvx_probinfo& P, const ScvxTabl
             for (int c = 0; c < 3; ++c) { Fv[r][c] = 0.0; Fb[r][c] = 0.0; }
     }
     const double im = 1.0 / x[0];
-    f[0] = -ldp<SP>(&P.a) * sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    f[0] = -pa * sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
     f[1] = x[4]; f[2] = x[5]; f[3] = x[6];
     f[4] = (c00 * u[0] + c01 * u[1] + c02 * u[2] + F[0]) * im - ldp<SP>(&P.g0);
     f[5] = (c10 * u[0] + c11 * u[1] + c12 * u[2] + F[1]) * im;
@@ -324,8 +324,8 @@ __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpre
 // out: this lane's NJ-double Jacobian record in the ring (the caller has waited for the slot).  The record is formed
 // and stored block by block, so only a few values are live at any time; every block that enters a stage increment
 // carries sigma * scale (scale = the stage's rk4 factor, see consume_stage8), the quadrature entries (v, sigma) do not.
-template <bool SP = false>
-__device__ __forceinline__ void produce_lean(const scvx_probinfo& P, const double* __restrict__ Kw,
+template <int SP = 0>
+__device__ __forceinline__ void produce_lean(const scvx_probinfo& P, double pa, const double* __restrict__ Kw,
                                              const double* __restrict__ Tw, bool aero_rec, double sigma,
                                              double scale, const double* __restrict__ rec, const double* __restrict__ unode,
                                              double pc, double* __restrict__ out) {
@@ -393,13 +393,13 @@ __device__ __forceinline__ void produce_lean(const scvx_probinfo& P, const doubl
         const double c10 = 2.0 * (q1 * q2 + q0 * q3), c11 = 1.0 - 2.0 * (q1 * q1 + q3 * q3), c12 = 2.0 * (q2 * q3 - q0 * q1);
         const double c20 = 2.0 * (q1 * q3 - q0 * q2), c21 = 2.0 * (q2 * q3 + q0 * q1), c22 = 1.0 - 2.0 * (q1 * q1 + q2 * q2);
         const double nu = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
-        const double gm = -ss * ldp<SP>(&P.a) / nu;
+        const double gm = -ss * pa / nu;
         const double r0 = ldp<SP>(&P.rTB[0]), r1 = ldp<SP>(&P.rTB[1]), r2 = ldp<SP>(&P.rTB[2]);
         double* G = out + J_G;
         // jBi * (rTB x e_j): rTB x e0 = (0, r2, -r1); x e1 = (-r2, 0, r0); x e2 = (r1, -r0, 0) — constant per parameter
         // record: taken from the kernel arguments when the record is shared (SP), formed here otherwise
         double kw[9];
-        if constexpr (SP) {
+        if constexpr (SP != 0) {
 #pragma unroll
             for (int k = 0; k < 9; ++k) kw[k] = Kw[k];
         } else {
@@ -425,7 +425,7 @@ __device__ __forceinline__ void produce_lean(const scvx_probinfo& P, const doubl
             const double w0 = rec[8 * GROUP], w1 = rec[9 * GROUP], w2 = rec[10 * GROUP];
             // fwq = -jBi (w x jB w), the rate-dependent part of f_w (the producer adds jBi (rTB x u) below).  d(wdot)/dw is
             // linear in w and  (d(wdot)/dw) w = -2 jBi (w x jB w),  so fwq = (Jww / ss) w / 2
-            if constexpr (SP) {
+            if constexpr (SP != 0) {
                 const double s0 = ss * w0, s1 = ss * w1, s2 = ss * w2;
                 auto jw = [&](int k) { return fma(s2, Tw[18 + k], fma(s1, Tw[9 + k], s0 * Tw[k])); };
                 const double j0 = jw(0), j1 = jw(1), j2 = jw(2), j3 = jw(3), j4 = jw(4), j5 = jw(5), j6 = jw(6), j7 = jw(7), j8 = jw(8);
@@ -471,7 +471,7 @@ __device__ __forceinline__ void produce_lean(const scvx_probinfo& P, const doubl
         const double fw0 = fma(kw[6], u2, fma(kw[3], u1, fma(kw[0], u0, fwq[0])));
         const double fw1 = fma(kw[7], u2, fma(kw[4], u1, fma(kw[1], u0, fwq[1])));
         const double fw2 = fma(kw[8], u2, fma(kw[5], u1, fma(kw[2], u0, fwq[2])));
-        st2(G + 20, ss * kw[8], -(scale * ldp<SP>(&P.a)) * nu);
+        st2(G + 20, ss * kw[8], -(scale * pa) * nu);
         st2(G + 22, scale * rec[R_FV * GROUP], scale * rec[(R_FV + 1) * GROUP]);
         st2(G + 24, scale * rec[(R_FV + 2) * GROUP], scale * fw0);
         st2(G + 26, scale * fw1, scale * fw2);

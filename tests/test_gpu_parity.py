@@ -760,6 +760,52 @@ def test_mixed_aero_kinds_in_one_batch(dyn, prob_aero, oracle_tables, kernel):
     assert np.array_equal(blocks[0, :, 5:8, 4:7], np.broadcast_to(np.eye(3), (9, 3, 3)))
 
 
+def test_per_trajectory_records_sweep_and_generic_paths(dyn, prob_aero, oracle_tables):
+    """Per-trajectory records take one of two STAGED paths: records that differ in `a` / `Tmin` only (a mass /
+    thrust-bound sweep, BASELINE.json configs[3]) keep the shared record in the kernel arguments and read those two
+    fields per trajectory; anything else reads whole records from global memory.  Both against the checker and against
+    each other, on a batch that spans more than one pipeline chunk of the host path (256 MiB of blocks per chunk: 5 210
+    trajectories of 20 intervals), so the per-chunk record offsets are exercised too."""
+    from successiveconvexification_b200 import workloads
+    rng = np.random.default_rng(77)
+    K, B, dt = 20, 5400, 1.0 / 21
+    X, U, sigma, P = workloads.monte_carlo_batch(prob_aero, K, B, 4711, sweep=True, sigma_range=(0.8, 1.5))
+    cache = dyn.make_cache(prob_aero)
+    cache.sim_prob.set_kernel(0)
+
+    def run(params, mode):
+        ptr, n, keep = workloads.as_c_params(params)
+        cache.sim_prob.set_params_raw(ptr, n)
+        return dyn.linearize_batch(cache, X, U, sigma, dt, 10, mode)
+
+    # (a) sweep records; (b) the same records with a jitter on rFB — a field the 3-control dynamics never reads —
+    # which sends the call down the generic path with identical mathematics
+    Pg = P.copy()
+    Pg["rFB"] += rng.normal(0.0, 1e-3, (B, 3))
+    # (c) records that differ everywhere: gravity, speed of sound, inertia (with its inverse), gimbal arm, force scale
+    Pf = P.copy()
+    Pf["g0"] *= rng.uniform(0.9, 1.1, B)
+    Pf["sos"] *= rng.uniform(0.9, 1.1, B)
+    Pf["force_scalar"] *= rng.uniform(0.8, 1.2, B)
+    Pf["rTB"] *= rng.uniform(0.9, 1.1, (B, 1))
+    sc = rng.uniform(0.8, 1.25, B)
+    Pf["jB"] *= sc[:, None]
+    Pf["jBi"] /= sc[:, None]
+    for mode in (0, 1):
+        ba, ea, ta = run(P, mode)
+        bg, eg, tg = run(Pg, mode)
+        ref, rerr, rtlb, _ = _oracle().linearize_batch(P, oracle_tables, X, U, sigma, dt, 10, mode)
+        assert_parity(ba, ref)
+        assert_parity(bg, ref)
+        assert np.abs(ta - rtlb).max() <= 1e-15 and np.array_equal(ta, tg)
+        scale = np.maximum(1.0, np.abs(ref).max(axis=(-2, -1), keepdims=True))
+        assert (np.abs(ba - bg) / scale).max() <= 1e-12
+        bf, ef, tf = run(Pf, mode)
+        reff, _, rtlbf, _ = _oracle().linearize_batch(Pf, oracle_tables, X, U, sigma, dt, 10, mode)
+        assert_parity(bf, reff)
+        assert np.abs(tf - rtlbf).max() <= 1e-15
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_large_tables_fall_back_to_the_global_memory_path(dyn, prob_aero, kernel):
     """The value kernel stages the drag table in shared memory when it fits (92 KB for the reference's 181 x 61 grid); a
