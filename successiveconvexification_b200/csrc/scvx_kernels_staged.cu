@@ -22,6 +22,7 @@
 //      registers are re-partitioned between the roles with setmaxnreg.  [A|B-|B+|Sigma] go from registers to the
 //      14x23 block with 16-byte stores; z is reduced over the 8 lanes and accumulated in place.
 #include "scvx_staged_dev.cuh"
+#include <cstdlib>
 #include "scvx_kernels.h"
 
 namespace {
@@ -61,10 +62,21 @@ constexpr int VALUE_SMEM_DOUBLES = 24 + (SCVX_A_PARK ? 28 : 0);
 __host__ __device__ constexpr size_t value_smem_bytes(int ts) {
     return (size_t)VALUE_SMEM_DOUBLES * value_threads(ts) * sizeof(double) + (ts == 3 ? 2 * WIN_I * WIN_J * sizeof(double) : 0);
 }
+// Programmatic dependent launch: the tangent kernel carries cudaLaunchAttributeProgrammaticStreamSerialization and the
+// value kernel releases its dependents as its blocks start, so the blocks of T_c become resident — barriers initialised —
+// on the SMs that V_c's last wave leaves, and wait there for V_c to complete: +0.15 %.  Measured and not adopted
+// (profiles/r2_ab_pdl_*.txt): T_c starting its passes as the value-kernel blocks publish their records through per-block
+// flags (+0.05 % more, for a spin-wait in the product); V_{c+1} moving into the SMs that T_c's blocks leave, over two
+// record buffers (-1.3 to -1.5 %, wherever T_c releases its dependents).
+// Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <int SP, int TS>
 __global__ void __launch_bounds__(value_threads(TS), value_minblocks(TS)) stage_value_kernel(const __grid_constant__ StagedArgs a) {
     constexpr int VT = value_threads(TS);
     extern __shared__ double light_smem[];            // [24][VT] doubles (+ the staged tables)
+    pdl_launch_dependents();                          // T_c may take the SMs this grid's last wave leaves (it waits for this grid)
     ScvxTables tbl = a.tb;
     if constexpr (TS == 1 || TS == 2) {
         const int ncoef = (a.tb.n1 + 2) * (a.tb.n2 + 2);
@@ -356,6 +368,7 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_wait();                                       // V_c is complete, its stage records and partial z are visible
 
     const int my_groups = (a.n_groups > (int)blockIdx.x) ? (a.n_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int total_steps = my_groups * npts;          // global step counter n = pass * npts + local step
@@ -555,24 +568,39 @@ cudaError_t scvx_staged_init() {
     return e;
 }
 
+// Launch with or without programmatic stream serialisation (see pdl_wait above).
+template <typename K>
+static cudaError_t launch_pdl(K kernel, unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool programmatic,
+                              const StagedArgs& a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = programmatic ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 template <int TS>
-static void launch_value(const StagedArgs& a, const ScvxTables& tb, int sp, cudaStream_t s) {
+static cudaError_t launch_value(const StagedArgs& a, const ScvxTables& tb, int sp, cudaStream_t s, bool programmatic) {
     constexpr int VT = value_threads(TS);
-    const int threads = a.n_groups * GROUP;
+    const unsigned grid = (unsigned)((a.n_groups * GROUP + VT - 1) / VT);
     size_t vsmem = value_smem_bytes(TS);
     if (TS == 1 || TS == 2) vsmem += (size_t)TS * (tb.n1 + 2) * (tb.n2 + 2) * sizeof(double);
-    if (sp == 2) stage_value_kernel<2, TS><<<(threads + VT - 1) / VT, VT, vsmem, s>>>(a);
-    else if (sp == 1) stage_value_kernel<1, TS><<<(threads + VT - 1) / VT, VT, vsmem, s>>>(a);
-    else stage_value_kernel<0, TS><<<(threads + VT - 1) / VT, VT, vsmem, s>>>(a);
+    if (sp == 2) return launch_pdl(stage_value_kernel<2, TS>, grid, VT, vsmem, s, programmatic, a);
+    if (sp == 1) return launch_pdl(stage_value_kernel<1, TS>, grid, VT, vsmem, s, programmatic, a);
+    return launch_pdl(stage_value_kernel<0, TS>, grid, VT, vsmem, s, programmatic, a);
 }
 
 cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool any_aero, const scvx_probinfo* shared_params,
                                bool sweep, void* scratch, int chunk_intervals, int sm_count, cudaStream_t s, int* launches) {
     const long total = (long)(bt.n_nodes - 1) * bt.B;
     const size_t smem = sizeof(StepSmem);
+    static const bool pdl = !(getenv("SCVX_PDL") && atoi(getenv("SCVX_PDL")) == 0);     // SCVX_PDL=0: plain launches (A/B)
     for (long first = 0; first < total; first += chunk_intervals) {
         StagedArgs a;
         a.bt = bt; a.tb = tb; a.rec = (double*)scratch; a.first = (int)first;
+        const int ts = value_table_mode(tb, any_aero);
         if (shared_params) {
             a.Pc = *shared_params;
             const double* bi = a.Pc.jBi;
@@ -603,11 +631,14 @@ cudaError_t scvx_launch_staged(const ScvxBatch& bt, const ScvxTables& tb, bool a
         // 0: one record per trajectory in global memory; 1: one shared record in the kernel arguments;
         // 2: shared record + per-trajectory `a` / `Tmin` (the records of bt.P differ in those two fields only)
         const int sp = !shared_params ? 0 : (sweep ? 2 : 1);
-        if (value_table_mode(tb, any_aero) != 0) launch_value<SCVX_A_SMEM_TABLES>(a, tb, sp, s);
-        else launch_value<0>(a, tb, sp, s);
-        if (sp == 2) tangent_kernel<2><<<grid, TANGENT_THREADS, smem, s>>>(a);
-        else if (sp == 1) tangent_kernel<1><<<grid, TANGENT_THREADS, smem, s>>>(a);
-        else tangent_kernel<0><<<grid, TANGENT_THREADS, smem, s>>>(a);
+        cudaError_t e;
+        if (ts != 0) e = launch_value<SCVX_A_SMEM_TABLES>(a, tb, sp, s, false);
+        else e = launch_value<0>(a, tb, sp, s, false);
+        if (e != cudaSuccess) return e;
+        if (sp == 2) e = launch_pdl(tangent_kernel<2>, grid, TANGENT_THREADS, smem, s, pdl, a);
+        else if (sp == 1) e = launch_pdl(tangent_kernel<1>, grid, TANGENT_THREADS, smem, s, pdl, a);
+        else e = launch_pdl(tangent_kernel<0>, grid, TANGENT_THREADS, smem, s, pdl, a);
+        if (e != cudaSuccess) return e;
         if (launches) *launches += 2;
     }
     return cudaGetLastError();
