@@ -23,6 +23,15 @@ VARIANTS = {
     "smem_drag": ["-DSCVX_A_SMEM_TABLES=1"],
     "smem_both": ["-DSCVX_A_SMEM_TABLES=2"],
     "smem_window": ["-DSCVX_A_SMEM_TABLES=3"],
+    "hoist_lift": ["-DSCVX_A_HOIST_LIFT=1"],
+    "mbar_hint": ["-DSCVX_MBAR_HINT=10000000"],
+    "mbar_hint_1us": ["-DSCVX_MBAR_HINT=1000"],
+    "producer_sleep200": ["-DSCVX_PRODUCER_SLEEP_NS=200"],
+    "producer_sleep1000": ["-DSCVX_PRODUCER_SLEEP_NS=1000"],
+    "producer_sleep500": ["-DSCVX_PRODUCER_SLEEP_NS=500"],
+    "producer_sleep3000": ["-DSCVX_PRODUCER_SLEEP_NS=3000"],
+    "sleep500_rec100": ["-DSCVX_PRODUCER_SLEEP_NS=500", "-DSCVX_RECORD_SLEEP_NS=100"],
+    "sleep500_rec400": ["-DSCVX_PRODUCER_SLEEP_NS=500", "-DSCVX_RECORD_SLEEP_NS=400"],
 }
 
 

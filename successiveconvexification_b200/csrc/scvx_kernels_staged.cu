@@ -54,6 +54,8 @@ namespace {
 //      the lift table (one branch only) through L1: +0.8 % with the LITERAL rule at sigma ~ U(1, 15), -2.6 % with the
 //      TEXTBOOK rule (one 256-thread block per SM drains less evenly than two of 128) — not the default;
 //   2  drag + lift tables (184 KB) staged; one block of 224 threads per SM (what fits beside the light-column state): -1.7 %;
+//   (a PATCH-EXPANDED global copy — the 16 coefficients of a cell and table in one 128-byte line — was measured too:
+//      -6 % / -8 %, profiles/r2_ab_patch_table.txt: neighbouring cells no longer share lines, the copy is 16x the table)
 //   3  a WIN_I x WIN_J WINDOW of both tables around the block's starting (cos aoa, Mach) cells (18 KB per block; two blocks
 //      of 128 threads per SM as in 0), 4 x 4 patches outside the window from global memory: -6.8 % (generic loads, spills).
 __host__ __device__ constexpr int value_threads(int ts) { return (ts == 1) ? 256 : (ts == 2 ? 224 : 128); }
@@ -348,6 +350,9 @@ struct __align__(16) StepSmem {
     uint64_t recfull[2][4];                  // [half][stage]: one waiting warp per barrier (it observes every phase)
 };
 
+#ifndef SCVX_RECORD_SLEEP_NS
+#define SCVX_RECORD_SLEEP_NS 0
+#endif
 template <int SP>
 __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __grid_constant__ StagedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -432,8 +437,8 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
                     // DRAM round trip
                     if (lane == 0 && more) bulk_prefetch_l2(record_src(nit, nls), rec_bytes);
                     const int half = n & 1, use = n >> 1;
-                    mbar_wait(&sm.recfull[half][kq], (uint32_t)(use & 1));      // this warp is the only waiter of recfull[half][kq]
-                    if (use > 0) mbar_wait(&sm.empty_step[half], (uint32_t)((use - 1) & 1));
+                    mbar_wait_relaxed<SCVX_RECORD_SLEEP_NS>(&sm.recfull[half][kq], (uint32_t)(use & 1));      // this warp is the only waiter of recfull[half][kq]
+                    if (use > 0) mbar_wait_relaxed(&sm.empty_step[half], (uint32_t)((use - 1) & 1));
                     const double pc = (kq == 0) ? pca : (kq == 3 ? pca + pcs : pca + 0.5 * pcs);     // as the value kernel
                     pca += pcs;
                     produce_lean<SP>(P, pa, a.Kw, a.Tw, a.rec_n == REC_AERO, sigma, stage_scale, sm.recbuf[kq] + lane,

@@ -62,6 +62,9 @@ template <int SP> __device__ __forceinline__ int ldpi(const int32_t* p) {
 // ------------------------------------------------------------------------------------------------
 // spline value and gradient w.r.t. the physical coordinates (gradient 0 when strictly outside: Flat extrapolation);
 // one pass over the 16 coefficients serves all three.
+#ifndef SCVX_A_HOIST_LIFT
+#define SCVX_A_HOIST_LIFT 0
+#endif
 #ifndef SCVX_A_EVICT_LAST
 #define SCVX_A_EVICT_LAST 0
 #endif
@@ -154,6 +157,12 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
     double drag, gx, gy;
     spline_val_grad<(TS == 1 || TS == 2), (TS == 3)>(tb.drag, tb.wdrag, tb, ca, mach, drag, gx, gy);
     drag *= fs; gx *= fs; gy *= fs;
+#if SCVX_A_HOIST_LIFT
+    // the lift spline is evaluated here, ahead of the |dp| branch that decides whether it is used: its loads then overlap
+    // the drag Jacobian below instead of standing alone behind the branch
+    double lift, lgx, lgy;
+    spline_val_grad<(TS == 2), (TS == 3)>(tb.lift, tb.wlift, tb, ca, mach, lift, lgx, lgy);
+#endif
     double dv[3], db[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { dv[k] = gx * cav[k] + gy * mv[k]; db[k] = gx * cab[k]; }
@@ -168,9 +177,16 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
         }
     }
     if (fabs(dp) >= 0.95) return;
+    // (the lift coefficients are read behind this branch with nothing left to overlap their latency: 18 % of the kernel's
+    // stall samples.  prefetch.global.L1 of their four rows before the drag evaluation: -6 % LITERAL, -37 % TEXTBOOK,
+    // profiles/r2_ab_prefetch_lift.txt)
+#if SCVX_A_HOIST_LIFT
+    lift *= fs; gx = lgx * fs; gy = lgy * fs;
+#else
     double lift;
     spline_val_grad<(TS == 2), (TS == 3)>(tb.lift, tb.wlift, tb, ca, mach, lift, gx, gy);
     lift *= fs; gx *= fs; gy *= fs;
+#endif
     double lv[3], lb[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { lv[k] = gx * cav[k] + gy * mv[k]; lb[k] = gx * cab[k]; }
@@ -294,7 +310,23 @@ __device__ __forceinline__ void mbar_arrive_lane0(uint64_t* bar, int lane) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n }" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// SCVX_MBAR_HINT: suspend-time hint (ns) on try_wait — the warp stays suspended until the phase completes or the time is
+// up, instead of re-issuing the instruction (A/B: profiles/r2_ab_mbar_wait.txt)
+#ifndef SCVX_MBAR_HINT
+#define SCVX_MBAR_HINT 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if SCVX_MBAR_HINT
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        " @p bra WAIT_DONE;\n"
+        " bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SCVX_MBAR_HINT) : "memory");
+#else
     asm volatile(
         "{\n"
         " .reg .pred p;\n"
@@ -304,6 +336,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         " bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
+}
+// Wait of a warp that is usually far ahead (the producers, on a free ring slot): back off between polls.  A polling
+// producer re-issued try_wait 35 times per step — 7.4 % of the instructions of the kernel (ncu source view), one polling
+// warp on every scheduler beside the two consumer warps it was waiting for.  With the back-off the step is 2.5 % faster;
+// 200 ns to 3 us all measure the same, a suspend-time hint on try_wait does not help (profiles/r2_ab_mbar_wait*.txt).
+#ifndef SCVX_PRODUCER_SLEEP_NS
+#define SCVX_PRODUCER_SLEEP_NS 200
+#endif
+template <int NS = SCVX_PRODUCER_SLEEP_NS>
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    if constexpr (NS > 0) {
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            " .reg .pred p;\n"
+            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        __nanosleep(NS);
+    }
+    } else {
+        mbar_wait(bar, parity);
+    }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
