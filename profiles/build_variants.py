@@ -24,6 +24,10 @@ VARIANTS = {
     "smem_both": ["-DSCVX_A_SMEM_TABLES=2"],
     "smem_window": ["-DSCVX_A_SMEM_TABLES=3"],
     "hoist_lift": ["-DSCVX_A_HOIST_LIFT=1"],
+    "first_body": ["-DSCVX_T_FIRST_BODY=1"],
+    "no_first_body": ["-DSCVX_T_FIRST_BODY=0"],
+    "four_bodies": ["-DSCVX_T_FIRST_BODY=2"],
+    "step_unroll2": ["-DSCVX_T_STEP_UNROLL=2"],
     "mbar_hint": ["-DSCVX_MBAR_HINT=10000000"],
     "mbar_hint_1us": ["-DSCVX_MBAR_HINT=1000"],
     "producer_sleep200": ["-DSCVX_PRODUCER_SLEEP_NS=200"],

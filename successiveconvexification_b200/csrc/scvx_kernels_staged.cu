@@ -350,6 +350,13 @@ struct __align__(16) StepSmem {
     uint64_t recfull[2][4];                  // [half][stage]: one waiting warp per barrier (it observes every phase)
 };
 
+// SCVX_T_FIRST_BODY: the first stage of a step runs its own instantiation of consume_stage8 (see there)
+#ifndef SCVX_T_FIRST_BODY
+#define SCVX_T_FIRST_BODY 2
+#endif
+#ifndef SCVX_T_STEP_UNROLL
+#define SCVX_T_STEP_UNROLL 2
+#endif
 #ifndef SCVX_RECORD_SLEEP_NS
 #define SCVX_RECORD_SLEEP_NS 0
 #endif
@@ -482,19 +489,36 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
         const double xcA = inp_of(colA), xcB = inp_of(colB);
 
         double pca = 0.0;
+#if SCVX_T_STEP_UNROLL > 1
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
         for (int ls = 0; ls < npts; ++ls, ++n) {
             // ---- consume the four stages of step n
             const int half = n & 1;
             mbar_wait(&sm.full_step[half], (uint32_t)((n >> 1) & 1));
             const double* J0 = &sm.ring[half * 4][warp * 4 + sub][0];
+#if SCVX_T_FIRST_BODY
+            consume_stage8<0>(FA, FB, J0, gcol, fma(cA1, pca, cA0), dsA, 1.0, h6, kappa, nullptr, lane);
+#if SCVX_T_FIRST_BODY == 2
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+            for (int k = 1; k < 3; ++k)
+                consume_stage8<1>(FA, FB, J0 + k * (GROUP * NJ), gcol, fma(cA1, pca + 0.5 * pcs, cA0), dsA, k == 1 ? 2.0 : 1.0,
+                                  2.0 * h6, kappa, nullptr, lane);
+            consume_stage8<2>(FA, FB, J0 + 3 * (GROUP * NJ), gcol, fma(cA1, pca + pcs, cA0), dsA, 1.0, h6, kappa, nullptr, lane);
+#else
 #pragma unroll 1
             for (int k = 0; k < 3; ++k) {
                 const double pc = (k == 0) ? pca : pca + 0.5 * pcs;
-                consume_stage8<false>(FA, FB, J0 + k * (GROUP * NJ), gcol, fma(cA1, pc, cA0), dsA, k == 1 ? 2.0 : 1.0,
-                                      k == 0 ? h6 : 2.0 * h6, kappa, nullptr, lane);
+                consume_stage8<1>(FA, FB, J0 + k * (GROUP * NJ), gcol, fma(cA1, pc, cA0), dsA, k == 1 ? 2.0 : 1.0,
+                                  k == 0 ? h6 : 2.0 * h6, kappa, nullptr, lane);
             }
-            consume_stage8<true>(FA, FB, J0 + 3 * (GROUP * NJ), gcol, fma(cA1, pca + pcs, cA0), dsA, 1.0, h6, kappa, nullptr, lane);
+            consume_stage8<3>(FA, FB, J0 + 3 * (GROUP * NJ), gcol, fma(cA1, pca + pcs, cA0), dsA, 1.0, h6, kappa, nullptr, lane);
+#endif
             __syncwarp();
             mbar_arrive_lane0(&sm.empty_step[half], lane);           // the four slabs of this step are free again
             pca += pcs;

@@ -560,11 +560,16 @@ struct FullCol {
 // (s = 1 LITERAL, h TEXTBOOK):   S_new = S + kappa (T - 4 S) + (h/6) K_4,  the last term again a chain started from
 // the first two.  T - 4S cancels exactly for entries that never move, so constants of D stay exact.
 // 11 % fewer FP64 instructions per stage than forming K, acc += w K, Y = S + c K.
-template <bool LAST>
+// KIND: 0 = first stage of a step (Y == S: the stage reads S, and A is written rather than accumulated, so that the last
+// stage of the previous step neither copies S into Y nor clears A), 1 = middle stage, 2 = last stage, 3 = last stage that
+// also sets Y = S and A = 0 (for a step whose first stage runs the middle-stage body: SCVX_T_FIRST_BODY = 0).
+template <int KIND>
 __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const double* __restrict__ J, const int gcol,
                                                const double alA, const double dsA, const double tw, const double cr,
                                                const double kappa, uint64_t* empty_bar, const int lane) {
-    constexpr bool last = LAST;
+    constexpr bool last = (KIND >= 2), first = (KIND == 0);
+    const double* const YA = first ? FA.S : FA.Y;
+    const double* const YB = first ? FB.S : FB.Y;
     // slot A: lanes 0..2 B- (alA = 1 - pc), 3..5 B+ (alA = pc), 6 Sigma (direct term = the f column, alA = 1, dsA = 1),
     // 7 the light column d/dm (no direct term): alA = cA0 + cA1 * pc with per-lane constants, formed by the caller
     const double* Gc = J + J_G + 7 * gcol;
@@ -573,8 +578,9 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
         else return fma(kappa, fma(-4.0, F.S[idx], F.A[idx]), F.S[idx]);
     };
     auto fin = [&](FullCol& F, const int idx, const double yn) {
-        if constexpr (!last) { F.A[idx] = fma(tw, yn, F.A[idx]); F.Y[idx] = yn; }
-        else { F.S[idx] = yn; F.Y[idx] = yn; F.A[idx] = 0.0; }
+        if constexpr (first) { F.A[idx] = tw * yn; F.Y[idx] = yn; }
+        else if constexpr (!last) { F.A[idx] = fma(tw, yn, F.A[idx]); F.Y[idx] = yn; }
+        else { F.S[idx] = yn; if constexpr (KIND == 3) { F.Y[idx] = yn; F.A[idx] = 0.0; } }
     };
     // ---- r rows (pure quadrature): S_r += cr * (sigma * Y_v + dsigma * f_r),  cr = h/6 * rk4 weight
     {
@@ -582,11 +588,11 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
         const double fr2 = J[J_FRQ + 2];
         const double sg = J[J_FRQ + 7];
         const double csg = cr * sg, cds = cr * dsA;
-        FA.Sr[0] = fma(csg, FA.Y[1], fma(cds, fr01.x, FA.Sr[0]));
-        FA.Sr[1] = fma(csg, FA.Y[2], fma(cds, fr01.y, FA.Sr[1]));
-        FA.Sr[2] = fma(csg, FA.Y[3], fma(cds, fr2, FA.Sr[2]));
+        FA.Sr[0] = fma(csg, YA[1], fma(cds, fr01.x, FA.Sr[0]));
+        FA.Sr[1] = fma(csg, YA[2], fma(cds, fr01.y, FA.Sr[1]));
+        FA.Sr[2] = fma(csg, YA[3], fma(cds, fr2, FA.Sr[2]));
 #pragma unroll
-        for (int r = 0; r < 3; ++r) FB.Sr[r] = fma(csg, FB.Y[1 + r], FB.Sr[r]);
+        for (int r = 0; r < 3; ++r) FB.Sr[r] = fma(csg, YB[1 + r], FB.Sr[r]);
     }
     // ---- v rows: Jvm Y_m + Jvv Y_v + Jvq Y_q + alpha * G_v
     {
@@ -596,10 +602,10 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
             const double2 c01 = ld2(J + J_V + 8 * row), c23 = ld2(J + J_V + 8 * row + 2);
             const double2 qa = ld2(J + J_V + 8 * row + 4), qb = ld2(J + J_V + 8 * row + 6);
             const double gg = Gc[1 + row];
-            kA[row] = fma(c01.x, FA.Y[0], fma(c01.y, FA.Y[1], fma(c23.x, FA.Y[2], fma(c23.y, FA.Y[3],
-                      fma(qa.x, FA.Y[4], fma(qa.y, FA.Y[5], fma(qb.x, FA.Y[6], fma(qb.y, FA.Y[7], fma(alA, gg, init(FA, 1 + row))))))))));
-            kB[row] = fma(c01.y, FB.Y[1], fma(c23.x, FB.Y[2], fma(c23.y, FB.Y[3],
-                      fma(qa.x, FB.Y[4], fma(qa.y, FB.Y[5], fma(qb.x, FB.Y[6], fma(qb.y, FB.Y[7], init(FB, 1 + row))))))));
+            kA[row] = fma(c01.x, YA[0], fma(c01.y, YA[1], fma(c23.x, YA[2], fma(c23.y, YA[3],
+                      fma(qa.x, YA[4], fma(qa.y, YA[5], fma(qb.x, YA[6], fma(qb.y, YA[7], fma(alA, gg, init(FA, 1 + row))))))))));
+            kB[row] = fma(c01.y, YB[1], fma(c23.x, YB[2], fma(c23.y, YB[3],
+                      fma(qa.x, YB[4], fma(qa.y, YB[5], fma(qb.x, YB[6], fma(qb.y, YB[7], init(FB, 1 + row))))))));
         }
 #pragma unroll
         for (int r = 0; r < 3; ++r) { fin(FA, 1 + r, kA[r]); fin(FB, 1 + r, kB[r]); }
@@ -619,13 +625,13 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
         const double2 fq12 = ld2(J + J_FRQ + 4);
         const double fq3 = J[J_FRQ + 6];
         double kA[4], kB[4];
-#define QROWS(F, K, i0, i1, i2, i3)                                                                                                  \
-        K[0] = fma(-hw0, F.Y[5], fma(-hw1, F.Y[6], fma(-hw2, F.Y[7], fma(-hq1, F.Y[8], fma(-hq2, F.Y[9], fma(-hq3, F.Y[10], i0))))));   \
-        K[1] = fma(hw0, F.Y[4], fma(hw2, F.Y[6], fma(-hw1, F.Y[7], fma(hq0, F.Y[8], fma(hq2, F.Y[10], fma(-hq3, F.Y[9], i1))))));       \
-        K[2] = fma(hw1, F.Y[4], fma(-hw2, F.Y[5], fma(hw0, F.Y[7], fma(hq0, F.Y[9], fma(-hq1, F.Y[10], fma(hq3, F.Y[8], i2))))));       \
-        K[3] = fma(hw2, F.Y[4], fma(hw1, F.Y[5], fma(-hw0, F.Y[6], fma(hq0, F.Y[10], fma(hq1, F.Y[9], fma(-hq2, F.Y[8], i3))))));
-        QROWS(FA, kA, fma(dsA, fq0, init(FA, 4)), fma(dsA, fq12.x, init(FA, 5)), fma(dsA, fq12.y, init(FA, 6)), fma(dsA, fq3, init(FA, 7)))
-        QROWS(FB, kB, init(FB, 4), init(FB, 5), init(FB, 6), init(FB, 7))
+#define QROWS(Yp, K, i0, i1, i2, i3)                                                                                                  \
+        K[0] = fma(-hw0, Yp[5], fma(-hw1, Yp[6], fma(-hw2, Yp[7], fma(-hq1, Yp[8], fma(-hq2, Yp[9], fma(-hq3, Yp[10], i0))))));   \
+        K[1] = fma(hw0, Yp[4], fma(hw2, Yp[6], fma(-hw1, Yp[7], fma(hq0, Yp[8], fma(hq2, Yp[10], fma(-hq3, Yp[9], i1))))));       \
+        K[2] = fma(hw1, Yp[4], fma(-hw2, Yp[5], fma(hw0, Yp[7], fma(hq0, Yp[9], fma(-hq1, Yp[10], fma(hq3, Yp[8], i2))))));       \
+        K[3] = fma(hw2, Yp[4], fma(hw1, Yp[5], fma(-hw0, Yp[6], fma(hq0, Yp[10], fma(hq1, Yp[9], fma(-hq2, Yp[8], i3))))));
+        QROWS(YA, kA, fma(dsA, fq0, init(FA, 4)), fma(dsA, fq12.x, init(FA, 5)), fma(dsA, fq12.y, init(FA, 6)), fma(dsA, fq3, init(FA, 7)))
+        QROWS(YB, kB, init(FB, 4), init(FB, 5), init(FB, 6), init(FB, 7))
 #undef QROWS
 #pragma unroll
         for (int r = 0; r < 4; ++r) { fin(FA, 4 + r, kA[r]); fin(FB, 4 + r, kB[r]); }
@@ -636,12 +642,12 @@ __device__ __forceinline__ void consume_stage8(FullCol& FA, FullCol& FB, const d
         const double j8 = J[J_WW + 8];
         const double g0 = Gc[4], g1 = Gc[5], g2 = Gc[6];
         double kA[3], kB[3];
-        kA[0] = fma(j01.x, FA.Y[8], fma(j01.y, FA.Y[9], fma(j23.x, FA.Y[10], fma(alA, g0, init(FA, 8)))));
-        kA[1] = fma(j23.y, FA.Y[8], fma(j45.x, FA.Y[9], fma(j45.y, FA.Y[10], fma(alA, g1, init(FA, 9)))));
-        kA[2] = fma(j67.x, FA.Y[8], fma(j67.y, FA.Y[9], fma(j8, FA.Y[10], fma(alA, g2, init(FA, 10)))));
-        kB[0] = fma(j01.x, FB.Y[8], fma(j01.y, FB.Y[9], fma(j23.x, FB.Y[10], init(FB, 8))));
-        kB[1] = fma(j23.y, FB.Y[8], fma(j45.x, FB.Y[9], fma(j45.y, FB.Y[10], init(FB, 9))));
-        kB[2] = fma(j67.x, FB.Y[8], fma(j67.y, FB.Y[9], fma(j8, FB.Y[10], init(FB, 10))));
+        kA[0] = fma(j01.x, YA[8], fma(j01.y, YA[9], fma(j23.x, YA[10], fma(alA, g0, init(FA, 8)))));
+        kA[1] = fma(j23.y, YA[8], fma(j45.x, YA[9], fma(j45.y, YA[10], fma(alA, g1, init(FA, 9)))));
+        kA[2] = fma(j67.x, YA[8], fma(j67.y, YA[9], fma(j8, YA[10], fma(alA, g2, init(FA, 10)))));
+        kB[0] = fma(j01.x, YB[8], fma(j01.y, YB[9], fma(j23.x, YB[10], init(FB, 8))));
+        kB[1] = fma(j23.y, YB[8], fma(j45.x, YB[9], fma(j45.y, YB[10], init(FB, 9))));
+        kB[2] = fma(j67.x, YB[8], fma(j67.y, YB[9], fma(j8, YB[10], init(FB, 10))));
         // all reads of the ring slot are done: hand it back (per-stage hand-over only; the step-synchronised kernel
         // passes a null barrier and releases a whole step at once)
         if (empty_bar != nullptr) {
