@@ -28,6 +28,8 @@ VARIANTS = {
     "no_first_body": ["-DSCVX_T_FIRST_BODY=0"],
     "four_bodies": ["-DSCVX_T_FIRST_BODY=2"],
     "step_unroll2": ["-DSCVX_T_STEP_UNROLL=2"],
+    "split_reduce": ["-DSCVX_T_SPLIT_REDUCE=1"],
+    "prefetch_epilogue": ["-DSCVX_A_PREFETCH_EPILOGUE=1"],
     "mbar_hint": ["-DSCVX_MBAR_HINT=10000000"],
     "mbar_hint_1us": ["-DSCVX_MBAR_HINT=1000"],
     "producer_sleep200": ["-DSCVX_PRODUCER_SLEEP_NS=200"],

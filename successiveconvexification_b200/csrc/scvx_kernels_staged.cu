@@ -42,6 +42,9 @@ namespace {
 // SCVX_A_PARK: the step-start state x and the rk4 accumulator (28 doubles) also live in lane-private shared memory, so
 // that the kernel fits 168 registers and a third block per SM (3 warps per scheduler hide the dependent-issue latency of
 // the serial value chain better than 2).
+#ifndef SCVX_A_PREFETCH_EPILOGUE
+#define SCVX_A_PREFETCH_EPILOGUE 1
+#endif
 #ifndef SCVX_A_SMEM_TABLES
 #define SCVX_A_SMEM_TABLES 0
 #endif
@@ -173,6 +176,17 @@ __global__ void __launch_bounds__(value_threads(TS), value_minblocks(TS)) stage_
     for (int r = 0; r < 14; ++r) PX[r * VT] = x[r];
 #endif
     for (int it = 0; it < bt.npts; ++it) {
+#if SCVX_A_PREFETCH_EPILOGUE
+        // the epilogue reads this node's and the next node's state and controls again (z, lin_err, thrust rows): by then
+        // they have left the caches, and nothing is left to overlap the loads with (6 % of the kernel's stall samples).
+        // One L2 prefetch per line before the last step brings them back in time.
+        if (it == bt.npts - 1) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(xin));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(xin + 14));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(xin + 27));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(uin + 5));
+        }
+#endif
         double y[14];
 #if SCVX_A_PARK
 #pragma unroll
@@ -353,6 +367,10 @@ struct __align__(16) StepSmem {
 // SCVX_T_FIRST_BODY: the first stage of a step runs its own instantiation of consume_stage8 (see there)
 #ifndef SCVX_T_FIRST_BODY
 #define SCVX_T_FIRST_BODY 2
+#endif
+// SCVX_T_SPLIT_REDUCE: halving butterfly for the z partials of the epilogue (see there)
+#ifndef SCVX_T_SPLIT_REDUCE
+#define SCVX_T_SPLIT_REDUCE 1
 #endif
 #ifndef SCVX_T_STEP_UNROLL
 #define SCVX_T_STEP_UNROLL 2
@@ -542,6 +560,37 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
         };
         emit_full(FA, colA, xcA);
         emit_full(FB, colB, xcB);
+#if SCVX_T_SPLIT_REDUCE
+        // Sum of the 14 partials over the 8 lanes of the interval, halving the rows a lane carries in every round (7 + 4 + 2
+        // exchanged values instead of 3 x 14: the epilogue is bound by the shuffle queue).  The pairing is the butterfly
+        // 1, 2, 4 of the plain reduction, so every sum is formed in the same order: bit-identical.  Lane l8 ends up with the
+        // rows 7 b0 + 4 b1 + 2 b2 + {0, 1} (b = the bits of l8; rows past the seventh of a half do not exist).
+        {
+            const bool b0 = l8 & 1, b1 = l8 & 2, b2 = l8 & 4;
+            double a7[7], a4[4], a2[2];
+#pragma unroll
+            for (int r = 0; r < 7; ++r) {
+                const double send = b0 ? zp[r] : zp[7 + r], keep = b0 ? zp[7 + r] : zp[r];
+                a7[r] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double hi = (r < 3) ? a7[4 + r] : 0.0;
+                const double send = b1 ? a7[r] : hi, keep = b1 ? hi : a7[r];
+                a4[r] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const double send = b2 ? a4[r] : a4[2 + r], keep = b2 ? a4[2 + r] : a4[r];
+                a2[r] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            // the z column holds the partial z written by stage_value_kernel; exactly one addend per entry -> deterministic
+            const int half_row = (b1 ? 4 : 0) + (b2 ? 2 : 0);
+            double* o = blk + 14 * 22 + (b0 ? 7 : 0) + half_row;
+            if (live && half_row < 7) atomicAdd(o, -a2[0]);
+            if (live && half_row + 1 < 7) atomicAdd(o + 1, -a2[1]);
+        }
+#else
 #pragma unroll
         for (int r = 0; r < 14; ++r) {
             double v = zp[r];
@@ -556,6 +605,7 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
 #pragma unroll
             for (int r = 0; r < 14; ++r) atomicAdd(o + r, -zp[r]);
         }
+#endif
     }
 }
 
