@@ -30,6 +30,8 @@ VARIANTS = {
     "step_unroll2": ["-DSCVX_T_STEP_UNROLL=2"],
     "split_reduce": ["-DSCVX_T_SPLIT_REDUCE=1"],
     "prefetch_epilogue": ["-DSCVX_A_PREFETCH_EPILOGUE=1"],
+    "vt64": ["-DSCVX_A_VT=64", "-DSCVX_A_MINBLOCKS=4"],
+    "vt256": ["-DSCVX_A_VT=256", "-DSCVX_A_MINBLOCKS=1"],
     "mbar_hint": ["-DSCVX_MBAR_HINT=10000000"],
     "mbar_hint_1us": ["-DSCVX_MBAR_HINT=1000"],
     "producer_sleep200": ["-DSCVX_PRODUCER_SLEEP_NS=200"],

@@ -166,6 +166,12 @@ int launch_linearize(scvx_ctx* c, Dev& d, const ScvxBatch& bt, cudaStream_t s) {
     // keep the stage-record scratch below ~4 GiB for long integrations (npts >> 10): whole tangent passes per SM
     while (chunk > d.sm_count * 32 && scvx_staged_scratch_bytes(bt.npts, chunk) > ((size_t)4 << 30)) chunk -= d.sm_count * 32;
     if (total < chunk) chunk = (int)((total + 31) / 32 * 32);
+    else {
+        // equal chunks instead of full ones and a remainder: whole waves of the value kernel (2 x 128 threads per SM)
+        const long n = (total + chunk - 1) / chunk, wave = (long)d.sm_count * 256;
+        const long per = ((total + n - 1) / n + wave - 1) / wave * wave;
+        if (per < chunk) chunk = (int)per;
+    }
     const size_t need = scvx_staged_scratch_bytes(bt.npts, chunk);
     if (need > d.scratch_cap) {
         CK(cudaDeviceSynchronize());

@@ -61,7 +61,10 @@ namespace {
 //      -6 % / -8 %, profiles/r2_ab_patch_table.txt: neighbouring cells no longer share lines, the copy is 16x the table)
 //   3  a WIN_I x WIN_J WINDOW of both tables around the block's starting (cos aoa, Mach) cells (18 KB per block; two blocks
 //      of 128 threads per SM as in 0), 4 x 4 patches outside the window from global memory: -6.8 % (generic loads, spills).
-__host__ __device__ constexpr int value_threads(int ts) { return (ts == 1) ? 256 : (ts == 2 ? 224 : 128); }
+#ifndef SCVX_A_VT
+#define SCVX_A_VT 128
+#endif
+__host__ __device__ constexpr int value_threads(int ts) { return (ts == 1) ? 256 : (ts == 2 ? 224 : SCVX_A_VT); }
 __host__ __device__ constexpr int value_minblocks(int ts) { return (ts == 1 || ts == 2) ? 1 : SCVX_A_MINBLOCKS; }
 constexpr int VALUE_SMEM_DOUBLES = 24 + (SCVX_A_PARK ? 28 : 0);
 __host__ __device__ constexpr size_t value_smem_bytes(int ts) {
@@ -617,8 +620,13 @@ size_t scvx_staged_scratch_bytes(int npts, int chunk_intervals) {
 }
 
 // chunk = whole waves of both kernels: the value kernel keeps 2 x 128 threads per SM resident (255 registers), the
-// tangent kernel 32 intervals per pass: 768 intervals per SM = 3 waves / 24 passes.
-int scvx_staged_chunk_intervals(int sm_count) { return sm_count * (SCVX_A_SMEM_TABLES == 2 ? 896 : 768); }
+// tangent kernel 32 intervals per pass.  Every chunk costs two kernel boundaries (ramp, tail, launch gap), so chunks are
+// long: 2304 intervals per SM = 9 waves / 72 passes, 3.5 GB of stage records at npts = 10 (768 per SM: -2.0 %, 1536:
+// -0.9 %, 3072: +0.3 %; profiles/r2_ab_chunk.txt).  SCVX_CHUNK_PER_SM overrides (A/B).
+int scvx_staged_chunk_intervals(int sm_count) {
+    static const int per_sm = getenv("SCVX_CHUNK_PER_SM") ? atoi(getenv("SCVX_CHUNK_PER_SM")) : (SCVX_A_SMEM_TABLES == 2 ? 2688 : 2304);
+    return sm_count * (per_sm > 0 ? (per_sm + 31) / 32 * 32 : 2304);
+}
 
 // the table-staging mode a launch uses: the compiled preference if the tables fit beside the light-column state, else 0
 static int value_table_mode(const ScvxTables& tb, bool any_aero) {
