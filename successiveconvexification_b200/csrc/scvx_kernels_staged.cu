@@ -375,6 +375,9 @@ struct __align__(16) StepSmem {
 #ifndef SCVX_T_SPLIT_REDUCE
 #define SCVX_T_SPLIT_REDUCE 1
 #endif
+#ifndef SCVX_T_PREFETCH_PASS
+#define SCVX_T_PREFETCH_PASS 1
+#endif
 #ifndef SCVX_T_STEP_UNROLL
 #define SCVX_T_STEP_UNROLL 2
 #endif
@@ -448,6 +451,17 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
                 const scvx_probinfo& P = SP ? a.Pc : bt.P[bt.n_params == 1 ? 0 : b];
                 const double pa = (SP == 2) ? __ldg(&bt.P[b].a) : ldp<SP>(&P.a);
                 const double sigma = __ldg(bt.sigma + b);
+#if SCVX_T_PREFETCH_PASS
+                if (kq == 0 && it + 1 < my_groups) {
+                    // the next pass starts with these loads on the consumers' critical path (they wait for its first
+                    // records at the pass boundary): have the lines in L2 by then
+                    int t2 = (g + (int)gridDim.x) * GROUP + lane; if (t2 >= a.count) t2 = a.count - 1;
+                    const int b2 = (a.first + t2) / ni, i2 = (a.first + t2) - b2 * ni;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(bt.sigma + b2));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(bt.U + ((size_t)b2 * bt.n_nodes + i2) * 3));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(bt.U + ((size_t)b2 * bt.n_nodes + i2) * 3 + 5));
+                }
+#endif
                 {   // the interval's node controls (the stage control is their FOH blend, re-formed per record)
                     const int ii = (a.first + t) - b * ni;
                     const double* uin = bt.U + ((size_t)b * bt.n_nodes + ii) * 3;
@@ -518,7 +532,7 @@ __global__ void __launch_bounds__(TANGENT_THREADS, 1) tangent_kernel(const __gri
         for (int ls = 0; ls < npts; ++ls, ++n) {
             // ---- consume the four stages of step n
             const int half = n & 1;
-            mbar_wait(&sm.full_step[half], (uint32_t)((n >> 1) & 1));
+            mbar_wait(&sm.full_step[half], (uint32_t)((n >> 1) & 1));      // (backing off here changes nothing: r2_ab_consumer_sleep.txt)
             const double* J0 = &sm.ring[half * 4][warp * 4 + sub][0];
 #if SCVX_T_FIRST_BODY
             consume_stage8<0>(FA, FB, J0, gcol, fma(cA1, pca, cA0), dsA, 1.0, h6, kappa, nullptr, lane);
