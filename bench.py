@@ -516,7 +516,12 @@ def main():
     achieved_gbs = BYTES_PER_INTERVAL * (B * ni) / (kern_ms * 1e-3) * 1e-9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+        # DRAM bytes of one tangent_kernel launch of THIS run: the per-interval figure of the ncu capture x the intervals
+        # an average launch of the timed region covers (the library splits a step into equal chunks)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        per_interval = tj.get("dram_bytes_per_interval") or tj["dram_bytes_per_launch"] / tj["intervals_per_launch"]
+        chunks_per_step = max(1, int(launches) // max(1, args.steps) // 2)
+        traffic = per_interval * (B * ni) / chunks_per_step
     except Exception:
         pass
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",

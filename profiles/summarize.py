@@ -30,12 +30,17 @@ for k in kernels:
     rr = list(csv.reader(out.splitlines())); h, u, v = rr[0], rr[1], rr[2]
     def get(name):
         i = h.index(name); return float(v[i].replace(",", "")) * mult.get(u[i], 1)
+    tu = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}[u[h.index("gpu__time_duration.sum")]]
     traffic[k] = {"dram_read": get("dram__bytes_read.sum"), "dram_write": get("dram__bytes_write.sum"),
-                  "duration_us": get("gpu__time_duration.sum") / (1e3 if u[h.index("gpu__time_duration.sum")] == "ns" else 1)}
+                  "duration_us": float(v[h.index("gpu__time_duration.sum")].replace(",", "")) * tu,
+                  "grid": int(float(v[h.index("launch__grid_size")].replace(",", "")))}
 t = traffic["tangent_kernel"]
+# the captured launches are the same chunk of the same step (-s 4 -c 1 of either kernel): its intervals = value-kernel grid x 128
+n_int = traffic["stage_value_kernel"]["grid"] * 128
 json.dump({"kernel": "tangent_kernel", "dram_bytes_per_launch": t["dram_read"] + t["dram_write"], "dram_read": t["dram_read"],
-           "dram_write": t["dram_write"], "intervals_per_launch": 113664, "per_kernel": traffic, "device_time_shares": shares,
-           "note": f"one full chunk (148 SMs x 768 intervals); ncu --set full, see {R}_tangent_kernel.txt; shares from "
+           "dram_write": t["dram_write"], "intervals_per_launch": n_int,
+           "dram_bytes_per_interval": (t["dram_read"] + t["dram_write"]) / n_int, "per_kernel": traffic, "device_time_shares": shares,
+           "note": f"one chunk of the capture run ({n_int} intervals); ncu --set full, see {R}_tangent_kernel.txt; shares from "
                    f"{R}_launches.csv (cold-cache, serialised launches: compare shares, not absolutes)"},
           open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print(json.dumps(shares, indent=1))
