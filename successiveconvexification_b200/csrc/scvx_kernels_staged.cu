@@ -348,7 +348,10 @@ __global__ void __launch_bounds__(value_threads(TS), value_minblocks(TS)) stage_
 //     warp per scheduler fills the issue slots their FP64 dependency chains leave empty;
 //   * hand-over once per rk4 STEP through a shared-memory ring two steps deep (2 x 4 stage slabs): consumers wait ONE
 //     "full" barrier per step and release the four slabs with ONE "empty" arrive per step (a per-stage hand-over cost
-//     17 % of the kernel in barrier waits and loop drain); producers run as far ahead as the ring allows.
+//     17 % of the kernel in barrier waits and loop drain); producers run as far ahead as the ring allows and back off
+//     between polls of a free ring slot (mbar_wait_relaxed: a polling producer took issue slots from the consumers);
+//   * the four stages of a step are four instantiations of consume_stage8 (first / middle / middle / last), the step
+//     loop is unrolled by two.
 // (Until the producers got their own warps the consumer warps took turns producing, inlined at step boundaries where
 //  only S is live; the consumers then spent 18 % of their issue slots on it: 9.8e7 -> 1.02e8 intervals/s.)
 // ------------------------------------------------------------------------------------------------
@@ -367,7 +370,9 @@ struct __align__(16) StepSmem {
     uint64_t recfull[2][4];                  // [half][stage]: one waiting warp per barrier (it observes every phase)
 };
 
-// SCVX_T_FIRST_BODY: the first stage of a step runs its own instantiation of consume_stage8 (see there)
+// Compile-time switches of the tangent kernel (A/B builds: profiles/build_variants.py; defaults = the measured best).
+// SCVX_T_FIRST_BODY: 0 = one body for the first three stages of a step, 1 = own body for the first stage (see
+// consume_stage8), 2 = and the two middle stages unrolled
 #ifndef SCVX_T_FIRST_BODY
 #define SCVX_T_FIRST_BODY 2
 #endif
@@ -375,12 +380,15 @@ struct __align__(16) StepSmem {
 #ifndef SCVX_T_SPLIT_REDUCE
 #define SCVX_T_SPLIT_REDUCE 1
 #endif
+// SCVX_T_PREFETCH_PASS: a producer warp pulls the next pass's sigma / control lines into L2
 #ifndef SCVX_T_PREFETCH_PASS
 #define SCVX_T_PREFETCH_PASS 1
 #endif
+// SCVX_T_STEP_UNROLL: 2 = the consumers' step loop unrolled by two
 #ifndef SCVX_T_STEP_UNROLL
 #define SCVX_T_STEP_UNROLL 2
 #endif
+// SCVX_RECORD_SLEEP_NS: back-off of the producers' wait for their TMA'd record (0 = spin; no measurable effect)
 #ifndef SCVX_RECORD_SLEEP_NS
 #define SCVX_RECORD_SLEEP_NS 0
 #endif

@@ -544,8 +544,8 @@ struct FullCol {
 };
 
 
-// One rk4 stage of TWO full tangent columns (8-lane variant).  LAST = final stage of the step (compile time, so
-// there is no control flow inside the stage; two instantiations keep the hot loop inside the instruction cache).
+// One rk4 stage of TWO full tangent columns (8-lane variant).  The position of the stage in its step is a compile-time
+// parameter (KIND below), so there is no control flow inside the stage; the caller unrolls the four stages of a step.
 // Rows are processed in cascade order (r, v, m, q, w): a row block is overwritten only after every block that
 // reads its old stage value has been formed.
 //
