@@ -62,6 +62,12 @@ template <int SP> __device__ __forceinline__ int ldpi(const int32_t* p) {
 // ------------------------------------------------------------------------------------------------
 // spline value and gradient w.r.t. the physical coordinates (gradient 0 when strictly outside: Flat extrapolation);
 // one pass over the 16 coefficients serves all three.
+#ifndef SCVX_A_BRANCHLESS_LIFT
+#define SCVX_A_BRANCHLESS_LIFT 1
+#endif
+#if SCVX_A_BRANCHLESS_LIFT && !SCVX_A_LEAN_LIFT
+#error "SCVX_A_BRANCHLESS_LIFT needs SCVX_A_LEAN_LIFT"
+#endif
 #ifndef SCVX_A_HOIST_LIFT
 #define SCVX_A_HOIST_LIFT 0
 #endif
@@ -176,7 +182,13 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
             Fb[r][c] = vh[r] * db[c];
         }
     }
+#if SCVX_A_BRANCHLESS_LIFT
+    // no branch: the lift terms are always formed and selected at the end, so that the whole stage is one basic block and
+    // the scheduler can overlap the lift loads and chains with the rest of the stage (A/B: profiles/r2_ab_branchless_lift.txt)
+    const bool take = !(fabs(dp) >= 0.95);
+#else
     if (fabs(dp) >= 0.95) return;
+#endif
     // (the lift coefficients are read behind this branch with nothing left to overlap their latency: 18 % of the kernel's
     // stall samples.  prefetch.global.L1 of their four rows before the drag evaluation: -6 % LITERAL, -37 % TEXTBOOK,
     // profiles/r2_ab_prefetch_lift.txt)
@@ -200,8 +212,13 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
     // The projections are formed from two scalars instead of from the 3 x 3 matrices:
     //   lh^T Lv = (v.b) lh^T + (lh.v) b^T - 2 (lh.b) v^T ,   lh^T Lb = (lh.v) v^T - (v.v) lh^T
     const double ln = lift * inl;
+#if SCVX_A_BRANCHLESS_LIFT
+#pragma unroll
+    for (int r = 0; r < 3; ++r) F[r] = take ? fma(ln, l[r], F[r]) : F[r];
+#else
 #pragma unroll
     for (int r = 0; r < 3; ++r) F[r] = fma(ln, l[r], F[r]);
+#endif
     const double lhv = lh[0] * v[0] + lh[1] * v[1] + lh[2] * v[2];
     const double lhb = lh[0] * b[0] + lh[1] * b[1] + lh[2] * b[2];
     double pjv[3], pjb[3], lnv[3], lnb2[3];
@@ -219,8 +236,15 @@ __device__ __forceinline__ void aero_force_jac(const scvx_probinfo& P, const Scv
     for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
+#if SCVX_A_BRANCHLESS_LIFT
+            const double nv_ = Fv[r][c] + fma(lh[r], pjv[c], fma(lnv[r], b[c], fma(lnb2[r], v[c], r == c ? dgv : 0.0)));
+            const double nb_ = Fb[r][c] + fma(lh[r], pjb[c], fma(lnv[r], v[c], r == c ? dgb : 0.0));
+            Fv[r][c] = take ? nv_ : Fv[r][c];
+            Fb[r][c] = take ? nb_ : Fb[r][c];
+#else
             Fv[r][c] += fma(lh[r], pjv[c], fma(lnv[r], b[c], fma(lnb2[r], v[c], r == c ? dgv : 0.0)));
             Fb[r][c] += fma(lh[r], pjb[c], fma(lnv[r], v[c], r == c ? dgb : 0.0));
+#endif
         }
 #else
     // dl/dv = (v.b) I + v b^T - 2 b v^T ;  dl/db = v v^T - (v.v) I
