@@ -34,6 +34,8 @@ VARIANTS = {
     "vt256": ["-DSCVX_A_VT=256", "-DSCVX_A_MINBLOCKS=1"],
     "prefetch_pass": ["-DSCVX_T_PREFETCH_PASS=1"],
     "branchless_lift": ["-DSCVX_A_BRANCHLESS_LIFT=1"],
+    "stage_unroll2": ["-DSCVX_A_STAGE_UNROLL=2"],
+    "stage_unroll4": ["-DSCVX_A_STAGE_UNROLL=4"],
     "mbar_hint": ["-DSCVX_MBAR_HINT=10000000"],
     "mbar_hint_1us": ["-DSCVX_MBAR_HINT=1000"],
     "producer_sleep200": ["-DSCVX_PRODUCER_SLEEP_NS=200"],

@@ -42,6 +42,10 @@ namespace {
 // SCVX_A_PARK: the step-start state x and the rk4 accumulator (28 doubles) also live in lane-private shared memory, so
 // that the kernel fits 168 registers and a third block per SM (3 warps per scheduler hide the dependent-issue latency of
 // the serial value chain better than 2).
+// SCVX_A_STAGE_UNROLL: unrolling of the four-stage loop of the value kernel (1 = none)
+#ifndef SCVX_A_STAGE_UNROLL
+#define SCVX_A_STAGE_UNROLL 1
+#endif
 #ifndef SCVX_A_PREFETCH_EPILOGUE
 #define SCVX_A_PREFETCH_EPILOGUE 1
 #endif
@@ -199,7 +203,13 @@ __global__ void __launch_bounds__(value_threads(TS), value_minblocks(TS)) stage_
 #pragma unroll
         for (int r = 0; r < 14; ++r) { y[r] = x[r]; acc[r] = 0.0; }
 #endif
+#if SCVX_A_STAGE_UNROLL == 4
+#pragma unroll
+#elif SCVX_A_STAGE_UNROLL == 2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
         for (int st = 0; st < 4; ++st) {
             const double pc = (st == 0) ? pca : (st == 3 ? pca + pcs : pca + 0.5 * pcs);
             double uc[3], f[14], Fv[3][3], Fb[3][3];
